@@ -1,0 +1,265 @@
+// Host-side state of one lumol_cuda_context: device buffers, interaction tables, launch bookkeeping.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "device_math.cuh"
+
+namespace lumol {
+
+// Growable device buffer.
+template <typename T>
+struct DeviceBuffer {
+    T* ptr = nullptr;
+    size_t capacity = 0;
+
+    cudaError_t reserve(size_t count) {
+        if (count <= capacity) {
+            return cudaSuccess;
+        }
+        if (ptr != nullptr) {
+            cudaFree(ptr);
+            ptr = nullptr;
+            capacity = 0;
+        }
+        size_t want = count + count / 8 + 32;
+        cudaError_t err = cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T));
+        if (err == cudaSuccess) {
+            capacity = want;
+        }
+        return err;
+    }
+
+    void release() {
+        if (ptr != nullptr) {
+            cudaFree(ptr);
+        }
+        ptr = nullptr;
+        capacity = 0;
+    }
+};
+
+// Result slots written by the reduction kernels (device `results` array).
+enum ResultSlot {
+    RES_E_PAIRS = 0,
+    RES_E_COULOMB_REAL = 1,
+    RES_W_PAIRS = 2,          // 6 values: xx xy xz yy yz zz
+    RES_W_COULOMB_REAL = 8,   // 6
+    RES_E_BONDS = 14,
+    RES_W_BONDS = 15,         // 6, directly after RES_E_BONDS (one 7-value reduction)
+    RES_E_ANGLES = 21,
+    RES_E_DIHEDRALS = 22,
+    RES_E_KSPACE = 23,
+    RES_W_KSPACE = 24,        // 6
+    RES_CHARGE2 = 30,         // sum q^2 (Ewald self) or sum over charged atoms of q^2 (Wolf self)
+    RES_KINETIC = 31,
+    RES_KINETIC_TENSOR = 32,  // 6
+    RES_MOMENTUM = 38,        // sum m v (3) and sum m (1)
+    RES_MOLECULAR_BLOCK = 42,      // same 14-value layout as slots 0..13, from the molecular-virial kernel
+    RES_W_MOLECULAR_PAIRS = 44,    // 6
+    RES_W_MOLECULAR_COULOMB = 50,  // 6
+    RES_W_KSPACE_CORRECTION = 56,  // 9: sum_mol sum_i f_i (x) (x_i - com), ewald.rs:736-753
+    RES_SCALE_FACTOR = 65,         // thermostat factor computed on the device
+    RES_FLAGS = 66,                // non-finite detector
+    RES_COUNT = 68
+};
+
+struct Timer {
+    cudaEvent_t start = nullptr, stop = nullptr;
+};
+
+struct KernelClock {
+    int64_t launches = 0;
+    double ms = 0.0;
+};
+
+struct Comm;  // comm.cu
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int sm_count = 148;
+
+    // ---- particles -------------------------------------------------------------------------
+    int64_t n = 0;
+    DeviceBuffer<double> position, velocity, force, mass, charge;
+    DeviceBuffer<double> aux;  // Verlet: previous positions; LeapFrog: accelerations
+    DeviceBuffer<unsigned> kind;
+    DeviceBuffer<int> mol_first;  // first atom of the molecule holding atom i
+    DeviceBuffer<int> bd_row;     // byte offset of atom i's row in bond_dist
+    DeviceBuffer<int> mol_of;     // molecule index of atom i
+    DeviceBuffer<unsigned char> bond_dist;
+    DeviceBuffer<int> mol_start;  // nmol + 1
+    DeviceBuffer<double> mol_com; // nmol x 3
+    int64_t nmol = 0;
+    int max_mol_size = 1;
+    bool has_molecules = false;
+
+    // ---- cell ------------------------------------------------------------------------------
+    CellView cell{};
+    bool cell_set = false;
+    uint64_t cell_generation = 0;
+
+    // ---- interactions ----------------------------------------------------------------------
+    int nkinds = 0;
+    std::vector<lumol_cuda_pair> host_pairs;
+    DeviceBuffer<PairParams> pairs;
+    double max_pair_cutoff = 0.0;
+    bool any_pair = false;
+    bool single_lj = false;  // every present pair is plain LJ with restriction None: fast path
+    std::vector<TableDesc> host_tables;
+    std::vector<double> host_table_energy, host_table_force;
+    DeviceBuffer<TableDesc> tables;
+    DeviceBuffer<double> table_energy, table_force;
+    bool tables_dirty = false;
+
+    std::vector<lumol_cuda_potential> host_bonded;
+    DeviceBuffer<lumol_cuda_potential> bonded;
+    int64_t nbonds = 0, nangles = 0, ndihedrals = 0;
+    DeviceBuffer<int> bonds, angles, dihedrals;  // index tuples followed by the potential id
+    CoulombView coulomb{};
+    int kmax = 0;
+
+    // ---- Ewald k-space -----------------------------------------------------------------------
+    uint64_t ewald_generation = ~0ull;  // cell generation the factor table was built for
+    int64_t nk = 0;
+    double kmax2 = 0.0;
+    std::vector<int> host_kindex;
+    std::vector<double> host_kenergy;
+    DeviceBuffer<short4> kindex;
+    DeviceBuffer<double> kenergy;  // EwaldFactor::energy
+    DeviceBuffer<double> kvirial;  // 6 per k
+    DeviceBuffer<double2> rho, rho_partial;
+    double kbasis[9] = {0};  // k_vector of the three unit indices, one per row
+
+    // ---- neighbour search ----------------------------------------------------------------------
+    int forced_path = -1;
+    int path = 0;
+    int ncell[3] = {0, 0, 0};
+    DeviceBuffer<int> cell_of, cell_count, cell_start, order;
+    DeviceBuffer<double4> sorted_pos;  // x, y, z (wrapped), charge
+    DeviceBuffer<int4> sorted_info;    // kind, mol_first, bd_row, original index
+    DeviceBuffer<int> scan_scratch;
+
+    // ---- reductions ------------------------------------------------------------------------------
+    DeviceBuffer<double> partials, reduce_scratch;
+    DeviceBuffer<double> results;
+    double* host_results = nullptr;  // pinned, RES_COUNT doubles
+
+    // ---- molecular dynamics --------------------------------------------------------------------------
+    int integrator = -1;
+    double dt = 0.0;
+    int thermostat = 0;
+    double thermostat_temperature = 0.0, thermostat_parameter = 0.0;
+    std::vector<double> csvr_noise;
+    DeviceBuffer<double> csvr_noise_dev;
+    int64_t csvr_cursor = 0, csvr_count = 0;
+    unsigned controls = 0;
+    int dof_mode = 0;
+    int64_t dof_frozen = 0;
+    int64_t md_step = 0;
+
+    // ---- multi-GPU -------------------------------------------------------------------------------------
+    Comm* comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // ---- measurement -----------------------------------------------------------------------------------
+    bool profiling = false;
+    Timer timer;
+    int64_t launches = 0;
+    KernelClock clk_pair, clk_kspace, clk_integrate, clk_neighbor, clk_comm;
+
+    int fail(int code, const char* fmt, ...) {
+        char buffer[512];
+        va_list args;
+        va_start(args, fmt);
+        vsnprintf(buffer, sizeof(buffer), fmt, args);
+        va_end(args);
+        error = buffer;
+        return code;
+    }
+
+    // atoms [lo, hi) owned by this rank (contiguous block; in cell-sorted order on the cell path)
+    void owned_range(int64_t total, int64_t& lo, int64_t& hi) const {
+        int64_t chunk = (total + nranks - 1) / nranks;
+        lo = chunk * rank;
+        hi = lo + chunk;
+        if (lo > total) lo = total;
+        if (hi > total) hi = total;
+    }
+};
+
+#define LUMOL_CUDA_CHECK(ctx, expr)                                                                        \
+    do {                                                                                                   \
+        cudaError_t err__ = (expr);                                                                        \
+        if (err__ != cudaSuccess) {                                                                        \
+            return (ctx)->fail(LUMOL_CUDA_ERROR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                               __FILE__, __LINE__);                                                        \
+        }                                                                                                  \
+    } while (0)
+
+// Scoped event timing of one kernel class on the context stream (only when profiling is enabled).
+struct ScopedClock {
+    Context* ctx;
+    KernelClock* clock;
+    ScopedClock(Context* c, KernelClock* k) : ctx(c), clock(k) {
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->timer.start, ctx->stream);
+        }
+    }
+    ~ScopedClock() {
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->timer.stop, ctx->stream);
+            cudaEventSynchronize(ctx->timer.stop);
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ctx->timer.start, ctx->timer.stop);
+            clock->ms += ms;
+        }
+    }
+};
+
+// ---- launchers implemented in the .cu files ---------------------------------------------------------
+struct ComputeRequest {
+    bool forces = false;
+    bool energy = false;
+    bool virial = false;            // atomic
+    bool molecular_virial = false;
+    bool pairs = false;
+    bool bonded = false;
+    bool coulomb = false;
+};
+
+int launch_reduce(Context* ctx, int nblocks, int nvalues, int first_slot);                       // reduce.cu
+int launch_pairs_allpairs(Context* ctx, const ComputeRequest& req);                              // pairs_allpairs.cu
+int launch_pairs_cells(Context* ctx, const ComputeRequest& req);                                 // pairs_cells.cu
+int choose_neighbor_path(Context* ctx, double cutoff);                                           // pairs_cells.cu
+int launch_coulomb_self(Context* ctx);                                                           // pairs_allpairs.cu
+int launch_molecule_com(Context* ctx);                                                           // pairs_allpairs.cu
+int launch_bonded(Context* ctx, const ComputeRequest& req);                                      // bonded.cu
+int ewald_prepare(Context* ctx);                                                                 // ewald.cu
+int launch_ewald_kspace(Context* ctx, const ComputeRequest& req);                                // ewald.cu
+int launch_kinetic(Context* ctx, bool tensor);                                                   // integrate.cu
+int md_setup(Context* ctx);                                                                      // integrate.cu
+int md_step(Context* ctx);                                                                       // integrate.cu
+int launch_scale_velocities(Context* ctx, double factor, bool from_device);                      // integrate.cu
+int launch_remove_translation(Context* ctx);                                                     // integrate.cu
+int evaluate_forces_device(Context* ctx, const ComputeRequest& req);                             // api.cu
+int comm_allgather_positions(Context* ctx);                                                      // comm.cu
+int comm_allreduce(Context* ctx, double* data, int64_t count);                                   // comm.cu
+int comm_allgather_blocks(Context* ctx, double* data, int64_t total);                            // comm.cu
+void comm_destroy(Context* ctx);                                                                 // comm.cu
+int measure_fp64_peak(Context* ctx, double* tflops);                                             // peaks.cu
+int measure_copy_bandwidth(Context* ctx, double* gbs);                                           // peaks.cu
+
+}  // namespace lumol
+
+// The opaque handle of include/lumol_cuda.h.
+struct lumol_cuda_context {
+    lumol::Context impl;
+};
