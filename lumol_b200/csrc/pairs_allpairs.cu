@@ -34,6 +34,7 @@ struct AllPairsArgs {
     CoulombView coulomb;
     int do_pairs;
     int do_coulomb;
+    int write_forces;  // energy-only queries must not clobber the forces the integrator holds
     double* __restrict__ force;
     double* __restrict__ partials;
 };
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(ALLPAIRS_THREADS) allpairs_kernel(AllPairsArgs
             }
         }
 
-        if (MODE != MODE_MOLECULAR) {
+        if (MODE != MODE_MOLECULAR && a.write_forces) {
             fx = warp_sum(fx);
             fy = warp_sum(fy);
             fz = warp_sum(fz);
@@ -338,6 +339,7 @@ int launch_pairs_allpairs(Context* ctx, const ComputeRequest& req) {
     a.do_pairs = req.pairs && ctx->any_pair;
     a.do_coulomb = req.coulomb && ctx->coulomb.kind != 0;
     a.force = ctx->force.ptr;
+    a.write_forces = req.forces;
 
     const int blocks = owned > 0 ? (owned + ALLPAIRS_WARPS - 1) / ALLPAIRS_WARPS : 0;
     const size_t smem = sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds + 32 * ALLPAIRS_NV * sizeof(double);

@@ -288,6 +288,7 @@ struct CellArgs {
     float cutoff2_f32;  // the same, enlarged by 1e-4 relative for the FP32 pre-filter
     // LJ fast path
     double lj_sigma2, lj_epsilon, lj_cutoff2, lj_shift;
+    int write_forces;            // energy-only queries must not clobber the forces the integrator holds
     double* __restrict__ force;  // original order, n x 3
     double* __restrict__ partials;
 };
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(CellArgs a) {
         __syncthreads();
         for (int t = threadIdx.x; t < ni; t += blockDim.x) {
             const int orig = a.sorted_info[ic + t].w;
-            if (orig < a.o_lo || orig >= a.o_hi) continue;
+            if (orig < a.o_lo || orig >= a.o_hi || !a.write_forces) continue;
             a.force[3 * orig] = sh_force[3 * t];
             a.force[3 * orig + 1] = sh_force[3 * t + 1];
             a.force[3 * orig + 2] = sh_force[3 * t + 2];
@@ -602,6 +603,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.cutoff2 = cutoff * cutoff;
     a.cutoff2_f32 = (float)(cutoff * cutoff * 1.0001);
     a.force = ctx->force.ptr;
+    a.write_forces = req.forces;
 
     const bool lj_only = do_pairs && !do_coulomb && ctx->single_lj;
     if (lj_only) {
