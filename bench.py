@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the force-evaluation hot path: atom-steps/s and ns/day of NVE velocity-Verlet MD.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lj|spce] [--atoms-side S] [--impl reference]
+
+One JSON line on stdout (rank 0).  ``value`` is the whole-job throughput of K device-resident MD steps
+(positions, velocities, forces never leave HBM); ``e2e`` is the same force evaluation driven the way lumol's
+host-side integrator would drive it through the C ABI: every step uploads the positions from pinned host
+memory and downloads the forces.  ``roofline`` describes the dominant kernel (the pair kernel), timed live
+with CUDA events on the library's stream in a separate profiled pass; ``cpu_baseline`` is the CPU oracle
+(a restatement of lumol's O(N^2) rayon loop, OpenMP on every host core) on a bounded sample of the same
+workload.  ``--impl reference`` prints that CPU arm alone.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "atom-steps/sec (LJ argon NVE velocity-Verlet MD, FP64)"
+UNIT = "atom-steps/s"
+TIMESTEP_FS = 1.0
+# algorithmic work per unit (restated in DESIGN.md)
+FLOP_PER_LJ_PAIR_FORCE = 36.0
+FLOP_PER_COULOMB_PAIR = 75.0
+FLOP_PER_ATOM_K_RHO = 16.0
+FLOP_PER_ATOM_K_FORCE = 21.0
+BYTES_PER_ATOM_VV = 208.0
+BYTES_PER_ATOM_SORT = 100.0
+
+
+def parse_args():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=200)
+    parser.add_argument("--warmup", type=int, default=20)
+    parser.add_argument("--impl", default="native", choices=["native", "reference"])
+    parser.add_argument("--workload", default="lj", choices=["lj", "spce"])
+    parser.add_argument("--lattice", default="128x128x64", help="lattice points per axis (lj) or molecules per axis (spce)")
+    parser.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-e2e", action="store_true")
+    return parser.parse_args()
+
+
+def lattice_of(text):
+    parts = [int(p) for p in text.lower().split("x")]
+    if len(parts) == 1:
+        parts = parts * 3
+    return tuple(parts)
+
+
+def build_workload(args):
+    """The synthetic boxes of SURVEY section 8d, through the host-side API."""
+    from lumol_b200 import synthetic
+    import lumol_b200 as lumol
+
+    lattice = lattice_of(args.lattice)
+    if args.workload == "lj":
+        system = synthetic.lj_box(lattice, seed=20240 + 20)
+        synthetic.maxwell_boltzmann(system, 120.0, seed=7)
+        description = {
+            "workload": f"synthetic LJ argon box, {system.size()} atoms, lattice {args.lattice}, rho=0.0213/A^3, "
+                        "sigma=3.4 A, eps=1 kJ/mol, rc=10 A, tail corrections, NVE velocity-Verlet dt=1 fs, 120 K",
+            "atoms": system.size(),
+            "cell_A": [round(float(v), 3) for v in system.cell.lengths()],
+        }
+    else:
+        if len(set(lattice)) != 1:
+            raise SystemExit("--workload spce needs a cubic lattice")
+        system = synthetic.spce_box(lattice[0], flexible=True)
+        ewald = lumol.Ewald.with_accuracy(9.0, 1e-5, system)
+        shared = lumol.SharedEwald(ewald)
+        shared.set_restriction(lumol.PairRestriction.InterMolecular)
+        system.set_coulomb_potential(shared)
+        synthetic.maxwell_boltzmann(system, 300.0, seed=7)
+        description = {
+            "workload": f"synthetic flexible SPC/E water box, {system.size()} atoms, {lattice[0]}^3 molecules, "
+                        f"O-O LJ rc=9 A + Ewald rc=9 A alpha={ewald.alpha:.4f} kmax={ewald.kmax} (with_accuracy 1e-5), "
+                        "inter-molecular, harmonic bonds/angles, NVE velocity-Verlet dt=1 fs, 300 K",
+            "atoms": system.size(),
+            "cell_A": [round(float(v), 3) for v in system.cell.lengths()],
+            "ewald": {"alpha": ewald.alpha, "kmax": ewald.kmax},
+        }
+    return system, description
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.process = None
+
+    def start(self):
+        try:
+            self.process = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=self.file, stderr=subprocess.DEVNULL,
+            )
+        except OSError:
+            self.process = None
+
+    def stop(self):
+        if self.process is not None:
+            self.process.terminate()
+            try:
+                self.process.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.process.kill()
+        self.file.flush()
+        self.file.seek(0)
+        clocks, max_clock, reasons = [], None, set()
+        for line in self.file.read().splitlines():
+            fields = [f.strip() for f in line.split(",")]
+            if len(fields) < 9:
+                continue
+            try:
+                clocks.append(float(fields[1]))
+                max_clock = float(fields[2])
+            except ValueError:
+                continue
+            for name, value in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), fields[5:9]):
+                if value.lower().startswith("active"):
+                    reasons.add(name)
+        self.file.close()
+        os.unlink(self.file.name)
+        if not clocks:
+            return {"sm_mhz": None, "sm_max_mhz": max_clock, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(clocks)), "sm_max_mhz": max_clock, "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+# ---- CPU arm -------------------------------------------------------------------------------------------------
+
+def cpu_sample_rows(system, target_seconds):
+    """Time the oracle (restatement of lumol's pair-force loop, sys/compute.rs:37-55) on uniformly spaced rows i of
+    the O(N^2) loop; returns (rows per second, rows, seconds, threads).  Test infrastructure used as the baseline."""
+    from oracle import oracle
+
+    reference = oracle.OracleSystem(system)
+    lib = reference.lib
+    threads = os.cpu_count() or 1
+    lib.orc_set_threads(threads)
+    n = system.size()
+    checksum = ctypes.c_double()
+
+    def run(count):
+        rows = np.ascontiguousarray(np.linspace(0, n - 1, count).astype(np.int64))
+        start = time.perf_counter()
+        lib.orc_pair_forces_sample(reference.ref, len(rows), oracle.iptr(rows), ctypes.byref(checksum))
+        return time.perf_counter() - start
+
+    probe_rows = max(threads * 2, 16)
+    probe = run(probe_rows)
+    rows = int(min(n, max(probe_rows, probe_rows * target_seconds / max(probe, 1e-6))))
+    rows = max(threads, rows // threads * threads)
+    seconds = run(rows)
+    return rows / seconds, rows, seconds, threads
+
+
+def run_reference(args):
+    """``--impl reference``: the CPU path alone, same metric and config, K bounded samples after W warm-ups."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    system, description = build_workload(args)
+    if args.workload != "lj":
+        description["note"] = "CPU arm times the pair-force loop only"
+    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1)))
+    values, rows, threads = [], 0, 1
+    for step in range(args.warmup + args.steps):
+        rate, rows, seconds, threads = cpu_sample_rows(system, per_step)
+        if step >= args.warmup:
+            values.append(rate)
+    value = float(np.mean(values)) if values else 0.0
+    n = system.size()
+    sample = f"pair-force rows of {rows} of {n} atoms (uniform stride), all j > i, O(N^2) loop of sys/compute.rs:37-55"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n / value if value else None, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": description,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ns_per_day": value / n * TIMESTEP_FS * 86400.0 * 1e-6 if value else None,
+    }))
+
+
+# ---- GPU arm ---------------------------------------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from lumol_b200 import _ffi, md
+    from lumol_b200.device import device_for
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lumol_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    system, description = build_workload(args)
+    system.device_ordinal = local_rank
+    n = system.size()
+    device = device_for(system, velocities=True)
+    lib, ctx = device.lib, device.ctx
+
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buffer = (ctypes.c_uint8 * 128)()
+            _ffi.check(None, lib.lumol_cuda_comm_unique_id(buffer))
+            uid = torch.tensor(list(buffer), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        buffer = (ctypes.c_uint8 * 128)(*uid.cpu().tolist())
+        _ffi.check(ctx, lib.lumol_cuda_comm_init(ctx, world, rank, buffer))
+
+    stream = torch.cuda.ExternalStream(lib.lumol_cuda_stream(ctx))
+
+    def barrier():
+        lib.lumol_cuda_synchronize(ctx)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(milliseconds):
+        if world == 1:
+            return milliseconds
+        value = torch.tensor([milliseconds], dtype=torch.float64, device="cuda")
+        dist.all_reduce(value, op=dist.ReduceOp.MAX)
+        return float(value.item())
+
+    propagator = md.MolecularDynamics(TIMESTEP_FS)
+    propagator.setup(system)
+
+    # ---- device-resident MD: warm-up, then exactly K timed steps --------------------------------------------
+    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, args.warmup))
+    barrier()
+    _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(stream)
+    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, args.steps))
+    stop.record(stream)
+    barrier()
+    elapsed_ms = max_over_ranks(start.elapsed_time(stop))
+    clocks = sampler.stop() if rank == 0 else None
+    stats = device.stats()
+    launches = int(stats.kernel_launches)
+    value = n * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_positions = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        host_forces = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+        positions = np.zeros((n, 3))
+        _ffi.check(ctx, lib.lumol_cuda_get_positions(ctx, _ffi.as_double_pointer(positions)))
+        host_positions.copy_(torch.from_numpy(positions))
+        p_in = ctypes.cast(host_positions.data_ptr(), ctypes.POINTER(ctypes.c_double))
+        p_out = ctypes.cast(host_forces.data_ptr(), ctypes.POINTER(ctypes.c_double))
+        e2e_steps = max(3, min(args.steps, 50))
+
+        def e2e_step():
+            # what lumol's VelocityVerlet::integrate does around system.forces() (integrators.rs:44-69) when the
+            # host arrays are the truth: positions in, forces out
+            _ffi.check(ctx, lib.lumol_cuda_set_positions(ctx, p_in))
+            _ffi.check(ctx, lib.lumol_cuda_compute(ctx, _ffi.FORCES, _ffi.PART_ALL, p_out, None, None))
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        start.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        stop.record(stream)
+        barrier()
+        e2e_ms = max_over_ranks(start.elapsed_time(stop))
+        e2e = {
+            "value": n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
+            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+            "call": "lumol_cuda_set_positions + lumol_cuda_compute(FORCES) with pinned host buffers, per rank",
+        }
+        # restore the device-resident state of the MD run
+        _ffi.check(ctx, lib.lumol_cuda_set_positions(ctx, _ffi.as_double_pointer(positions)))
+
+    # ---- roofline of the dominant kernels: separate profiled pass (events around each kernel class) -------------
+    energy = _ffi.Energy()
+    _ffi.check(ctx, lib.lumol_cuda_compute(ctx, _ffi.ENERGY, _ffi.PART_ALL, None, ctypes.byref(energy), None))
+    counts = device.stats()
+    pair_count, coulomb_pairs, nk = counts.pair_count, counts.coulomb_pair_count, int(counts.nkvectors)
+    fp64_peak = ctypes.c_double()
+    _ffi.check(ctx, lib.lumol_cuda_measure_fp64_peak(ctx, ctypes.byref(fp64_peak)))
+    profile_steps = max(3, min(args.steps, 20))
+    propagator.setup(system)
+    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, 2))
+    _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
+    _ffi.check(ctx, lib.lumol_cuda_set_profiling(ctx, 1))
+    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, profile_steps))
+    _ffi.check(ctx, lib.lumol_cuda_set_profiling(ctx, 0))
+    profile = device.stats()
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fd:
+            peaks = json.load(fd)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+
+    def per_launch(clock_ms, clock_launches):
+        return clock_ms / clock_launches if clock_launches else None
+
+    pair_ms = per_launch(profile.pair_ms, profile.pair_launches)
+    pair_flops = (pair_count * FLOP_PER_LJ_PAIR_FORCE + coulomb_pairs * FLOP_PER_COULOMB_PAIR) / world
+    kspace_ms = per_launch(profile.kspace_ms, profile.kspace_launches)
+    roofline_pair = None
+    if pair_ms:
+        achieved = pair_flops / (pair_ms * 1e-3) / 1e12
+        roofline_pair = {
+            "kernel": "cell_pairs_kernel" if counts.neighbor_path == 1 else "allpairs_kernel", "bound": "fp64",
+            "achieved": achieved, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value,
+            "peak_source": "measured live: dependent-free DFMA chains on every SM (lumol_cuda_measure_fp64_peak); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "algorithmic_flop_per_launch": pair_flops, "pairs_in_cutoff": pair_count, "coulomb_pairs_in_cutoff": coulomb_pairs,
+            "avg_launch_ms": pair_ms, "launches_timed": int(profile.pair_launches), "traffic": None,
+        }
+    roofline_extra = {}
+    if kspace_ms and nk:
+        # one rho launch + one force launch per evaluation
+        flops = n * nk * (FLOP_PER_ATOM_K_RHO + FLOP_PER_ATOM_K_FORCE) / world
+        total_ms = profile.kspace_ms / (profile.kspace_launches / 2.0)
+        achieved = flops / (total_ms * 1e-3) / 1e12
+        roofline_extra["ewald_kspace"] = {
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value,
+            "nkvectors": nk, "rho_plus_force_ms": total_ms,
+        }
+    if profile.integrate_launches:
+        steps_profiled = profile_steps
+        total_ms = profile.integrate_ms / steps_profiled
+        achieved = BYTES_PER_ATOM_VV * n / world / (total_ms * 1e-3) / 1e9
+        roofline_extra["velocity_verlet"] = {
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_source": hbm_source, "ms_per_step": total_ms, "bytes_per_atom_step": BYTES_PER_ATOM_VV,
+        }
+    if profile.neighbor_launches:
+        total_ms = profile.neighbor_ms / (profile.neighbor_launches / 6.0)
+        achieved = BYTES_PER_ATOM_SORT * n / (total_ms * 1e-3) / 1e9
+        roofline_extra["cell_sort"] = {
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_source": hbm_source, "ms_per_build": total_ms, "bytes_per_atom": BYTES_PER_ATOM_SORT,
+        }
+    dominant = roofline_pair
+    if "ewald_kspace" in roofline_extra and kspace_ms and pair_ms and profile.kspace_ms > profile.pair_ms:
+        dominant = dict(roofline_extra["ewald_kspace"], kernel="ewald_rho_kernel + ewald_force_kernel", traffic=None)
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, rows, seconds, threads = cpu_sample_rows(system, args.cpu_seconds)
+        cpu_baseline = {
+            "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"pair-force rows of {rows} of {n} atoms (uniform stride), all j > i: {seconds:.1f} s of the O(N^2) "
+                      "loop of sys/compute.rs:37-55 restated in oracle/lumol_oracle.c (OpenMP)",
+        }
+
+    bytes_resident = n * (24 * 3 + 8 * 2 + 4 + 4 * 3 + 32 + 16 + 4 * 4)
+    description.update({
+        "parallelism": f"{world} x B200, atoms in contiguous blocks per rank, replicated positions" if world > 1 else "1 x B200",
+        "neighbor_path": "cell list" if counts.neighbor_path == 1 else "all-pairs",
+        "cells": [int(c) for c in counts.ncells],
+        "l2": f"working set {bytes_resident / 1e6:.0f} MB per rank is larger than the 126 MB L2; no explicit flush",
+    })
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": description,
+        "ns_per_day": args.steps / (elapsed_ms * 1e-3) * TIMESTEP_FS * 86400.0 * 1e-6,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": dominant, "roofline_extra": roofline_extra,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -179,6 +179,8 @@ typedef struct {
     double neighbor_ms;
     int64_t comm_launches;
     double comm_ms;
+    double pair_count;         /* pairs inside their cut-off at the last energy/virial evaluation (each once) */
+    double coulomb_pair_count; /* same for the coulomb real-space / Wolf term */
 } lumol_cuda_stats;
 
 /* ---- lifetime ----------------------------------------------------------------------------------- */

@@ -96,6 +96,8 @@ class Stats(ctypes.Structure):
         ("neighbor_ms", ctypes.c_double),
         ("comm_launches", ctypes.c_int64),
         ("comm_ms", ctypes.c_double),
+        ("pair_count", ctypes.c_double),
+        ("coulomb_pair_count", ctypes.c_double),
     ]
 
 

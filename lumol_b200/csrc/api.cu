@@ -611,8 +611,8 @@ int evaluate_forces_device(Context* c, const ComputeRequest& req) {
         if (req.forces) {
             LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->force.ptr, 0, (size_t)n * 3 * sizeof(double), c->stream));
         }
-        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_E_PAIRS, 0, 14 * sizeof(double), c->stream));
-        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_MOLECULAR_BLOCK, 0, 14 * sizeof(double), c->stream));
+        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_E_PAIRS, 0, 16 * sizeof(double), c->stream));
+        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_MOLECULAR_BLOCK, 0, 16 * sizeof(double), c->stream));
     }
 
     if (req.bonded) {
@@ -695,6 +695,10 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
     }
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     const double* r = c->host_results;
+    if (req.energy || req.virial) {
+        c->last_pair_count = r[RES_PAIR_COUNT];
+        c->last_coulomb_pair_count = r[RES_COULOMB_PAIR_COUNT];
+    }
 
     // tail corrections are host scalars: sum over kinds present in the system, both orders
     // (energy.rs:63-79, compute.rs:219-228)
@@ -949,6 +953,8 @@ extern "C" int32_t lumol_cuda_get_stats(lumol_cuda_context* ctx, lumol_cuda_stat
     stats->neighbor_ms = c->clk_neighbor.ms;
     stats->comm_launches = c->clk_comm.launches;
     stats->comm_ms = c->clk_comm.ms;
+    stats->pair_count = c->last_pair_count;
+    stats->coulomb_pair_count = c->last_coulomb_pair_count;
     return LUMOL_CUDA_SUCCESS;
 }
 

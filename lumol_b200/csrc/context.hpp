@@ -46,27 +46,32 @@ struct DeviceBuffer {
 
 // Result slots written by the reduction kernels (device `results` array).
 enum ResultSlot {
+    // ---- one 16-value block written by the pair kernels -------------------------------------------
     RES_E_PAIRS = 0,
     RES_E_COULOMB_REAL = 1,
     RES_W_PAIRS = 2,          // 6 values: xx xy xz yy yz zz
     RES_W_COULOMB_REAL = 8,   // 6
-    RES_E_BONDS = 14,
-    RES_W_BONDS = 15,         // 6, directly after RES_E_BONDS (one 7-value reduction)
-    RES_E_ANGLES = 21,
-    RES_E_DIHEDRALS = 22,
-    RES_E_KSPACE = 23,
-    RES_W_KSPACE = 24,        // 6
-    RES_CHARGE2 = 30,         // sum q^2 (Ewald self) or sum over charged atoms of q^2 (Wolf self)
-    RES_KINETIC = 31,
-    RES_KINETIC_TENSOR = 32,  // 6
-    RES_MOMENTUM = 38,        // sum m v (3) and sum m (1)
-    RES_MOLECULAR_BLOCK = 42,      // same 14-value layout as slots 0..13, from the molecular-virial kernel
-    RES_W_MOLECULAR_PAIRS = 44,    // 6
-    RES_W_MOLECULAR_COULOMB = 50,  // 6
-    RES_W_KSPACE_CORRECTION = 56,  // 9: sum_mol sum_i f_i (x) (x_i - com), ewald.rs:736-753
-    RES_SCALE_FACTOR = 65,         // thermostat factor computed on the device
-    RES_FLAGS = 66,                // non-finite detector
-    RES_COUNT = 68
+    RES_PAIR_COUNT = 14,          // pair interactions evaluated inside their cut-off (each pair once)
+    RES_COULOMB_PAIR_COUNT = 15,  // same for the coulomb real-space term
+    // ---- bonded -----------------------------------------------------------------------------------
+    RES_E_BONDS = 16,
+    RES_W_BONDS = 17,         // 6, directly after RES_E_BONDS (one 7-value reduction)
+    RES_E_ANGLES = 23,
+    RES_E_DIHEDRALS = 24,
+    // ---- everything below is NOT a per-rank partial sum ---------------------------------------------
+    RES_E_KSPACE = 25,
+    RES_W_KSPACE = 26,        // 6
+    RES_CHARGE2 = 32,         // sum q^2 over the atoms of this rank
+    RES_KINETIC = 33,
+    RES_KINETIC_TENSOR = 34,  // 6
+    RES_MOMENTUM = 40,        // sum m v (3) and sum m (1)
+    RES_MOLECULAR_BLOCK = 44,      // same 16-value layout as slots 0..15, from the molecular-virial kernel
+    RES_W_MOLECULAR_PAIRS = 46,    // 6
+    RES_W_MOLECULAR_COULOMB = 52,  // 6
+    RES_W_KSPACE_CORRECTION = 60,  // 9: sum_mol sum_i f_i (x) (x_i - com), ewald.rs:736-753
+    RES_SCALE_FACTOR = 69,         // thermostat factor computed on the device
+    RES_FLAGS = 70,
+    RES_COUNT = 72
 };
 
 struct Timer {
@@ -174,6 +179,7 @@ struct Context {
     Timer timer;
     int64_t launches = 0;
     KernelClock clk_pair, clk_kspace, clk_integrate, clk_neighbor, clk_comm;
+    double last_pair_count = 0.0, last_coulomb_pair_count = 0.0;
 
     int fail(int code, const char* fmt, ...) {
         char buffer[512];

@@ -45,7 +45,7 @@ constexpr int MODE_MOLECULAR = 2;  // molecular virial only
 
 constexpr int ALLPAIRS_THREADS = 256;
 constexpr int ALLPAIRS_WARPS = ALLPAIRS_THREADS / 32;
-constexpr int ALLPAIRS_NV = 14;  // e_pairs, e_coulomb, W_pairs[6], W_coulomb[6]
+constexpr int ALLPAIRS_NV = 16;  // e_pairs, e_coulomb, W_pairs[6], W_coulomb[6], pair count, coulomb pair count
 
 template <int MODE>
 __global__ void __launch_bounds__(ALLPAIRS_THREADS) allpairs_kernel(AllPairsArgs a) {
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(ALLPAIRS_THREADS) allpairs_kernel(AllPairsArgs
                         if (MODE != MODE_FORCES && count) {
                             const double w = fr * proj;
                             acc[0] += scaling * e;
+                            acc[14] += 1.0;
                             acc[2] += w * dx * dx;
                             acc[3] += w * dx * dy;
                             acc[4] += w * dx * dz;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(ALLPAIRS_THREADS) allpairs_kernel(AllPairsArgs
                         if (MODE != MODE_FORCES && count) {
                             const double w = fr * proj;
                             acc[1] += e;
+                            acc[15] += 1.0;
                             acc[8] += w * dx * dx;
                             acc[9] += w * dx * dy;
                             acc[10] += w * dx * dz;

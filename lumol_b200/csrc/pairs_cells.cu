@@ -264,7 +264,7 @@ static int build_cells(Context* ctx, const GridView& g) {
 constexpr int CELL_THREADS = 128;
 constexpr int CELL_WARPS = CELL_THREADS / 32;
 constexpr int CELL_ICHUNK = 128;  // home atoms whose forces are accumulated in shared memory at a time
-constexpr int CELL_NV = 14;       // same layout as the all-pairs kernel
+constexpr int CELL_NV = 16;       // same layout as the all-pairs kernel
 constexpr int CELL_MODE_FORCES = 0;
 constexpr int CELL_MODE_FULL = 1;
 
@@ -313,6 +313,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
             fz += fr * dz;
             if (MODE == CELL_MODE_FULL && count) {
                 acc[0] += 4.0 * a.lj_epsilon * (s6 * s6 - s6) - a.lj_shift;
+                acc[14] += 1.0;
                 acc[2] += fr * dx * dx;
                 acc[3] += fr * dx * dy;
                 acc[4] += fr * dx * dz;
@@ -340,6 +341,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
                 fz += fr * dz;
                 if (MODE == CELL_MODE_FULL && count) {
                     acc[0] += scaling * e;
+                    acc[14] += 1.0;
                     acc[2] += fr * dx * dx;
                     acc[3] += fr * dx * dy;
                     acc[4] += fr * dx * dz;
@@ -372,6 +374,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
                 fz += fr * dz;
                 if (MODE == CELL_MODE_FULL && count) {
                     acc[1] += e;
+                    acc[15] += 1.0;
                     acc[8] += fr * dx * dx;
                     acc[9] += fr * dx * dy;
                     acc[10] += fr * dx * dz;

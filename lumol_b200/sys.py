@@ -149,8 +149,14 @@ class Molecule:
         return len(self.particles)
 
 
+_SINGLE_FAR = np.full((1, 1), BOND_FAR, dtype=np.uint8)
+_SINGLE_FAR.setflags(write=False)
+
+
 class Bonding:
     """``Bonding`` (bonding.rs:16-30) for one molecule spanning atoms ``[start, end)``."""
+
+    __slots__ = ("start", "end", "bonds", "angles", "dihedrals", "distances")
 
     def __init__(self, start, end):
         self.start = start
@@ -158,7 +164,8 @@ class Bonding:
         self.bonds = set()  # (i, j) global indices, i < j
         self.angles = set()
         self.dihedrals = set()
-        self.distances = np.full((end - start, end - start), BOND_FAR, dtype=np.uint8)
+        # single atoms share one read-only matrix (systems with millions of free atoms)
+        self.distances = _SINGLE_FAR if end - start == 1 else np.full((end - start, end - start), BOND_FAR, dtype=np.uint8)
 
     def size(self):
         return self.end - self.start

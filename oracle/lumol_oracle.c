@@ -931,6 +931,56 @@ void orc_pair_forces(const orc_system* s, double* out) {
     thread_vec_sum_into(&tv, out);
 }
 
+/* Bounded sample of compute.rs:37-55 for the CPU baseline: the inner loop `for j in (i + 1)..natoms` of the
+ * rows listed in `rows`, spread over the OpenMP threads exactly like the full loop, forces accumulated in
+ * per-thread buffers.  Rows drawn uniformly from [0, n) cost on average what a row of the full O(N^2) loop
+ * costs, so (time * n / nrows) estimates one full evaluation.  Returns the number of pairs inside the cut-off
+ * among the visited ones; `checksum` receives the sum of |force_i| over the sampled rows. */
+int64_t orc_pair_forces_sample(const orc_system* s, int64_t nrows, const int64_t* rows, double* checksum) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    int64_t n = s->n;
+    thread_vec_t tv;
+    thread_vec_init(&tv, 3 * n);
+    int64_t inside = 0;
+    double sum = 0.0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : inside, sum)
+    for (int64_t row = 0; row < nrows; row++) {
+        int64_t i = rows[row];
+        double* forces = tv.data + (size_t)thread_id() * (size_t)(3 * n);
+        double force_i[3] = {0.0, 0.0, 0.0};
+        for (int64_t j = i + 1; j < n; j++) {
+            int32_t path = orc_bond_path(s, i, j);
+            double d[3];
+            nearest_image(s, &g, i, j, d);
+            double r = norm3(d);
+            double dn[3] = {d[0] / r, d[1] / r, d[2] / r};
+            const orc_pair* potential = pair_potential(s, i, j);
+            if (potential != NULL) {
+                int32_t excluded;
+                double scaling;
+                orc_restriction_information(potential->restriction, potential->scale14, path, &excluded, &scaling);
+                if (!excluded) {
+                    double f = scaling * orc_pair_force(potential, r);
+                    if (r < potential->cutoff) inside++;
+                    for (int k = 0; k < 3; k++) {
+                        double force = f * dn[k];
+                        force_i[k] += force;
+                        forces[3 * j + k] -= force;
+                    }
+                }
+            }
+        }
+        for (int k = 0; k < 3; k++) {
+            forces[3 * i + k] += force_i[k];
+        }
+        sum += fabs(force_i[0]) + fabs(force_i[1]) + fabs(force_i[2]);
+    }
+    free(tv.data);
+    if (checksum) *checksum = sum;
+    return inside;
+}
+
 /* compute.rs:62-97 */
 void orc_bonded_forces(const orc_system* s, double* forces) {
     geom_t g;

@@ -193,6 +193,7 @@ void orc_set_threads(int32_t nthreads);
 int32_t orc_get_threads(void);
 void orc_pair_forces(const orc_system* s, double* forces);   /* compute.rs:37-60, zero-initialised output */
 void orc_bonded_forces(const orc_system* s, double* forces); /* compute.rs:62-97, accumulates */
+int64_t orc_pair_forces_sample(const orc_system* s, int64_t nrows, const int64_t* rows, double* checksum);
 void orc_coulomb_forces(const orc_system* s, double* forces); /* accumulates, like GlobalPotential::forces */
 void orc_forces(const orc_system* s, double* forces);         /* Forces::compute */
 double orc_pairs_energy(const orc_system* s);

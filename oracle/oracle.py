@@ -131,6 +131,7 @@ def library():
             "orc_get_threads": (ctypes.c_int32, []),
             "orc_pair_forces": (None, [sp, _dp]),
             "orc_bonded_forces": (None, [sp, _dp]),
+            "orc_pair_forces_sample": (ctypes.c_int64, [sp, ctypes.c_int64, _ip, _dp]),
             "orc_coulomb_forces": (None, [sp, _dp]),
             "orc_forces": (None, [sp, _dp]),
             "orc_pairs_energy": (d, [sp]),
@@ -252,6 +253,12 @@ class OracleSystem:
         chunks, bonds, angles, dihedrals = [], [], [], []
         cursor = 0
         cache = {}
+        if nmol == n:
+            # only free atoms: no topology to rebuild
+            self.mol_start[:n] = np.arange(n)
+            self.molid[:n] = np.arange(n)
+            chunks.append(np.full(1, 8, dtype=np.uint8))
+            bondings = []
         for m, bonding in enumerate(bondings):
             self.mol_start[m] = bonding.start
             self.molid[bonding.start:bonding.end] = m
