@@ -88,7 +88,7 @@ extern "C" int32_t lumol_cuda_destroy(lumol_cuda_context* ctx) {
     c->table_energy.release(); c->table_force.release(); c->bonded.release(); c->bonds.release();
     c->angles.release(); c->dihedrals.release(); c->kindex.release(); c->kenergy.release(); c->kvirial.release();
     c->rho.release(); c->rho_partial.release(); c->cell_of.release(); c->cell_count.release();
-    c->cell_start.release(); c->order.release(); c->sorted_pos.release(); c->sorted_info.release();
+    c->cell_start.release(); c->order.release(); c->sorted_pos.release(); c->sorted_f32.release(); c->sorted_info.release();
     c->scan_scratch.release(); c->partials.release(); c->reduce_scratch.release(); c->results.release();
     c->csvr_noise_dev.release();
     if (c->host_results) cudaFreeHost(c->host_results);

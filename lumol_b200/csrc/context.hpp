@@ -148,7 +148,8 @@ struct Context {
     int path = 0;
     int ncell[3] = {0, 0, 0};
     DeviceBuffer<int> cell_of, cell_count, cell_start, order;
-    DeviceBuffer<double4> sorted_pos;  // x, y, z (wrapped), charge
+    DeviceBuffer<double4> sorted_pos;  // x, y, z relative to the centre of the own cell, charge
+    DeviceBuffer<float4> sorted_f32;   // the same position in FP32
     DeviceBuffer<int4> sorted_info;    // kind, mol_first, bd_row, original index
     DeviceBuffer<int> scan_scratch;
 

@@ -1,6 +1,6 @@
-// Cell-list pair path: counting sort of the atoms into cells of edge >= the largest cut-off, then one
-// block per home cell sweeping its 27 neighbour cells.  The reference has no neighbour search at all
-// (SURVEY F1): this replaces the O(N^2) loops of
+// Cell-list pair path: counting sort of the atoms into cells of edge >= the largest cut-off, then a sweep of
+// the 27 neighbour cells of every home cell.  The reference has no neighbour search at all: this
+// replaces the O(N^2) loops of
 //   Forces::compute        sys/compute.rs:37-55
 //   EnergyEvaluator::pairs sys/energy.rs:47-59
 //   AtomicVirial::compute  sys/compute.rs:202-216
@@ -9,18 +9,25 @@
 // by an O(N) sweep that visits exactly the same pairs (every pair with r below the cut-off lies in the
 // 27-cell neighbourhood when each edge holds at least three cells).
 //
-// Data layout in HBM: `sorted_pos` holds (x, y, z, q) as one 32-byte double4 per atom, positions wrapped
-// into the cell with the floor convention of UnitCell::wrap_vector (cells.rs:263-279), atoms of one cell
-// contiguous, cells in z-major order; `sorted_info` holds (kind, first atom of the molecule, bond-distance
-// row, original index).  The order inside a cell is by original index, so the sort is deterministic
-// (every rank of a multi-GPU run derives the same order).
+// Data layout in HBM (rebuilt every evaluation from the positions in original order):
+//   sorted_pos  double4 (x, y, z, q): position RELATIVE TO THE CENTRE OF THE ATOM'S OWN CELL (the wrap into the
+//               cell uses the floor convention of UnitCell::wrap_vector, cells.rs:263-279) and the charge;
+//   sorted_f32  float4: the same relative position in FP32, for the pre-filter;
+//   sorted_info int4 (kind, first atom of the molecule, bond-distance row, original index);
+//   cell_start  exclusive scan of the cell populations; cells in z-major order, atoms of one cell contiguous and
+//               ordered by original index, so the sort is deterministic (every rank derives the same order).
+// With cell-relative coordinates the separation of atom i in home cell h and atom j in the neighbour cell
+// h + (a, b, c) is (x_i - (a, b, c) * edge) - x_j whatever the periodic wrap of the cell index, so the kernel
+// needs no image logic at all and keeps full relative precision in arbitrarily large boxes.
 //
-// Pair kernel: the block stages the neighbourhood (27 cells, periodic shifts already applied) in shared
-// memory as FP64 double4 plus an FP32 copy relative to the home-cell centre.  One warp owns one atom i at
-// a time: the 32 lanes test 32 candidates per iteration in FP32 against a slightly enlarged cut-off,
-// compact the survivors into a per-warp queue with ballot/popc, and whenever 32 survivors are queued the
-// warp evaluates them densely in FP64 (exact r < rc test included).  The FP64 pipe therefore only sees
-// pairs that are (almost all) inside the cut-off, at full lane occupancy.  No atomics: each pair is
+// Pair kernel: one lane per atom i, one warp per home cell (cells above 32 atoms take several passes), each warp
+// walking its own contiguous range of cells so that successive home cells reuse their neighbourhoods from L1.
+//   phase 1 (FP32 / integer pipes): the warp streams the candidates of the 27 neighbour cells; all lanes read
+//     the same candidate (a broadcast load), each lane tests it against its own atom with an enlarged FP32
+//     cut-off and appends survivors to its private queue in shared memory;
+//   phase 2 (FP64 pipe): every lane walks its queue: gathers the FP64 position, applies the exact r < rc test
+//     and evaluates the pair.  The queue is flushed whenever a lane could overflow.
+// Forces are accumulated in registers by the lane that owns the atom: no atomics, no shuffles; each pair is
 // evaluated from both sides, energies/virials are taken from the side with the larger sorted index.
 #include "context.hpp"
 
@@ -188,6 +195,7 @@ struct ScatterArgs {
     const int* __restrict__ grouped;
     int* __restrict__ order;
     double4* __restrict__ sorted_pos;
+    float4* __restrict__ sorted_f32;
     int4* __restrict__ sorted_info;
 };
 
@@ -204,9 +212,13 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
     }
     const int dst = lo + rank;
     a.order[dst] = i;
-    a.sorted_pos[dst] = make_double4(wrap_coordinate(a.pos[3 * i], a.g.length[0]),
-                                     wrap_coordinate(a.pos[3 * i + 1], a.g.length[1]),
-                                     wrap_coordinate(a.pos[3 * i + 2], a.g.length[2]), a.charge[i]);
+    // position relative to the centre of the cell the atom was binned into
+    const int cx = c % a.g.nc[0], cy = (c / a.g.nc[0]) % a.g.nc[1], cz = c / (a.g.nc[0] * a.g.nc[1]);
+    const double x = wrap_coordinate(a.pos[3 * i], a.g.length[0]) - ((double)cx + 0.5) * a.g.edge[0];
+    const double y = wrap_coordinate(a.pos[3 * i + 1], a.g.length[1]) - ((double)cy + 0.5) * a.g.edge[1];
+    const double z = wrap_coordinate(a.pos[3 * i + 2], a.g.length[2]) - ((double)cz + 0.5) * a.g.edge[2];
+    a.sorted_pos[dst] = make_double4(x, y, z, a.charge[i]);
+    a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, 0.0f);
     a.sorted_info[dst] = make_int4((int)a.kind[i], a.mol_first[i], a.bd_row[i], i);
 }
 
@@ -218,6 +230,7 @@ static int build_cells(Context* ctx, const GridView& g) {
     LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)ncells + 1));
     LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));  // order + grouped
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_pos.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_info.reserve((size_t)n));
     const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
     LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)scan_blocks + 1));
@@ -249,6 +262,7 @@ static int build_cells(Context* ctx, const GridView& g) {
     s.grouped = grouped;
     s.order = order;
     s.sorted_pos = ctx->sorted_pos.ptr;
+    s.sorted_f32 = ctx->sorted_f32.ptr;
     s.sorted_info = ctx->sorted_info.ptr;
     cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
     ctx->launches += 6;
@@ -263,18 +277,21 @@ static int build_cells(Context* ctx, const GridView& g) {
 
 constexpr int CELL_THREADS = 128;
 constexpr int CELL_WARPS = CELL_THREADS / 32;
-constexpr int CELL_ICHUNK = 128;  // home atoms whose forces are accumulated in shared memory at a time
-constexpr int CELL_NV = 16;       // same layout as the all-pairs kernel
+constexpr int CELL_QUEUE = 96;   // queue slots per lane
+constexpr int CELL_CHUNK = 16;   // candidates streamed between two overflow checks
+constexpr int CELL_NV = 16;      // same layout as the all-pairs kernel
 constexpr int CELL_MODE_FORCES = 0;
 constexpr int CELL_MODE_FULL = 1;
+constexpr unsigned QUEUE_INDEX_MASK = (1u << 26) - 1u;
 
 struct CellArgs {
     GridView g;
-    int cell_lo, cell_hi;  // home cells handled by this launch
-    int o_lo, o_hi;        // original-index range of the atoms this rank owns (forces are computed for those)
-    int tile;              // candidates staged per pass
+    int ncells;
+    int cells_per_warp;
+    int o_lo, o_hi;  // original-index range of the atoms this rank owns (forces are computed for those)
     const int* __restrict__ cell_start;
     const double4* __restrict__ sorted_pos;
+    const float4* __restrict__ sorted_f32;
     const int4* __restrict__ sorted_info;
     const unsigned char* __restrict__ bond_dist;
     int nkinds;
@@ -284,21 +301,23 @@ struct CellArgs {
     const double* __restrict__ table_force;
     CoulombView coulomb;
     int do_pairs, do_coulomb;
-    double cutoff2;     // (largest cut-off)^2, exact FP64 gate for the general path
+    double cutoff2;     // (largest cut-off)^2: early-out of the general path
     float cutoff2_f32;  // the same, enlarged by 1e-4 relative for the FP32 pre-filter
     // LJ fast path
-    double lj_sigma2, lj_epsilon, lj_cutoff2, lj_shift;
+    double lj_sigma2, lj_epsilon24, lj_epsilon4, lj_cutoff2, lj_shift;
     int write_forces;            // energy-only queries must not clobber the forces the integrator holds
     double* __restrict__ force;  // original order, n x 3
     double* __restrict__ partials;
 };
 
+// One queued candidate, FP64: exact cut-off test and pair evaluation for the lane's atom.
 template <bool LJ_ONLY, int MODE>
 __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const PairParams* __restrict__ sp,
-                                                   const double4& pi, const int4& info_i, int s_i, const double4& pj,
-                                                   const int4& info_j, int s_j, double& fx, double& fy, double& fz,
+                                                   double xi, double yi, double zi, double qi, const int4& info_i,
+                                                   int s_i, int s_j, double& fx, double& fy, double& fz,
                                                    double (&acc)[CELL_NV]) {
-    const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    const double4 pj = a.sorted_pos[s_j];
+    const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double r2 = dx * dx + dy * dy + dz * dz;
     const bool count = s_j > s_i;
     if (LJ_ONLY) {
@@ -307,12 +326,12 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
             const double s2 = a.lj_sigma2 * rinv2;
             const double s6 = s2 * s2 * s2;
             // force(r) / r = -24 eps (s6 - 2 s6^2) / r^2 (functions.rs:85-88)
-            const double fr = 24.0 * a.lj_epsilon * (2.0 * s6 * s6 - s6) * rinv2;
+            const double fr = a.lj_epsilon24 * s6 * (2.0 * s6 - 1.0) * rinv2;
             fx += fr * dx;
             fy += fr * dy;
             fz += fr * dz;
             if (MODE == CELL_MODE_FULL && count) {
-                acc[0] += 4.0 * a.lj_epsilon * (s6 * s6 - s6) - a.lj_shift;
+                acc[0] += a.lj_epsilon4 * (s6 * s6 - s6) - a.lj_shift;
                 acc[14] += 1.0;
                 acc[2] += fr * dx * dx;
                 acc[3] += fr * dx * dy;
@@ -326,6 +345,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
     }
     if (!(r2 < a.cutoff2 * 1.0000000001)) return;
     const double r = sqrt(r2);
+    const int4 info_j = a.sorted_info[s_j];
     const bool same_molecule = info_i.y == info_j.y;
     const unsigned bits = same_molecule ? a.bond_dist[info_i.z + (info_j.w - info_j.y)] : 0u;
     if (a.do_pairs) {
@@ -353,7 +373,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
         }
     }
     if (a.do_coulomb && r <= a.coulomb.rc) {
-        const double qi = pi.w, qj = pj.w;
+        const double qj = pj.w;
         if (qi != 0.0 && qj != 0.0) {
             double scaling;
             const bool excluded = restriction_excluded(a.coulomb.restriction, bits, a.coulomb.scale14, scaling);
@@ -390,24 +410,14 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
 template <bool LJ_ONLY, int MODE>
 __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(CellArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double4* tpos = reinterpret_cast<double4*>(smem_raw);
-    float4* tf32 = reinterpret_cast<float4*>(tpos + a.tile);
-    int4* tinfo = reinterpret_cast<int4*>(tf32 + a.tile);
-    PairParams* sp = reinterpret_cast<PairParams*>(tinfo + (LJ_ONLY ? 0 : a.tile));
-
-    __shared__ int r_start[27];
-    __shared__ int r_prefix[28];
-    __shared__ double r_shift[27][3];
-    __shared__ double sh_force[CELL_ICHUNK * 3];
-    __shared__ unsigned short queue[CELL_WARPS][64];
+    unsigned* queues = reinterpret_cast<unsigned*>(smem_raw);  // [warp][slot][lane]
+    PairParams* sp = reinterpret_cast<PairParams*>(queues + CELL_WARPS * CELL_QUEUE * 32);
+    __shared__ double offset64[27][3];  // (a, b, c) * edge for the 27 neighbour offsets
+    __shared__ float offset32[27][3];
     __shared__ double scratch[32 * CELL_NV];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int c = a.cell_lo + blockIdx.x;
-    const int cx = c % a.g.nc[0];
-    const int cy = (c / a.g.nc[0]) % a.g.nc[1];
-    const int cz = c / (a.g.nc[0] * a.g.nc[1]);
 
     if (!LJ_ONLY) {
         const int words = (int)(sizeof(PairParams) / sizeof(double)) * a.nkinds * a.nkinds;
@@ -417,139 +427,118 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(CellArgs a) {
     }
     if (threadIdx.x < 27) {
         const int t = threadIdx.x;
-        int nx = cx + (t % 3) - 1, ny = cy + ((t / 3) % 3) - 1, nz = cz + (t / 9) - 1;
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        if (nx < 0) { nx += a.g.nc[0]; sx = -a.g.length[0]; }
-        if (nx >= a.g.nc[0]) { nx -= a.g.nc[0]; sx = a.g.length[0]; }
-        if (ny < 0) { ny += a.g.nc[1]; sy = -a.g.length[1]; }
-        if (ny >= a.g.nc[1]) { ny -= a.g.nc[1]; sy = a.g.length[1]; }
-        if (nz < 0) { nz += a.g.nc[2]; sz = -a.g.length[2]; }
-        if (nz >= a.g.nc[2]) { nz -= a.g.nc[2]; sz = a.g.length[2]; }
-        const int nb = (nz * a.g.nc[1] + ny) * a.g.nc[0] + nx;
-        r_start[t] = a.cell_start[nb];
-        r_prefix[t + 1] = a.cell_start[nb + 1] - a.cell_start[nb];  // length for now
-        r_shift[t][0] = sx;
-        r_shift[t][1] = sy;
-        r_shift[t][2] = sz;
+        const double ox = (double)((t % 3) - 1) * a.g.edge[0];
+        const double oy = (double)(((t / 3) % 3) - 1) * a.g.edge[1];
+        const double oz = (double)((t / 9) - 1) * a.g.edge[2];
+        offset64[t][0] = ox;
+        offset64[t][1] = oy;
+        offset64[t][2] = oz;
+        offset32[t][0] = (float)ox;
+        offset32[t][1] = (float)oy;
+        offset32[t][2] = (float)oz;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        r_prefix[0] = 0;
-        for (int t = 0; t < 27; t++) r_prefix[t + 1] += r_prefix[t];
-    }
-    __syncthreads();
-    const int total = r_prefix[27];
 
-    // home atoms of this block; only those this rank owns are evaluated
-    const int hs = a.cell_start[c], he = a.cell_start[c + 1];
-    {
-        int owned = 0;
-        for (int s = hs + threadIdx.x; s < he; s += blockDim.x) {
-            const int orig = a.sorted_info[s].w;
-            owned |= (orig >= a.o_lo && orig < a.o_hi) ? 1 : 0;
-        }
-        if (!__syncthreads_or(owned)) {
-            if (MODE == CELL_MODE_FULL && threadIdx.x == 0) {
-                for (int k = 0; k < CELL_NV; k++) a.partials[(size_t)blockIdx.x * CELL_NV + k] = 0.0;
-            }
-            return;
-        }
-    }
-
-    // centre of the home cell: origin of the FP32 coordinates
-    const double ox = ((double)cx + 0.5) * a.g.edge[0];
-    const double oy = ((double)cy + 0.5) * a.g.edge[1];
-    const double oz = ((double)cz + 0.5) * a.g.edge[2];
+    unsigned* q = queues + warp * CELL_QUEUE * 32 + lane;  // slot k at q[k * 32]
 
     double acc[CELL_NV];
 #pragma unroll
     for (int k = 0; k < CELL_NV; k++) acc[k] = 0.0;
 
-    for (int ic = hs; ic < he; ic += CELL_ICHUNK) {
-        const int ni = min(CELL_ICHUNK, he - ic);
-        for (int t = threadIdx.x; t < 3 * ni; t += blockDim.x) sh_force[t] = 0.0;
+    const int global_warp = blockIdx.x * CELL_WARPS + warp;
+    const int cell_lo = global_warp * a.cells_per_warp;
+    const int cell_hi = min(a.ncells, cell_lo + a.cells_per_warp);
 
-        for (int base = 0; base < total; base += a.tile) {
-            const int cnt = min(a.tile, total - base);
-            __syncthreads();
-            // stage candidates [base, base + cnt) of the flattened neighbourhood
-            for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
-                const int gidx = base + t;
-                int r = 0;
-                while (gidx >= r_prefix[r + 1]) r++;
-                const int s = r_start[r] + (gidx - r_prefix[r]);
-                double4 p = a.sorted_pos[s];
-                p.x += r_shift[r][0];
-                p.y += r_shift[r][1];
-                p.z += r_shift[r][2];
-                tpos[t] = p;
-                tf32[t] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float(s));
-                if (!LJ_ONLY) tinfo[t] = a.sorted_info[s];
-            }
-            __syncthreads();
+    for (int c = cell_lo; c < cell_hi; c++) {
+        const int hs = a.cell_start[c], he = a.cell_start[c + 1];
+        if (hs == he) continue;
+        const int cx = c % a.g.nc[0];
+        const int cy = (c / a.g.nc[0]) % a.g.nc[1];
+        const int cz = c / (a.g.nc[0] * a.g.nc[1]);
 
-            for (int il = warp; il < ni; il += CELL_WARPS) {
-                const int s_i = ic + il;
-                const int4 info_i = a.sorted_info[s_i];
-                if (info_i.w < a.o_lo || info_i.w >= a.o_hi) continue;  // warp-uniform
+        for (int base = hs; base < he; base += 32) {
+            // this lane's atom (lanes without an atom, or with an atom another rank owns, sit far away)
+            const int s_i = base + lane;
+            bool active = s_i < he;
+            int4 info_i = make_int4(0, 0, 0, -1);
+            double xi = 0.0, yi = 0.0, zi = 0.0, qi = 0.0;
+            if (active) {
+                info_i = a.sorted_info[s_i];
+                active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
                 const double4 pi = a.sorted_pos[s_i];
-                const float fxi = (float)(pi.x - ox), fyi = (float)(pi.y - oy), fzi = (float)(pi.z - oz);
-                double fx = 0.0, fy = 0.0, fz = 0.0;
-                int queued = 0;
-                unsigned short* q = queue[warp];
+                xi = pi.x;
+                yi = pi.y;
+                zi = pi.z;
+                qi = pi.w;
+            }
+            if (!__any_sync(0xffffffffu, active)) continue;
+            const float xf = active ? (float)xi : 1.0e18f, yf = (float)yi, zf = (float)zi;
 
-                for (int b = 0; b < cnt; b += 32) {
-                    const int t = b + lane;
-                    bool pass = false;
-                    if (t < cnt) {
-                        const float4 f = tf32[t];
-                        const float ddx = fxi - f.x, ddy = fyi - f.y, ddz = fzi - f.z;
-                        const float r2f = ddx * ddx + ddy * ddy + ddz * ddz;
-                        pass = r2f < a.cutoff2_f32 && __float_as_int(f.w) != s_i;
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                    if (pass) q[queued + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)t;
-                    queued += __popc(mask);
-                    __syncwarp();
-                    if (queued >= 32) {
-                        const int t2 = q[lane];
-                        const int4 info_j = LJ_ONLY ? make_int4(0, 0, 0, 0) : tinfo[t2];
-                        evaluate_candidate<LJ_ONLY, MODE>(a, sp, pi, info_i, s_i, tpos[t2], info_j,
-                                                          __float_as_int(tf32[t2].w), fx, fy, fz, acc);
-                        const int rest = queued - 32;
-                        const unsigned short carry = lane < rest ? q[32 + lane] : (unsigned short)0;
-                        __syncwarp();
-                        if (lane < rest) q[lane] = carry;
-                        queued = rest;
-                        __syncwarp();
+            double fx = 0.0, fy = 0.0, fz = 0.0;
+            // next free slot of this lane's queue as a 32-bit shared-memory address (slots are 128 bytes apart)
+            const unsigned queue_base = (unsigned)__cvta_generic_to_shared(q);
+            unsigned tail = queue_base;
+
+            // phase 2: walk the private queues (FP64)
+            auto flush = [&]() {
+                const int queued = (int)((tail - queue_base) >> 7);
+                const int longest = __reduce_max_sync(0xffffffffu, queued);
+                for (int k = 0; k < longest; k++) {
+                    if (k < queued) {
+                        const unsigned entry = q[k * 32];
+                        const int code = (int)(entry >> 26);
+                        const int s_j = (int)(entry & QUEUE_INDEX_MASK);
+                        if (s_j != s_i) {
+                            evaluate_candidate<LJ_ONLY, MODE>(a, sp, xi - offset64[code][0], yi - offset64[code][1],
+                                                              zi - offset64[code][2], qi, info_i, s_i, s_j, fx, fy, fz, acc);
+                        }
                     }
                 }
-                if (lane < queued) {
-                    const int t2 = q[lane];
-                    const int4 info_j = LJ_ONLY ? make_int4(0, 0, 0, 0) : tinfo[t2];
-                    evaluate_candidate<LJ_ONLY, MODE>(a, sp, pi, info_i, s_i, tpos[t2], info_j,
-                                                      __float_as_int(tf32[t2].w), fx, fy, fz, acc);
-                }
-                __syncwarp();
-                fx = warp_sum(fx);
-                fy = warp_sum(fy);
-                fz = warp_sum(fz);
-                if (lane == 0) {
-                    sh_force[3 * il] += fx;
-                    sh_force[3 * il + 1] += fy;
-                    sh_force[3 * il + 2] += fz;
+                tail = queue_base;
+            };
+
+            // phase 1: stream the 27 neighbour cells (FP32 pre-filter); rows of three cells along x
+            for (int row = 0; row < 9; row++) {
+                int ny = cy + (row % 3) - 1, nz = cz + (row / 3) - 1;
+                ny += ny < 0 ? a.g.nc[1] : 0;
+                ny -= ny >= a.g.nc[1] ? a.g.nc[1] : 0;
+                nz += nz < 0 ? a.g.nc[2] : 0;
+                nz -= nz >= a.g.nc[2] ? a.g.nc[2] : 0;
+                const int row_base = (nz * a.g.nc[1] + ny) * a.g.nc[0];
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const int code = row * 3 + dx;
+                    int nx = cx + dx - 1;
+                    nx += nx < 0 ? a.g.nc[0] : 0;
+                    nx -= nx >= a.g.nc[0] ? a.g.nc[0] : 0;
+                    const int s0 = a.cell_start[row_base + nx], s1 = a.cell_start[row_base + nx + 1];
+                    // atom i seen from the neighbour cell's centre
+                    const float xr = xf - offset32[code][0], yr = yf - offset32[code][1], zr = zf - offset32[code][2];
+                    const unsigned tag = (unsigned)code << 26;
+                    for (int chunk = s0; chunk < s1; chunk += CELL_CHUNK) {
+                        if (__any_sync(0xffffffffu, tail > queue_base + 128u * (CELL_QUEUE - CELL_CHUNK))) flush();
+                        const int stop = min(s1, chunk + CELL_CHUNK);
+#pragma unroll 4
+                        for (int s_j = chunk; s_j < stop; s_j++) {
+                            const float4 f = __ldg(a.sorted_f32 + s_j);  // same address in every lane: one broadcast
+                            const float ddx = xr - f.x, ddy = yr - f.y, ddz = zr - f.z;
+                            const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                            if (r2 < a.cutoff2_f32) {  // the atom itself passes too; phase 2 drops it
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(tail), "r"(tag + (unsigned)s_j) : "memory");
+                                tail += 128u;
+                            }
+                        }
+                    }
                 }
             }
+            flush();
+
+            if (active && a.write_forces) {
+                a.force[3 * info_i.w] = fx;
+                a.force[3 * info_i.w + 1] = fy;
+                a.force[3 * info_i.w + 2] = fz;
+            }
         }
-        __syncthreads();
-        for (int t = threadIdx.x; t < ni; t += blockDim.x) {
-            const int orig = a.sorted_info[ic + t].w;
-            if (orig < a.o_lo || orig >= a.o_hi || !a.write_forces) continue;
-            a.force[3 * orig] = sh_force[3 * t];
-            a.force[3 * orig + 1] = sh_force[3 * t + 1];
-            a.force[3 * orig + 2] = sh_force[3 * t + 2];
-        }
-        __syncthreads();
     }
 
     if (MODE == CELL_MODE_FULL) {
@@ -572,6 +561,9 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         g.length[d] = ctx->cell.h[4 * d];
         g.edge[d] = g.length[d] / (double)g.nc[d];
     }
+    if (ctx->n >= (int64_t)QUEUE_INDEX_MASK) {
+        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the cell list handles at most %u atoms per GPU", QUEUE_INDEX_MASK);
+    }
     int status = build_cells(ctx, g);
     if (status != 0) return status;
 
@@ -587,12 +579,12 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
 
     CellArgs a;
     a.g = g;
-    a.cell_lo = 0;
-    a.cell_hi = ncells;
+    a.ncells = ncells;
     a.o_lo = (int)o_lo;
     a.o_hi = (int)o_hi;
     a.cell_start = ctx->cell_start.ptr;
     a.sorted_pos = ctx->sorted_pos.ptr;
+    a.sorted_f32 = ctx->sorted_f32.ptr;
     a.sorted_info = ctx->sorted_info.ptr;
     a.bond_dist = ctx->bond_dist.ptr;
     a.nkinds = ctx->nkinds;
@@ -609,35 +601,33 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.write_forces = req.forces;
 
     const bool lj_only = do_pairs && !do_coulomb && ctx->single_lj;
+    a.lj_sigma2 = a.lj_epsilon24 = a.lj_epsilon4 = a.lj_cutoff2 = a.lj_shift = 0.0;
     if (lj_only) {
         const lumol_cuda_pair& p = ctx->host_pairs[0];
         a.lj_sigma2 = p.p[0] * p.p[0];
-        a.lj_epsilon = p.p[1];
+        a.lj_epsilon24 = 24.0 * p.p[1];
+        a.lj_epsilon4 = 4.0 * p.p[1];
         a.lj_cutoff2 = p.cutoff * p.cutoff;
         a.lj_shift = p.shift;
-    } else {
-        a.lj_sigma2 = a.lj_epsilon = a.lj_cutoff2 = a.lj_shift = 0.0;
     }
 
-    // candidates staged per pass: the mean neighbourhood plus a quarter, a multiple of 32
-    const double mean = 27.0 * (double)ctx->n / (double)ncells;
-    int tile = (int)(mean * 1.25) + 32;
-    tile = (tile + 31) / 32 * 32;
-    if (tile < 128) tile = 128;
-    const size_t per_entry = sizeof(double4) + sizeof(float4) + (lj_only ? 0 : sizeof(int4));
     const size_t table_bytes = lj_only ? 0 : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
-    const size_t budget = 64 * 1024;
     if (table_bytes > 100 * 1024) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many particle kinds (%d) for the shared pair table",
                          ctx->nkinds);
     }
-    if ((size_t)tile * per_entry > budget) tile = (int)(budget / per_entry) / 32 * 32;
-    if (tile > 16384) tile = 16384;  // queue entries are 16-bit
-    a.tile = tile;
-    const size_t smem = (size_t)tile * per_entry + table_bytes;
+    const size_t smem = (size_t)CELL_WARPS * CELL_QUEUE * 32 * sizeof(unsigned) + table_bytes;
+
+    // persistent warps: each walks a contiguous run of cells (neighbouring cells share 2/3 of their
+    // neighbourhood, which then comes from L1)
+    int blocks = ctx->sm_count * 6;
+    int warps = blocks * CELL_WARPS;
+    int cells_per_warp = (ncells + warps - 1) / warps;
+    if (cells_per_warp < 1) cells_per_warp = 1;
+    blocks = (ncells + cells_per_warp * CELL_WARPS - 1) / (cells_per_warp * CELL_WARPS);
+    a.cells_per_warp = cells_per_warp;
 
     const bool full = req.energy || req.virial;
-    const int blocks = ncells;
     LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)blocks * CELL_NV));
     a.partials = ctx->partials.ptr;
 
