@@ -42,8 +42,8 @@ BYTES_PER_ATOM_SORT = 100.0
 def parse_args():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=200)
-    parser.add_argument("--warmup", type=int, default=20)
+    parser.add_argument("--steps", type=int, default=1000)
+    parser.add_argument("--warmup", type=int, default=50)
     parser.add_argument("--impl", default="native", choices=["native", "reference"])
     parser.add_argument("--workload", default="lj", choices=["lj", "spce"])
     parser.add_argument("--lattice", default="128x128x64", help="lattice points per axis (lj) or molecules per axis (spce)")
@@ -263,6 +263,7 @@ def main():
     _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, args.warmup))
     barrier()
     _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
+    rebuilds_before_timed = int(device.stats().neighbor_rebuilds)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -276,6 +277,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     stats = device.stats()
     launches = int(stats.kernel_launches)
+    rebuilds_timed = int(stats.neighbor_rebuilds) - rebuilds_before_timed
     value = n * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------
@@ -324,6 +326,7 @@ def main():
     propagator.setup(system)
     _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, 2))
     _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
+    rebuilds_before_profile = int(device.stats().neighbor_rebuilds)
     _ffi.check(ctx, lib.lumol_cuda_set_profiling(ctx, 1))
     _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, profile_steps))
     _ffi.check(ctx, lib.lumol_cuda_set_profiling(ctx, 0))
@@ -354,7 +357,7 @@ def main():
     if pair_ms:
         achieved = pair_flops / (pair_ms * 1e-3) / 1e12
         roofline_pair = {
-            "kernel": "cell_pairs_kernel" if counts.neighbor_path == 1 else "allpairs_kernel", "bound": "fp64",
+            "kernel": "list_force_kernel" if counts.neighbor_path == 1 else "allpairs_kernel", "bound": "fp64",
             "achieved": achieved, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value,
             "peak_source": "measured live: dependent-free DFMA chains on every SM (lumol_cuda_measure_fp64_peak); "
                            "MEASURED_PEAKS.json has no FP64 entry",
@@ -380,11 +383,14 @@ def main():
             "peak_source": hbm_source, "ms_per_step": total_ms, "bytes_per_atom_step": BYTES_PER_ATOM_VV,
         }
     if profile.neighbor_launches:
-        total_ms = profile.neighbor_ms / (profile.neighbor_launches / 6.0)
-        achieved = BYTES_PER_ATOM_SORT * n / (total_ms * 1e-3) / 1e9
-        roofline_extra["cell_sort"] = {
+        # per step: refresh of the sorted positions (116 B/atom) plus the amortised rebuilds (flag-guarded kernels)
+        total_ms = profile.neighbor_ms / profile_steps
+        achieved = 116.0 * n / (total_ms * 1e-3) / 1e9
+        roofline_extra["neighbor_list"] = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "peak_source": hbm_source, "ms_per_build": total_ms, "bytes_per_atom": BYTES_PER_ATOM_SORT,
+            "peak_source": hbm_source, "ms_per_step": total_ms, "bytes_per_atom_step": 116.0,
+            "rebuilds_in_profiled_steps": int(profile.neighbor_rebuilds - rebuilds_before_profile),
+            "skin_A": profile.neighbor_skin,
         }
     dominant = roofline_pair
     if "ewald_kspace" in roofline_extra and kspace_ms and pair_ms and profile.kspace_ms > profile.pair_ms:
@@ -404,6 +410,7 @@ def main():
         "parallelism": f"{world} x B200, atoms in contiguous blocks per rank, replicated positions" if world > 1 else "1 x B200",
         "neighbor_path": "cell list" if counts.neighbor_path == 1 else "all-pairs",
         "cells": [int(c) for c in counts.ncells],
+        "neighbor_list": {"skin_A": counts.neighbor_skin, "rebuilds_in_timed_steps": rebuilds_timed},
         "l2": f"working set {bytes_resident / 1e6:.0f} MB per rank is larger than the 126 MB L2; no explicit flush",
     })
     result = {

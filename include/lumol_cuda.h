@@ -181,6 +181,8 @@ typedef struct {
     double comm_ms;
     double pair_count;         /* pairs inside their cut-off at the last energy/virial evaluation (each once) */
     double coulomb_pair_count; /* same for the coulomb real-space / Wolf term */
+    int64_t neighbor_rebuilds; /* neighbour-list rebuilds since the context was created */
+    double neighbor_skin;      /* skin in use (may be smaller than requested in small boxes) */
 } lumol_cuda_stats;
 
 /* ---- lifetime ----------------------------------------------------------------------------------- */
@@ -278,6 +280,10 @@ int32_t lumol_cuda_get_stats(lumol_cuda_context* ctx, lumol_cuda_stats* stats);
 int32_t lumol_cuda_reset_stats(lumol_cuda_context* ctx);
 /* Force the neighbour search path: -1 automatic, 0 all-pairs, 1 cell list (error when a cell edge has < 3 cells). */
 int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t path);
+/* Verlet skin of the neighbour list (default 1 A): the list is rebuilt, on the device, when an atom has moved more
+ * than skin / 2 since the last build.  Results do not depend on it: every listed pair is re-tested against its
+ * cut-off in FP64 at every evaluation. */
+int32_t lumol_cuda_set_neighbor_skin(lumol_cuda_context* ctx, double skin);
 /* cudaStream_t the context launches on, for event timing by the harness. */
 void* lumol_cuda_stream(lumol_cuda_context* ctx);
 int32_t lumol_cuda_synchronize(lumol_cuda_context* ctx);

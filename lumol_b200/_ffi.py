@@ -98,6 +98,8 @@ class Stats(ctypes.Structure):
         ("comm_ms", ctypes.c_double),
         ("pair_count", ctypes.c_double),
         ("coulomb_pair_count", ctypes.c_double),
+        ("neighbor_rebuilds", ctypes.c_int64),
+        ("neighbor_skin", ctypes.c_double),
     ]
 
 
@@ -153,6 +155,7 @@ SIGNATURES = {
     "lumol_cuda_get_stats": (_c.c_int32, [_ctx, _c.POINTER(Stats)]),
     "lumol_cuda_reset_stats": (_c.c_int32, [_ctx]),
     "lumol_cuda_set_neighbor_path": (_c.c_int32, [_ctx, _c.c_int32]),
+    "lumol_cuda_set_neighbor_skin": (_c.c_int32, [_ctx, _c.c_double]),
     "lumol_cuda_stream": (_c.c_void_p, [_ctx]),
     "lumol_cuda_synchronize": (_c.c_int32, [_ctx]),
     "lumol_cuda_measure_fp64_peak": (_c.c_int32, [_ctx, _dp]),

@@ -89,6 +89,7 @@ extern "C" int32_t lumol_cuda_destroy(lumol_cuda_context* ctx) {
     c->angles.release(); c->dihedrals.release(); c->kindex.release(); c->kenergy.release(); c->kvirial.release();
     c->rho.release(); c->rho_partial.release(); c->cell_of.release(); c->cell_count.release();
     c->cell_start.release(); c->order.release(); c->sorted_pos.release(); c->sorted_f32.release(); c->sorted_info.release();
+    c->nl_flags.release(); c->nlist.release(); c->ncount.release(); c->xref.release(); c->rel0.release();
     c->scan_scratch.release(); c->partials.release(); c->reduce_scratch.release(); c->results.release();
     c->csvr_noise_dev.release();
     if (c->host_results) cudaFreeHost(c->host_results);
@@ -179,6 +180,7 @@ static int reset_molecules(Context* c) {
     c->nmol = n;
     c->max_mol_size = 1;
     c->has_molecules = false;
+    c->structure_generation++;
     return 0;
 }
 
@@ -191,6 +193,7 @@ extern "C" int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, 
     }
     const bool resized = n != c->n;
     c->n = n;
+    c->structure_generation++;
     // blocks of a multi-GPU all-gather are padded to equal size: keep room for nranks * chunk atoms
     const size_t padded = (size_t)n + 64 * 3 + 8;
     LUMOL_CUDA_CHECK(c, c->position.reserve(3 * padded));
@@ -325,6 +328,7 @@ extern "C" int32_t lumol_cuda_set_molecules(lumol_cuda_context* ctx, int64_t nmo
     c->nmol = nmol;
     c->max_mol_size = max_size;
     c->has_molecules = true;
+    c->structure_generation++;
     return LUMOL_CUDA_SUCCESS;
 }
 
@@ -380,6 +384,7 @@ extern "C" int32_t lumol_cuda_set_pairs(lumol_cuda_context* ctx, int32_t nkinds,
     }
     c->single_lj = single_lj;
     c->nkinds = nkinds;
+    c->structure_generation++;
     c->host_pairs.assign(pairs, pairs + count);
     LUMOL_CUDA_CHECK(c, c->pairs.reserve(count + 1));
     if (count > 0) {
@@ -504,6 +509,7 @@ extern "C" int32_t lumol_cuda_set_dihedrals(lumol_cuda_context* ctx, int64_t n, 
 
 extern "C" int32_t lumol_cuda_set_coulomb_none(lumol_cuda_context* ctx) {
     CTX_OR_FAIL(ctx);
+    if (c->coulomb.kind != 0) c->structure_generation++;
     c->coulomb = CoulombView{};
     c->kmax = 0;
     return LUMOL_CUDA_SUCCESS;
@@ -529,6 +535,7 @@ extern "C" int32_t lumol_cuda_set_coulomb_ewald(lumol_cuda_context* ctx, double 
     if (c->coulomb.kind != 1 || c->coulomb.alpha != alpha || c->kmax != kmax) {
         c->ewald_generation = ~0ull;  // new factors
     }
+    if (c->coulomb.kind != 1 || c->coulomb.rc != cutoff) c->structure_generation++;
     c->coulomb = v;
     c->kmax = kmax;
     return LUMOL_CUDA_SUCCESS;
@@ -549,6 +556,7 @@ extern "C" int32_t lumol_cuda_set_coulomb_wolf(lumol_cuda_context* ctx, double c
     const double alpha_cutoff_2 = alpha_cutoff * alpha_cutoff;
     v.wolf_energy_constant = std::erfc(alpha_cutoff) / cutoff;
     v.wolf_force_constant = std::erfc(alpha_cutoff) / (cutoff * cutoff) + FRAC_2_SQRT_PI * v.alpha * std::exp(-alpha_cutoff_2) / cutoff;
+    if (c->coulomb.kind != 2 || c->coulomb.rc != cutoff) c->structure_generation++;
     c->coulomb = v;
     c->kmax = 0;
     return LUMOL_CUDA_SUCCESS;
@@ -694,6 +702,14 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
                                             cudaMemcpyDeviceToHost, c->stream));
     }
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->path == 1) {
+        int rebuilds = 0, overflow = 0;
+        status = neighbor_list_status(c, &rebuilds, &overflow);
+        if (status) return status;
+        if (overflow) {
+            return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list capacity exceeded (strongly inhomogeneous density)");
+        }
+    }
     const double* r = c->host_results;
     if (req.energy || req.virial) {
         c->last_pair_count = r[RES_PAIR_COUNT];
@@ -903,6 +919,14 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
         if (status) return status;
     }
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->path == 1) {
+        int rebuilds = 0, overflow = 0;
+        int status = neighbor_list_status(c, &rebuilds, &overflow);
+        if (status) return status;
+        if (overflow) {
+            return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list capacity exceeded (strongly inhomogeneous density)");
+        }
+    }
     return LUMOL_CUDA_SUCCESS;
 }
 
@@ -955,6 +979,11 @@ extern "C" int32_t lumol_cuda_get_stats(lumol_cuda_context* ctx, lumol_cuda_stat
     stats->comm_ms = c->clk_comm.ms;
     stats->pair_count = c->last_pair_count;
     stats->coulomb_pair_count = c->last_coulomb_pair_count;
+    int rebuilds = 0, overflow = 0;
+    int status = neighbor_list_status(c, &rebuilds, &overflow);
+    if (status) return status;
+    stats->neighbor_rebuilds = rebuilds;
+    stats->neighbor_skin = c->skin_effective;
     return LUMOL_CUDA_SUCCESS;
 }
 
@@ -969,6 +998,15 @@ extern "C" int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t
     CTX_OR_FAIL(ctx);
     if (path < -1 || path > 1) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "neighbour path must be -1, 0 or 1");
     c->forced_path = path;
+    c->structure_generation++;
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_set_neighbor_skin(lumol_cuda_context* ctx, double skin) {
+    CTX_OR_FAIL(ctx);
+    if (!(skin >= 0.0)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "the neighbour-list skin must be >= 0");
+    c->skin = skin;
+    c->structure_generation++;
     return LUMOL_CUDA_SUCCESS;
 }
 

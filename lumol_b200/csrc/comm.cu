@@ -151,5 +151,6 @@ extern "C" int32_t lumol_cuda_comm_init(lumol_cuda_context* ctx, int32_t nranks,
     NCCL_CHECK(c, g_nccl.comm_init_rank(&c->comm->comm, nranks, uid, rank));
     c->nranks = nranks;
     c->rank = rank;
+    c->structure_generation++;
     return LUMOL_CUDA_SUCCESS;
 }

@@ -147,6 +147,17 @@ struct Context {
     int forced_path = -1;
     int path = 0;
     int ncell[3] = {0, 0, 0};
+    double skin = 1.0;             // Verlet skin in Angstrom; rebuild when an atom moved more than skin / 2
+    double skin_effective = 0.0;   // what fits in the box
+    bool list_valid = false;
+    bool flags_initialised = false;
+    uint64_t list_signature = 0;
+    uint64_t structure_generation = 0;  // bumped by every change the list depends on besides positions
+    DeviceBuffer<int> nl_flags;         // rebuild flag, overflow flag, rebuild counter
+    DeviceBuffer<unsigned> nlist;       // transposed neighbour list: entry k of atom i at [k * stride + i]
+    DeviceBuffer<int> ncount;
+    DeviceBuffer<double> xref;          // positions at the last rebuild, original order
+    DeviceBuffer<double4> rel0;         // cell-relative positions at the last rebuild, sorted order
     DeviceBuffer<int> cell_of, cell_count, cell_start, order;
     DeviceBuffer<double4> sorted_pos;  // x, y, z relative to the centre of the own cell, charge
     DeviceBuffer<float4> sorted_f32;   // the same position in FP32
@@ -246,6 +257,7 @@ int launch_reduce(Context* ctx, int nblocks, int nvalues, int first_slot);      
 int launch_pairs_allpairs(Context* ctx, const ComputeRequest& req);                              // pairs_allpairs.cu
 int launch_pairs_cells(Context* ctx, const ComputeRequest& req);                                 // pairs_cells.cu
 int choose_neighbor_path(Context* ctx, double cutoff);                                           // pairs_cells.cu
+int neighbor_list_status(Context* ctx, int* rebuilds, int* overflow);                            // pairs_cells.cu
 int launch_coulomb_self(Context* ctx);                                                           // pairs_allpairs.cu
 int launch_molecule_com(Context* ctx);                                                           // pairs_allpairs.cu
 int launch_bonded(Context* ctx, const ComputeRequest& req);                                      // bonded.cu

@@ -1,35 +1,37 @@
-// Cell-list pair path: counting sort of the atoms into cells of edge >= the largest cut-off, then a sweep of
-// the 27 neighbour cells of every home cell.  The reference has no neighbour search at all: this
-// replaces the O(N^2) loops of
+// Cell-list / Verlet-list pair path for boxes with at least three (cut-off + skin) lengths per edge.
+// The reference has no neighbour search at all: this replaces the O(N^2) loops of
 //   Forces::compute        sys/compute.rs:37-55
 //   EnergyEvaluator::pairs sys/energy.rs:47-59
 //   AtomicVirial::compute  sys/compute.rs:202-216
 //   Ewald real space       energy/global/ewald.rs:430-530
 //   Wolf                   energy/global/wolf.rs:177-283
-// by an O(N) sweep that visits exactly the same pairs (every pair with r below the cut-off lies in the
-// 27-cell neighbourhood when each edge holds at least three cells).
+// by an O(N) evaluation over exactly the same pairs: every listed pair is still tested against its cut-off in
+// FP64 at every evaluation; the list only bounds which pairs can pass.
 //
-// Data layout in HBM (rebuilt every evaluation from the positions in original order):
-//   sorted_pos  double4 (x, y, z, q): position RELATIVE TO THE CENTRE OF THE ATOM'S OWN CELL (the wrap into the
-//               cell uses the floor convention of UnitCell::wrap_vector, cells.rs:263-279) and the charge;
-//   sorted_f32  float4: the same relative position in FP32, for the pre-filter;
-//   sorted_info int4 (kind, first atom of the molecule, bond-distance row, original index);
-//   cell_start  exclusive scan of the cell populations; cells in z-major order, atoms of one cell contiguous and
-//               ordered by original index, so the sort is deterministic (every rank derives the same order).
-// With cell-relative coordinates the separation of atom i in home cell h and atom j in the neighbour cell
-// h + (a, b, c) is (x_i - (a, b, c) * edge) - x_j whatever the periodic wrap of the cell index, so the kernel
-// needs no image logic at all and keeps full relative precision in arbitrarily large boxes.
-//
-// Pair kernel: one lane per atom i, one warp per home cell (cells above 32 atoms take several passes), each warp
-// walking its own contiguous range of cells so that successive home cells reuse their neighbourhoods from L1.
-//   phase 1 (FP32 / integer pipes): the warp streams the candidates of the 27 neighbour cells; all lanes read
-//     the same candidate (a broadcast load), each lane tests it against its own atom with an enlarged FP32
-//     cut-off and appends survivors to its private queue in shared memory;
-//   phase 2 (FP64 pipe): every lane walks its queue: gathers the FP64 position, applies the exact r < rc test
-//     and evaluates the pair.  The queue is flushed whenever a lane could overflow.
-// Forces are accumulated in registers by the lane that owns the atom: no atomics, no shuffles; each pair is
-// evaluated from both sides, energies/virials are taken from the side with the larger sorted index.
+// Rebuild (only when some atom moved more than skin / 2 since the last one; decided on the device, no host
+// round trip: the rebuild kernels are launched every time and return at once when the flag is clear):
+//   1. counting sort of the atoms into cells of edge >= cut-off + skin (z-major cells, atoms of a cell
+//      contiguous and ordered by original index, so every rank of a multi-GPU run derives the same order);
+//   2. per atom, in cell order ("sorted index"):
+//        sorted_pos  double4 (x, y, z, q): position RELATIVE TO THE CENTRE OF THE ATOM'S CELL + charge
+//        sorted_f32  float4: the same position in FP32 (pre-filter of the list build)
+//        sorted_info int4 (kind, first atom of the molecule, bond-distance row, original index)
+//      With cell-relative coordinates the separation of atom i in cell h and atom j in cell h + (a, b, c) is
+//      (x_i - (a, b, c) * edge) - x_j whatever the periodic wrap of the cell index: no image logic in the
+//      kernels, and full relative precision in arbitrarily large boxes;
+//   3. list build: one lane per atom, one warp per home cell; the warp streams the 27 neighbour cells, every
+//      lane tests the broadcast candidate against its own atom in FP32 with an enlarged radius and appends
+//      survivors to its column of the transposed list nlist[k * stride + i] = (offset code << 26) | j.
+// Every evaluation:
+//   - positions in sorted order are refreshed as rel0 + (x - x_at_build), so an atom keeps the periodic image
+//     it had at build time, and the displacement is compared with skin / 2;
+//   - force kernel: one thread per atom walks its column (coalesced across the warp), gathers the FP64
+//     position of each neighbour (software-pipelined one entry ahead), applies the exact r < rc test and
+//     accumulates the force in registers: no atomics, no shuffles.  Each pair is evaluated from both sides;
+//     energies / virials are taken from the side with the larger sorted index.
 #include "context.hpp"
+
+#include <cstring>
 
 namespace lumol {
 
@@ -39,14 +41,23 @@ namespace lumol {
 
 constexpr int CELL_PATH_MIN_ATOMS = 3000;
 
-// Returns 1 when the cell list can (and should) be used, 0 for the all-pairs kernel; fills ctx->ncell.
+// Returns 1 when the cell list can (and should) be used, 0 for the all-pairs kernel, -1 when it was forced
+// but is impossible; fills ctx->ncell and ctx->skin_effective.
 int choose_neighbor_path(Context* ctx, double cutoff) {
     ctx->ncell[0] = ctx->ncell[1] = ctx->ncell[2] = 0;
     bool possible = ctx->cell.shape == LUMOL_CUDA_CELL_ORTHORHOMBIC && cutoff > 0.0;
     if (possible) {
         const double lengths[3] = {ctx->cell.h[0], ctx->cell.h[4], ctx->cell.h[8]};
+        // the skin shrinks when the box cannot hold three (cut-off + skin) lengths per edge
+        double skin = ctx->skin;
         for (int d = 0; d < 3; d++) {
-            double nc = floor(lengths[d] / cutoff);
+            const double room = lengths[d] / 3.0 - cutoff;
+            if (room < skin) skin = room * 0.999;
+        }
+        if (skin < 0.0) skin = 0.0;
+        ctx->skin_effective = skin;
+        for (int d = 0; d < 3; d++) {
+            double nc = floor(lengths[d] / (cutoff + skin));
             if (nc > 1024.0) nc = 1024.0;
             ctx->ncell[d] = (int)nc;
             if (ctx->ncell[d] < 3) possible = false;
@@ -57,8 +68,11 @@ int choose_neighbor_path(Context* ctx, double cutoff) {
     return possible && ctx->n >= CELL_PATH_MIN_ATOMS ? 1 : 0;
 }
 
+// flags[0]: rebuild requested, flags[1]: a list column overflowed, flags[2]: number of rebuilds so far
+constexpr int FLAG_REBUILD = 0, FLAG_OVERFLOW = 1, FLAG_COUNT = 2;
+
 // ------------------------------------------------------------------------------------------------
-// counting sort
+// counting sort (every kernel returns immediately when no rebuild is requested)
 // ------------------------------------------------------------------------------------------------
 
 struct GridView {
@@ -79,9 +93,15 @@ __device__ __forceinline__ int cell_coordinate(double wrapped, double length, in
     return c;
 }
 
+__global__ void __launch_bounds__(256) cell_zero_kernel(int count, int* __restrict__ cell_count, const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) cell_count[k] = 0;
+}
+
 __global__ void __launch_bounds__(256)
     cell_assign_kernel(int n, GridView g, const double* __restrict__ pos, int* __restrict__ cell_of,
-                       int* __restrict__ slot_of, int* __restrict__ cell_count) {
+                       int* __restrict__ slot_of, int* __restrict__ cell_count, const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = cell_coordinate(wrap_coordinate(pos[3 * i], g.length[0]), g.length[0], g.nc[0]);
@@ -98,7 +118,6 @@ constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ int block_exclusive_scan(int value, int* shared, int& total) {
-    // inclusive warp scan
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int v = value;
 #pragma unroll
@@ -125,7 +144,9 @@ __device__ __forceinline__ int block_exclusive_scan(int value, int* shared, int&
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-    scan_blocks_kernel(int count, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ block_sums) {
+    scan_blocks_kernel(int count, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ block_sums,
+                       const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
     __shared__ int shared[32];
     const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     int items[SCAN_ITEMS];
@@ -145,7 +166,8 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) scan_sums_kernel(int nblocks, int* __restrict__ block_sums) {
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int nblocks, int* __restrict__ block_sums, const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
     __shared__ int shared[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -163,7 +185,9 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(int nblocks, int* __res
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-    scan_add_kernel(int count, int* __restrict__ out, const int* __restrict__ block_sums, int total_count) {
+    scan_add_kernel(int count, int* __restrict__ out, const int* __restrict__ block_sums, int total_count,
+                    const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
     const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     const int add = block_sums[blockIdx.x];
 #pragma unroll
@@ -176,7 +200,8 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 // first pass of the scatter: original indices grouped by cell, arrival order
 __global__ void __launch_bounds__(256)
     cell_group_kernel(int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
-                      const int* __restrict__ cell_start, int* __restrict__ grouped) {
+                      const int* __restrict__ cell_start, int* __restrict__ grouped, const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     grouped[cell_start[cell_of[i]] + slot_of[i]] = i;
@@ -195,12 +220,16 @@ struct ScatterArgs {
     const int* __restrict__ grouped;
     int* __restrict__ order;
     double4* __restrict__ sorted_pos;
+    double4* __restrict__ rel0;
     float4* __restrict__ sorted_f32;
     int4* __restrict__ sorted_info;
+    double* __restrict__ xref;
+    const int* __restrict__ flags;
 };
 
 // second pass: rank inside the cell = number of cell mates with a smaller original index
 __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
     const int i = a.grouped[s];
@@ -214,84 +243,167 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
     a.order[dst] = i;
     // position relative to the centre of the cell the atom was binned into
     const int cx = c % a.g.nc[0], cy = (c / a.g.nc[0]) % a.g.nc[1], cz = c / (a.g.nc[0] * a.g.nc[1]);
-    const double x = wrap_coordinate(a.pos[3 * i], a.g.length[0]) - ((double)cx + 0.5) * a.g.edge[0];
-    const double y = wrap_coordinate(a.pos[3 * i + 1], a.g.length[1]) - ((double)cy + 0.5) * a.g.edge[1];
-    const double z = wrap_coordinate(a.pos[3 * i + 2], a.g.length[2]) - ((double)cz + 0.5) * a.g.edge[2];
-    a.sorted_pos[dst] = make_double4(x, y, z, a.charge[i]);
+    const double px = a.pos[3 * i], py = a.pos[3 * i + 1], pz = a.pos[3 * i + 2];
+    const double x = wrap_coordinate(px, a.g.length[0]) - ((double)cx + 0.5) * a.g.edge[0];
+    const double y = wrap_coordinate(py, a.g.length[1]) - ((double)cy + 0.5) * a.g.edge[1];
+    const double z = wrap_coordinate(pz, a.g.length[2]) - ((double)cz + 0.5) * a.g.edge[2];
+    const double4 p = make_double4(x, y, z, a.charge[i]);
+    a.sorted_pos[dst] = p;
+    a.rel0[dst] = p;
     a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, 0.0f);
     a.sorted_info[dst] = make_int4((int)a.kind[i], a.mol_first[i], a.bd_row[i], i);
+    a.xref[3 * i] = px;
+    a.xref[3 * i + 1] = py;
+    a.xref[3 * i + 2] = pz;
 }
 
-static int build_cells(Context* ctx, const GridView& g) {
-    const int n = (int)ctx->n;
-    const int ncells = g.nc[0] * g.nc[1] * g.nc[2];
-    LUMOL_CUDA_CHECK(ctx, ctx->cell_of.reserve((size_t)2 * n));  // cell_of + slot_of
-    LUMOL_CUDA_CHECK(ctx, ctx->cell_count.reserve((size_t)ncells + 1));
-    LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)ncells + 1));
-    LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));  // order + grouped
-    LUMOL_CUDA_CHECK(ctx, ctx->sorted_pos.reserve((size_t)n));
-    LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
-    LUMOL_CUDA_CHECK(ctx, ctx->sorted_info.reserve((size_t)n));
-    const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)scan_blocks + 1));
+// Between rebuilds: positions in sorted order follow the atoms with the image they had at build time, and any
+// displacement above skin / 2 requests a rebuild.
+__global__ void __launch_bounds__(256)
+    list_update_kernel(int n, const int* __restrict__ order, const double* __restrict__ pos,
+                       const double* __restrict__ xref, const double4* __restrict__ rel0,
+                       double4* __restrict__ sorted_pos, double threshold2, int* __restrict__ flags) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = order[s];
+    const double dx = pos[3 * i] - xref[3 * i];
+    const double dy = pos[3 * i + 1] - xref[3 * i + 1];
+    const double dz = pos[3 * i + 2] - xref[3 * i + 2];
+    if (!(dx * dx + dy * dy + dz * dz <= threshold2)) flags[FLAG_REBUILD] = 1;  // also catches NaN
+    const double4 r = rel0[s];
+    sorted_pos[s] = make_double4(r.x + dx, r.y + dy, r.z + dz, r.w);
+}
 
-    int* cell_of = ctx->cell_of.ptr;
-    int* slot_of = ctx->cell_of.ptr + n;
-    int* order = ctx->order.ptr;
-    int* grouped = ctx->order.ptr + n;
-
-    ScopedClock clock(ctx, &ctx->clk_neighbor);
-    LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->cell_count.ptr, 0, ((size_t)ncells + 1) * sizeof(int), ctx->stream));
-    const int blocks = (n + 255) / 256;
-    cell_assign_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, ctx->position.ptr, cell_of, slot_of, ctx->cell_count.ptr);
-    scan_blocks_kernel<<<scan_blocks, SCAN_THREADS, 0, ctx->stream>>>(ncells, ctx->cell_count.ptr, ctx->cell_start.ptr,
-                                                                      ctx->scan_scratch.ptr);
-    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(scan_blocks, ctx->scan_scratch.ptr);
-    scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, ctx->stream>>>(ncells, ctx->cell_start.ptr, ctx->scan_scratch.ptr, n);
-    cell_group_kernel<<<blocks, 256, 0, ctx->stream>>>(n, cell_of, slot_of, ctx->cell_start.ptr, grouped);
-    ScatterArgs s;
-    s.n = n;
-    s.g = g;
-    s.pos = ctx->position.ptr;
-    s.charge = ctx->charge.ptr;
-    s.kind = ctx->kind.ptr;
-    s.mol_first = ctx->mol_first.ptr;
-    s.bd_row = ctx->bd_row.ptr;
-    s.cell_of = cell_of;
-    s.cell_start = ctx->cell_start.ptr;
-    s.grouped = grouped;
-    s.order = order;
-    s.sorted_pos = ctx->sorted_pos.ptr;
-    s.sorted_f32 = ctx->sorted_f32.ptr;
-    s.sorted_info = ctx->sorted_info.ptr;
-    cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
-    ctx->launches += 6;
-    ctx->clk_neighbor.launches += 6;
-    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
-    return 0;
+__global__ void list_finish_kernel(int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    flags[FLAG_REBUILD] = 0;
+    flags[FLAG_COUNT] += 1;
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair kernel
+// list build
 // ------------------------------------------------------------------------------------------------
 
-constexpr int CELL_THREADS = 128;
-constexpr int CELL_WARPS = CELL_THREADS / 32;
-constexpr int CELL_QUEUE = 96;   // queue slots per lane
-constexpr int CELL_CHUNK = 16;   // candidates streamed between two overflow checks
-constexpr int CELL_NV = 16;      // same layout as the all-pairs kernel
-constexpr int CELL_MODE_FORCES = 0;
-constexpr int CELL_MODE_FULL = 1;
-constexpr unsigned QUEUE_INDEX_MASK = (1u << 26) - 1u;
+constexpr unsigned LIST_INDEX_MASK = (1u << 26) - 1u;
+constexpr int BUILD_THREADS = 128;
+constexpr int BUILD_WARPS = BUILD_THREADS / 32;
 
-struct CellArgs {
+struct BuildArgs {
     GridView g;
     int ncells;
     int cells_per_warp;
-    int o_lo, o_hi;  // original-index range of the atoms this rank owns (forces are computed for those)
+    int o_lo, o_hi;  // original-index range of the atoms this rank owns (lists are built for those)
+    int capacity;
+    size_t stride;
+    float radius2;  // (cut-off + skin)^2, enlarged by 1e-4 relative
     const int* __restrict__ cell_start;
-    const double4* __restrict__ sorted_pos;
     const float4* __restrict__ sorted_f32;
+    const int4* __restrict__ sorted_info;
+    unsigned* __restrict__ nlist;
+    int* __restrict__ ncount;
+    int* __restrict__ flags;
+};
+
+__global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    __shared__ float offset32[27][3];
+    if (threadIdx.x < 27) {
+        const int t = threadIdx.x;
+        offset32[t][0] = (float)((double)((t % 3) - 1) * a.g.edge[0]);
+        offset32[t][1] = (float)((double)(((t / 3) % 3) - 1) * a.g.edge[1]);
+        offset32[t][2] = (float)((double)((t / 9) - 1) * a.g.edge[2]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int global_warp = blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5);
+    const int cell_lo = global_warp * a.cells_per_warp;
+    const int cell_hi = min(a.ncells, cell_lo + a.cells_per_warp);
+
+    for (int c = cell_lo; c < cell_hi; c++) {
+        const int hs = a.cell_start[c], he = a.cell_start[c + 1];
+        if (hs == he) continue;
+        const int cx = c % a.g.nc[0];
+        const int cy = (c / a.g.nc[0]) % a.g.nc[1];
+        const int cz = c / (a.g.nc[0] * a.g.nc[1]);
+        for (int base = hs; base < he; base += 32) {
+            const int s_i = base + lane;
+            bool active = s_i < he;
+            float xf = 1.0e18f, yf = 0.0f, zf = 0.0f;  // lanes without an owned atom sit far away
+            if (active) {
+                const int orig = a.sorted_info[s_i].w;
+                active = orig >= a.o_lo && orig < a.o_hi;
+                if (active) {
+                    const float4 f = a.sorted_f32[s_i];
+                    xf = f.x;
+                    yf = f.y;
+                    zf = f.z;
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (s_i < he) a.ncount[s_i] = 0;
+                continue;
+            }
+            unsigned* column = a.nlist + s_i;
+            int count = 0;
+            for (int row = 0; row < 9; row++) {
+                int ny = cy + (row % 3) - 1, nz = cz + (row / 3) - 1;
+                ny += ny < 0 ? a.g.nc[1] : 0;
+                ny -= ny >= a.g.nc[1] ? a.g.nc[1] : 0;
+                nz += nz < 0 ? a.g.nc[2] : 0;
+                nz -= nz >= a.g.nc[2] ? a.g.nc[2] : 0;
+                const int row_base = (nz * a.g.nc[1] + ny) * a.g.nc[0];
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const int code = row * 3 + dx;
+                    int nx = cx + dx - 1;
+                    nx += nx < 0 ? a.g.nc[0] : 0;
+                    nx -= nx >= a.g.nc[0] ? a.g.nc[0] : 0;
+                    const int s0 = a.cell_start[row_base + nx], s1 = a.cell_start[row_base + nx + 1];
+                    // atom i seen from the neighbour cell's centre
+                    const float xr = xf - offset32[code][0], yr = yf - offset32[code][1], zr = zf - offset32[code][2];
+                    const unsigned tag = (unsigned)code << 26;
+#pragma unroll 4
+                    for (int s_j = s0; s_j < s1; s_j++) {
+                        const float4 f = __ldg(a.sorted_f32 + s_j);  // same address in every lane: one broadcast
+                        const float ddx = xr - f.x, ddy = yr - f.y, ddz = zr - f.z;
+                        const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                        if (r2 < a.radius2 && s_j != s_i) {
+                            if (count < a.capacity) column[(size_t)count * a.stride] = tag + (unsigned)s_j;
+                            count++;
+                        }
+                    }
+                }
+            }
+            if (active) {
+                if (count > a.capacity) {
+                    a.flags[FLAG_OVERFLOW] = 1;
+                    count = a.capacity;
+                }
+                a.ncount[s_i] = count;
+            } else if (s_i < he) {
+                a.ncount[s_i] = 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// force kernel
+// ------------------------------------------------------------------------------------------------
+
+constexpr int NL_THREADS = 128;
+constexpr int NL_NV = 16;  // same layout as the all-pairs kernel
+constexpr int NL_MODE_FORCES = 0;
+constexpr int NL_MODE_FULL = 1;
+
+struct ForceArgs {
+    int n;
+    int o_lo, o_hi;
+    size_t stride;
+    double edge[3];
+    const unsigned* __restrict__ nlist;
+    const int* __restrict__ ncount;
+    const double4* __restrict__ sorted_pos;
     const int4* __restrict__ sorted_info;
     const unsigned char* __restrict__ bond_dist;
     int nkinds;
@@ -301,8 +413,7 @@ struct CellArgs {
     const double* __restrict__ table_force;
     CoulombView coulomb;
     int do_pairs, do_coulomb;
-    double cutoff2;     // (largest cut-off)^2: early-out of the general path
-    float cutoff2_f32;  // the same, enlarged by 1e-4 relative for the FP32 pre-filter
+    double cutoff2;  // (largest cut-off)^2: early-out of the general path
     // LJ fast path
     double lj_sigma2, lj_epsilon24, lj_epsilon4, lj_cutoff2, lj_shift;
     int write_forces;            // energy-only queries must not clobber the forces the integrator holds
@@ -310,13 +421,12 @@ struct CellArgs {
     double* __restrict__ partials;
 };
 
-// One queued candidate, FP64: exact cut-off test and pair evaluation for the lane's atom.
+// One listed neighbour, FP64: exact cut-off test and pair evaluation for the thread's atom.
 template <bool LJ_ONLY, int MODE>
-__device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const PairParams* __restrict__ sp,
-                                                   double xi, double yi, double zi, double qi, const int4& info_i,
-                                                   int s_i, int s_j, double& fx, double& fy, double& fz,
-                                                   double (&acc)[CELL_NV]) {
-    const double4 pj = a.sorted_pos[s_j];
+__device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const PairParams* __restrict__ sp, double xi,
+                                                  double yi, double zi, double qi, const int4& info_i, int s_i,
+                                                  int s_j, const double4& pj, double& fx, double& fy, double& fz,
+                                                  double (&acc)[NL_NV]) {
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double r2 = dx * dx + dy * dy + dz * dz;
     const bool count = s_j > s_i;
@@ -330,7 +440,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
             fx += fr * dx;
             fy += fr * dy;
             fz += fr * dz;
-            if (MODE == CELL_MODE_FULL && count) {
+            if (MODE == NL_MODE_FULL && count) {
                 acc[0] += a.lj_epsilon4 * (s6 * s6 - s6) - a.lj_shift;
                 acc[14] += 1.0;
                 acc[2] += fr * dx * dx;
@@ -359,7 +469,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
                 fx += fr * dx;
                 fy += fr * dy;
                 fz += fr * dz;
-                if (MODE == CELL_MODE_FULL && count) {
+                if (MODE == NL_MODE_FULL && count) {
                     acc[0] += scaling * e;
                     acc[14] += 1.0;
                     acc[2] += fr * dx * dx;
@@ -392,7 +502,7 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
                 fx += fr * dx;
                 fy += fr * dy;
                 fz += fr * dz;
-                if (MODE == CELL_MODE_FULL && count) {
+                if (MODE == NL_MODE_FULL && count) {
                     acc[1] += e;
                     acc[15] += 1.0;
                     acc[8] += fr * dx * dx;
@@ -408,16 +518,11 @@ __device__ __forceinline__ void evaluate_candidate(const CellArgs& a, const Pair
 }
 
 template <bool LJ_ONLY, int MODE>
-__global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(CellArgs a) {
+__global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned* queues = reinterpret_cast<unsigned*>(smem_raw);  // [warp][slot][lane]
-    PairParams* sp = reinterpret_cast<PairParams*>(queues + CELL_WARPS * CELL_QUEUE * 32);
-    __shared__ double offset64[27][3];  // (a, b, c) * edge for the 27 neighbour offsets
-    __shared__ float offset32[27][3];
-    __shared__ double scratch[32 * CELL_NV];
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    PairParams* sp = reinterpret_cast<PairParams*>(smem_raw);
+    __shared__ double offset64[27][3];  // (a, b, c) * edge for the 27 neighbour-cell offsets
+    __shared__ double scratch[32 * NL_NV];
 
     if (!LJ_ONLY) {
         const int words = (int)(sizeof(PairParams) / sizeof(double)) * a.nkinds * a.nkinds;
@@ -427,125 +532,56 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(CellArgs a) {
     }
     if (threadIdx.x < 27) {
         const int t = threadIdx.x;
-        const double ox = (double)((t % 3) - 1) * a.g.edge[0];
-        const double oy = (double)(((t / 3) % 3) - 1) * a.g.edge[1];
-        const double oz = (double)((t / 9) - 1) * a.g.edge[2];
-        offset64[t][0] = ox;
-        offset64[t][1] = oy;
-        offset64[t][2] = oz;
-        offset32[t][0] = (float)ox;
-        offset32[t][1] = (float)oy;
-        offset32[t][2] = (float)oz;
+        offset64[t][0] = (double)((t % 3) - 1) * a.edge[0];
+        offset64[t][1] = (double)(((t / 3) % 3) - 1) * a.edge[1];
+        offset64[t][2] = (double)((t / 9) - 1) * a.edge[2];
     }
     __syncthreads();
 
-    unsigned* q = queues + warp * CELL_QUEUE * 32 + lane;  // slot k at q[k * 32]
-
-    double acc[CELL_NV];
+    double acc[NL_NV];
 #pragma unroll
-    for (int k = 0; k < CELL_NV; k++) acc[k] = 0.0;
+    for (int k = 0; k < NL_NV; k++) acc[k] = 0.0;
 
-    const int global_warp = blockIdx.x * CELL_WARPS + warp;
-    const int cell_lo = global_warp * a.cells_per_warp;
-    const int cell_hi = min(a.ncells, cell_lo + a.cells_per_warp);
+    const int s_i = blockIdx.x * NL_THREADS + threadIdx.x;
+    int4 info_i = make_int4(0, 0, 0, -1);
+    bool active = s_i < a.n;
+    if (active) {
+        info_i = a.sorted_info[s_i];
+        active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
+    }
+    if (active) {
+        const double4 pi = a.sorted_pos[s_i];
+        const int count = a.ncount[s_i];
+        const unsigned* column = a.nlist + s_i;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
 
-    for (int c = cell_lo; c < cell_hi; c++) {
-        const int hs = a.cell_start[c], he = a.cell_start[c + 1];
-        if (hs == he) continue;
-        const int cx = c % a.g.nc[0];
-        const int cy = (c / a.g.nc[0]) % a.g.nc[1];
-        const int cz = c / (a.g.nc[0] * a.g.nc[1]);
-
-        for (int base = hs; base < he; base += 32) {
-            // this lane's atom (lanes without an atom, or with an atom another rank owns, sit far away)
-            const int s_i = base + lane;
-            bool active = s_i < he;
-            int4 info_i = make_int4(0, 0, 0, -1);
-            double xi = 0.0, yi = 0.0, zi = 0.0, qi = 0.0;
-            if (active) {
-                info_i = a.sorted_info[s_i];
-                active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
-                const double4 pi = a.sorted_pos[s_i];
-                xi = pi.x;
-                yi = pi.y;
-                zi = pi.z;
-                qi = pi.w;
-            }
-            if (!__any_sync(0xffffffffu, active)) continue;
-            const float xf = active ? (float)xi : 1.0e18f, yf = (float)yi, zf = (float)zi;
-
-            double fx = 0.0, fy = 0.0, fz = 0.0;
-            // next free slot of this lane's queue as a 32-bit shared-memory address (slots are 128 bytes apart)
-            const unsigned queue_base = (unsigned)__cvta_generic_to_shared(q);
-            unsigned tail = queue_base;
-
-            // phase 2: walk the private queues (FP64)
-            auto flush = [&]() {
-                const int queued = (int)((tail - queue_base) >> 7);
-                const int longest = __reduce_max_sync(0xffffffffu, queued);
-                for (int k = 0; k < longest; k++) {
-                    if (k < queued) {
-                        const unsigned entry = q[k * 32];
-                        const int code = (int)(entry >> 26);
-                        const int s_j = (int)(entry & QUEUE_INDEX_MASK);
-                        if (s_j != s_i) {
-                            evaluate_candidate<LJ_ONLY, MODE>(a, sp, xi - offset64[code][0], yi - offset64[code][1],
-                                                              zi - offset64[code][2], qi, info_i, s_i, s_j, fx, fy, fz, acc);
-                        }
-                    }
-                }
-                tail = queue_base;
-            };
-
-            // phase 1: stream the 27 neighbour cells (FP32 pre-filter); rows of three cells along x
-            for (int row = 0; row < 9; row++) {
-                int ny = cy + (row % 3) - 1, nz = cz + (row / 3) - 1;
-                ny += ny < 0 ? a.g.nc[1] : 0;
-                ny -= ny >= a.g.nc[1] ? a.g.nc[1] : 0;
-                nz += nz < 0 ? a.g.nc[2] : 0;
-                nz -= nz >= a.g.nc[2] ? a.g.nc[2] : 0;
-                const int row_base = (nz * a.g.nc[1] + ny) * a.g.nc[0];
-#pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    const int code = row * 3 + dx;
-                    int nx = cx + dx - 1;
-                    nx += nx < 0 ? a.g.nc[0] : 0;
-                    nx -= nx >= a.g.nc[0] ? a.g.nc[0] : 0;
-                    const int s0 = a.cell_start[row_base + nx], s1 = a.cell_start[row_base + nx + 1];
-                    // atom i seen from the neighbour cell's centre
-                    const float xr = xf - offset32[code][0], yr = yf - offset32[code][1], zr = zf - offset32[code][2];
-                    const unsigned tag = (unsigned)code << 26;
-                    for (int chunk = s0; chunk < s1; chunk += CELL_CHUNK) {
-                        if (__any_sync(0xffffffffu, tail > queue_base + 128u * (CELL_QUEUE - CELL_CHUNK))) flush();
-                        const int stop = min(s1, chunk + CELL_CHUNK);
-#pragma unroll 4
-                        for (int s_j = chunk; s_j < stop; s_j++) {
-                            const float4 f = __ldg(a.sorted_f32 + s_j);  // same address in every lane: one broadcast
-                            const float ddx = xr - f.x, ddy = yr - f.y, ddz = zr - f.z;
-                            const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                            if (r2 < a.cutoff2_f32) {  // the atom itself passes too; phase 2 drops it
-                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(tail), "r"(tag + (unsigned)s_j) : "memory");
-                                tail += 128u;
-                            }
-                        }
-                    }
-                }
-            }
-            flush();
-
-            if (active && a.write_forces) {
-                a.force[3 * info_i.w] = fx;
-                a.force[3 * info_i.w + 1] = fy;
-                a.force[3 * info_i.w + 2] = fz;
-            }
+        // software pipeline: list entry two ahead, neighbour position one ahead
+        unsigned e1 = count > 0 ? column[0] : 0u;
+        unsigned e2 = count > 1 ? column[a.stride] : 0u;
+        double4 p1 = a.sorted_pos[e1 & LIST_INDEX_MASK];
+        for (int k = 0; k < count; k++) {
+            const unsigned entry = e1;
+            const double4 pj = p1;
+            e1 = e2;
+            if (k + 2 < count) e2 = column[(size_t)(k + 2) * a.stride];
+            if (k + 1 < count) p1 = a.sorted_pos[e1 & LIST_INDEX_MASK];
+            const int code = (int)(entry >> 26);
+            const int s_j = (int)(entry & LIST_INDEX_MASK);
+            evaluate_neighbor<LJ_ONLY, MODE>(a, sp, pi.x - offset64[code][0], pi.y - offset64[code][1],
+                                             pi.z - offset64[code][2], pi.w, info_i, s_i, s_j, pj, fx, fy, fz, acc);
+        }
+        if (a.write_forces) {
+            a.force[3 * info_i.w] = fx;
+            a.force[3 * info_i.w + 1] = fy;
+            a.force[3 * info_i.w + 2] = fz;
         }
     }
 
-    if (MODE == CELL_MODE_FULL) {
-        block_sum<CELL_NV>(acc, scratch);
+    if (MODE == NL_MODE_FULL) {
+        block_sum<NL_NV>(acc, scratch);
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int k = 0; k < CELL_NV; k++) a.partials[(size_t)blockIdx.x * CELL_NV + k] = acc[k];
+            for (int k = 0; k < NL_NV; k++) a.partials[(size_t)blockIdx.x * NL_NV + k] = acc[k];
         }
     }
 }
@@ -554,37 +590,159 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(CellArgs a) {
 // launcher
 // ------------------------------------------------------------------------------------------------
 
+__global__ void set_flag_kernel(int* flags, int index, int value) { flags[index] = value; }
+
+static uint64_t mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
 int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
+    const int n = (int)ctx->n;
+    if (ctx->n >= (int64_t)LIST_INDEX_MASK) {
+        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the neighbour list handles at most %u atoms per GPU", LIST_INDEX_MASK);
+    }
     GridView g;
     for (int d = 0; d < 3; d++) {
         g.nc[d] = ctx->ncell[d];
         g.length[d] = ctx->cell.h[4 * d];
         g.edge[d] = g.length[d] / (double)g.nc[d];
     }
-    if (ctx->n >= (int64_t)QUEUE_INDEX_MASK) {
-        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the cell list handles at most %u atoms per GPU", QUEUE_INDEX_MASK);
-    }
-    int status = build_cells(ctx, g);
-    if (status != 0) return status;
-
     const int ncells = g.nc[0] * g.nc[1] * g.nc[2];
     int64_t o_lo, o_hi;
     ctx->owned_range(ctx->n, o_lo, o_hi);
 
+    // the list covers every interaction family so that it does not depend on which parts are requested
+    double cutoff = ctx->any_pair ? ctx->max_pair_cutoff : 0.0;
+    if (ctx->coulomb.kind != 0 && ctx->coulomb.rc > cutoff) cutoff = ctx->coulomb.rc;
+    const double skin = ctx->skin_effective;
+    const double radius = cutoff + skin;
+
+    // ---- buffers ---------------------------------------------------------------------------------
+    const double volume = g.length[0] * g.length[1] * g.length[2];
+    const double mean_neighbors = 4.0 / 3.0 * PI * radius * radius * radius * (double)n / volume;
+    int capacity = (int)(2.0 * mean_neighbors) + 64;
+    capacity = (capacity + 7) / 8 * 8;
+    if (capacity > n) capacity = n;
+    const size_t stride = ((size_t)n + 31) / 32 * 32;
+    LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(8));
+    LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(stride * (size_t)capacity));
+    LUMOL_CUDA_CHECK(ctx, ctx->ncount.reserve(stride));
+    LUMOL_CUDA_CHECK(ctx, ctx->xref.reserve((size_t)3 * n));
+    LUMOL_CUDA_CHECK(ctx, ctx->rel0.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_of.reserve((size_t)2 * n));  // cell_of + slot_of
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_count.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));  // order + grouped
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_pos.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_info.reserve((size_t)n));
+    const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)scan_blocks + 1));
+    int* flags = ctx->nl_flags.ptr;
+    int* cell_of = ctx->cell_of.ptr;
+    int* slot_of = ctx->cell_of.ptr + n;
+    int* order = ctx->order.ptr;
+    int* grouped = ctx->order.ptr + n;
+
+    // ---- is the current list still describing this system? ------------------------------------------
+    uint64_t signature = mix(0x1234, (uint64_t)n);
+    signature = mix(signature, ctx->cell_generation);
+    signature = mix(signature, ctx->structure_generation);
+    uint64_t bits;
+    std::memcpy(&bits, &radius, sizeof(bits));
+    signature = mix(signature, bits);
+    signature = mix(signature, (uint64_t)o_lo * 1315423911ull + (uint64_t)o_hi);
+    signature = mix(signature, (uint64_t)capacity);
+    const bool reuse = ctx->list_valid && signature == ctx->list_signature;
+    const int blocks = (n + 255) / 256;
+    {
+        ScopedClock clock(ctx, &ctx->clk_neighbor);
+        if (!reuse) {
+            if (!ctx->flags_initialised) {
+                LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(flags, 0, 8 * sizeof(int), ctx->stream));
+                ctx->flags_initialised = true;
+            }
+            set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, 1);
+        } else {
+            const double half = 0.5 * skin;
+            list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
+                                                                ctx->sorted_pos.ptr, half * half, flags);
+        }
+        ctx->launches++;
+        ctx->clk_neighbor.launches++;
+
+        // ---- rebuild pipeline (no-ops while flags[FLAG_REBUILD] == 0) -----------------------------------
+        cell_zero_kernel<<<64, 256, 0, ctx->stream>>>(ncells + 1, ctx->cell_count.ptr, flags);
+        cell_assign_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, ctx->position.ptr, cell_of, slot_of, ctx->cell_count.ptr, flags);
+        scan_blocks_kernel<<<scan_blocks, SCAN_THREADS, 0, ctx->stream>>>(ncells, ctx->cell_count.ptr, ctx->cell_start.ptr,
+                                                                          ctx->scan_scratch.ptr, flags);
+        scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(scan_blocks, ctx->scan_scratch.ptr, flags);
+        scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, ctx->stream>>>(ncells, ctx->cell_start.ptr, ctx->scan_scratch.ptr, n, flags);
+        cell_group_kernel<<<blocks, 256, 0, ctx->stream>>>(n, cell_of, slot_of, ctx->cell_start.ptr, grouped, flags);
+        ScatterArgs s;
+        s.n = n;
+        s.g = g;
+        s.pos = ctx->position.ptr;
+        s.charge = ctx->charge.ptr;
+        s.kind = ctx->kind.ptr;
+        s.mol_first = ctx->mol_first.ptr;
+        s.bd_row = ctx->bd_row.ptr;
+        s.cell_of = cell_of;
+        s.cell_start = ctx->cell_start.ptr;
+        s.grouped = grouped;
+        s.order = order;
+        s.sorted_pos = ctx->sorted_pos.ptr;
+        s.rel0 = ctx->rel0.ptr;
+        s.sorted_f32 = ctx->sorted_f32.ptr;
+        s.sorted_info = ctx->sorted_info.ptr;
+        s.xref = ctx->xref.ptr;
+        s.flags = flags;
+        cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
+
+        BuildArgs b;
+        b.g = g;
+        b.ncells = ncells;
+        int build_blocks = ctx->sm_count * 8;
+        int warps = build_blocks * BUILD_WARPS;
+        b.cells_per_warp = (ncells + warps - 1) / warps;
+        if (b.cells_per_warp < 1) b.cells_per_warp = 1;
+        build_blocks = (ncells + b.cells_per_warp * BUILD_WARPS - 1) / (b.cells_per_warp * BUILD_WARPS);
+        b.o_lo = (int)o_lo;
+        b.o_hi = (int)o_hi;
+        b.capacity = capacity;
+        b.stride = stride;
+        b.radius2 = (float)(radius * radius * 1.0001);
+        b.cell_start = ctx->cell_start.ptr;
+        b.sorted_f32 = ctx->sorted_f32.ptr;
+        b.sorted_info = ctx->sorted_info.ptr;
+        b.nlist = ctx->nlist.ptr;
+        b.ncount = ctx->ncount.ptr;
+        b.flags = flags;
+        list_build_kernel<<<build_blocks, BUILD_THREADS, 0, ctx->stream>>>(b);
+        list_finish_kernel<<<1, 1, 0, ctx->stream>>>(flags);
+        ctx->launches += 9;
+        ctx->clk_neighbor.launches += 9;
+        LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    ctx->list_valid = true;
+    ctx->list_signature = signature;
+
+    // ---- forces ------------------------------------------------------------------------------------------
     const bool do_pairs = req.pairs && ctx->any_pair;
     const bool do_coulomb = req.coulomb && ctx->coulomb.kind != 0;
-    double cutoff = 0.0;
-    if (do_pairs) cutoff = ctx->max_pair_cutoff;
-    if (do_coulomb && ctx->coulomb.rc > cutoff) cutoff = ctx->coulomb.rc;
+    double active_cutoff = do_pairs ? ctx->max_pair_cutoff : 0.0;
+    if (do_coulomb && ctx->coulomb.rc > active_cutoff) active_cutoff = ctx->coulomb.rc;
 
-    CellArgs a;
-    a.g = g;
-    a.ncells = ncells;
+    ForceArgs a;
+    a.n = n;
     a.o_lo = (int)o_lo;
     a.o_hi = (int)o_hi;
-    a.cell_start = ctx->cell_start.ptr;
+    a.stride = stride;
+    for (int d = 0; d < 3; d++) a.edge[d] = g.edge[d];
+    a.nlist = ctx->nlist.ptr;
+    a.ncount = ctx->ncount.ptr;
     a.sorted_pos = ctx->sorted_pos.ptr;
-    a.sorted_f32 = ctx->sorted_f32.ptr;
     a.sorted_info = ctx->sorted_info.ptr;
     a.bond_dist = ctx->bond_dist.ptr;
     a.nkinds = ctx->nkinds;
@@ -595,8 +753,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.coulomb = ctx->coulomb;
     a.do_pairs = do_pairs;
     a.do_coulomb = do_coulomb;
-    a.cutoff2 = cutoff * cutoff;
-    a.cutoff2_f32 = (float)(cutoff * cutoff * 1.0001);
+    a.cutoff2 = active_cutoff * active_cutoff;
     a.force = ctx->force.ptr;
     a.write_forces = req.forces;
 
@@ -610,47 +767,48 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         a.lj_cutoff2 = p.cutoff * p.cutoff;
         a.lj_shift = p.shift;
     }
-
-    const size_t table_bytes = lj_only ? 0 : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
-    if (table_bytes > 100 * 1024) {
-        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many particle kinds (%d) for the shared pair table",
-                         ctx->nkinds);
+    const size_t smem = lj_only ? 0 : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
+    if (smem > 100 * 1024) {
+        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many particle kinds (%d) for the shared pair table", ctx->nkinds);
     }
-    const size_t smem = (size_t)CELL_WARPS * CELL_QUEUE * 32 * sizeof(unsigned) + table_bytes;
-
-    // persistent warps: each walks a contiguous run of cells (neighbouring cells share 2/3 of their
-    // neighbourhood, which then comes from L1)
-    int blocks = ctx->sm_count * 6;
-    int warps = blocks * CELL_WARPS;
-    int cells_per_warp = (ncells + warps - 1) / warps;
-    if (cells_per_warp < 1) cells_per_warp = 1;
-    blocks = (ncells + cells_per_warp * CELL_WARPS - 1) / (cells_per_warp * CELL_WARPS);
-    a.cells_per_warp = cells_per_warp;
-
     const bool full = req.energy || req.virial;
-    LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)blocks * CELL_NV));
+    const int force_blocks = (n + NL_THREADS - 1) / NL_THREADS;
+    LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)force_blocks * NL_NV));
     a.partials = ctx->partials.ptr;
 
     const void* kernel;
     if (lj_only) {
-        kernel = full ? (const void*)cell_pairs_kernel<true, CELL_MODE_FULL>
-                      : (const void*)cell_pairs_kernel<true, CELL_MODE_FORCES>;
+        kernel = full ? (const void*)list_force_kernel<true, NL_MODE_FULL> : (const void*)list_force_kernel<true, NL_MODE_FORCES>;
     } else {
-        kernel = full ? (const void*)cell_pairs_kernel<false, CELL_MODE_FULL>
-                      : (const void*)cell_pairs_kernel<false, CELL_MODE_FORCES>;
+        kernel = full ? (const void*)list_force_kernel<false, NL_MODE_FULL> : (const void*)list_force_kernel<false, NL_MODE_FORCES>;
     }
-    LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) {
+        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     {
         ScopedClock clock(ctx, &ctx->clk_pair);
         void* params[] = {&a};
-        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(blocks), dim3(CELL_THREADS), params, smem, ctx->stream));
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(force_blocks), dim3(NL_THREADS), params, smem, ctx->stream));
         ctx->launches++;
         ctx->clk_pair.launches++;
     }
     if (full) {
-        status = launch_reduce(ctx, blocks, CELL_NV, RES_E_PAIRS);
+        int status = launch_reduce(ctx, force_blocks, NL_NV, RES_E_PAIRS);
         if (status != 0) return status;
     }
+    return 0;
+}
+
+// Reads the device-side list counters (synchronises the stream).
+int neighbor_list_status(Context* ctx, int* rebuilds, int* overflow) {
+    *rebuilds = 0;
+    *overflow = 0;
+    if (ctx->nl_flags.ptr == nullptr || !ctx->flags_initialised) return 0;
+    int host[3] = {0, 0, 0};
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(host, ctx->nl_flags.ptr, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *overflow = host[FLAG_OVERFLOW];
+    *rebuilds = host[FLAG_COUNT];
     return 0;
 }
 

@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_ffi.Potential) == 48
     assert ctypes.sizeof(_ffi.Pair) == 16 + 8 * 10
     assert ctypes.sizeof(_ffi.Energy) == 64
-    assert ctypes.sizeof(_ffi.Stats) == 8 * 19
+    assert ctypes.sizeof(_ffi.Stats) == 8 * 21
 
 
 def test_no_cpu_fallback_without_device():
