@@ -21,7 +21,8 @@
 //      kernels, and full relative precision in arbitrarily large boxes;
 //   3. list build: one lane per atom, one warp per home cell; the warp streams the 27 neighbour cells, every
 //      lane tests the broadcast candidate against its own atom in FP32 with an enlarged radius and appends
-//      survivors to its column of the transposed list nlist[k * stride + i] = (offset code << 26) | j.
+//      survivors to its column of the list, entries (offset code << 26) | j, the columns of 32 consecutive atoms
+//      interleaved in one contiguous slab.
 // Every evaluation:
 //   - positions in sorted order are refreshed as rel0 + (x - x_at_build), so an atom keeps the periodic image
 //     it had at build time, and the displacement is compared with skin / 2;
@@ -343,7 +344,11 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                 if (s_i < he) a.ncount[s_i] = 0;
                 continue;
             }
-            unsigned* column = a.nlist + s_i;
+            // Entry k of atom i lives in 16-byte word k / 4 of its column; the columns of 32 consecutive atoms are
+            // interleaved word by word in one contiguous slab: word w of atom i is word (w * 32 + i % 32) of slab
+            // i / 32.  A warp of the force kernel therefore streams its slab front to back (DRAM-page and TLB
+            // friendly) with 512-byte coalesced reads.
+            unsigned* column = a.nlist + ((size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31)) * 4;
             int count = 0;
             for (int row = 0; row < 9; row++) {
                 int ny = cy + (row % 3) - 1, nz = cz + (row / 3) - 1;
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                         const float ddx = xr - f.x, ddy = yr - f.y, ddz = zr - f.z;
                         const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
                         if (r2 < a.radius2 && s_j != s_i) {
-                            if (count < a.capacity) column[(size_t)count * a.stride] = tag + (unsigned)s_j;
+                            if (count < a.capacity) column[(count >> 2) * 128 + (count & 3)] = tag + (unsigned)s_j;
                             count++;
                         }
                     }
@@ -380,6 +385,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                     count = a.capacity;
                 }
                 a.ncount[s_i] = count;
+                // the force kernel reads whole 16-byte words: pad the last one with a valid index
+                for (int k = count; (k & 3) != 0; k++) column[(k >> 2) * 128 + (k & 3)] = (unsigned)s_i;
             } else if (s_i < he) {
                 a.ncount[s_i] = 0;
             }
@@ -399,7 +406,7 @@ constexpr int NL_MODE_FULL = 1;
 struct ForceArgs {
     int n;
     int o_lo, o_hi;
-    size_t stride;
+    int capacity;
     double edge[3];
     const unsigned* __restrict__ nlist;
     const int* __restrict__ ncount;
@@ -421,6 +428,50 @@ struct ForceArgs {
     double* __restrict__ partials;
 };
 
+// 1 / x to full FP64 precision without the slow-path branch of the compiler's division: the hardware seed
+// (MUFU.RCP64H, ~2^-23 relative) followed by two Newton-Raphson steps (2^-46, then rounding-limited).
+// Only used where x is a squared distance already known to be normal and positive.
+__device__ __forceinline__ double reciprocal(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Lennard-Jones fast path, branch-free so that the four neighbours of a list word form four independent
+// dependency chains the scheduler can interleave (the FP64 pipe has a long latency and few warps are resident).
+template <int MODE>
+__device__ __forceinline__ void evaluate_lj(const ForceArgs& a, double xi, double yi, double zi, int s_i, int s_j,
+                                            bool listed, const double4& pj, double& fx, double& fy, double& fz,
+                                            double (&acc)[NL_NV]) {
+    const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const bool inside = listed && r2 < a.lj_cutoff2;
+    const double rinv2 = reciprocal(inside ? r2 : 1.0);
+    const double s2 = a.lj_sigma2 * rinv2;
+    const double s6 = s2 * s2 * s2;
+    // force(r) / r = -24 eps (s6 - 2 s6^2) / r^2 (functions.rs:85-88)
+    double fr = a.lj_epsilon24 * s6 * (2.0 * s6 - 1.0) * rinv2;
+    fr = inside ? fr : 0.0;
+    fx += fr * dx;
+    fy += fr * dy;
+    fz += fr * dz;
+    if (MODE == NL_MODE_FULL) {
+        const bool count = inside && s_j > s_i;
+        const double w = count ? fr : 0.0;
+        acc[0] += count ? a.lj_epsilon4 * (s6 * s6 - s6) - a.lj_shift : 0.0;
+        acc[14] += count ? 1.0 : 0.0;
+        acc[2] += w * dx * dx;
+        acc[3] += w * dx * dy;
+        acc[4] += w * dx * dz;
+        acc[5] += w * dy * dy;
+        acc[6] += w * dy * dz;
+        acc[7] += w * dz * dz;
+    }
+}
+
 // One listed neighbour, FP64: exact cut-off test and pair evaluation for the thread's atom.
 template <bool LJ_ONLY, int MODE>
 __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const PairParams* __restrict__ sp, double xi,
@@ -430,29 +481,6 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double r2 = dx * dx + dy * dy + dz * dz;
     const bool count = s_j > s_i;
-    if (LJ_ONLY) {
-        if (r2 < a.lj_cutoff2) {
-            const double rinv2 = 1.0 / r2;
-            const double s2 = a.lj_sigma2 * rinv2;
-            const double s6 = s2 * s2 * s2;
-            // force(r) / r = -24 eps (s6 - 2 s6^2) / r^2 (functions.rs:85-88)
-            const double fr = a.lj_epsilon24 * s6 * (2.0 * s6 - 1.0) * rinv2;
-            fx += fr * dx;
-            fy += fr * dy;
-            fz += fr * dz;
-            if (MODE == NL_MODE_FULL && count) {
-                acc[0] += a.lj_epsilon4 * (s6 * s6 - s6) - a.lj_shift;
-                acc[14] += 1.0;
-                acc[2] += fr * dx * dx;
-                acc[3] += fr * dx * dy;
-                acc[4] += fr * dx * dz;
-                acc[5] += fr * dy * dy;
-                acc[6] += fr * dy * dz;
-                acc[7] += fr * dz * dz;
-            }
-        }
-        return;
-    }
     if (!(r2 < a.cutoff2 * 1.0000000001)) return;
     const double r = sqrt(r2);
     const int4 info_j = a.sorted_info[s_j];
@@ -552,23 +580,54 @@ __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
     if (active) {
         const double4 pi = a.sorted_pos[s_i];
         const int count = a.ncount[s_i];
-        const unsigned* column = a.nlist + s_i;
         double fx = 0.0, fy = 0.0, fz = 0.0;
 
-        // software pipeline: list entry two ahead, neighbour position one ahead
-        unsigned e1 = count > 0 ? column[0] : 0u;
-        unsigned e2 = count > 1 ? column[a.stride] : 0u;
-        double4 p1 = a.sorted_pos[e1 & LIST_INDEX_MASK];
-        for (int k = 0; k < count; k++) {
-            const unsigned entry = e1;
-            const double4 pj = p1;
-            e1 = e2;
-            if (k + 2 < count) e2 = column[(size_t)(k + 2) * a.stride];
-            if (k + 1 < count) p1 = a.sorted_pos[e1 & LIST_INDEX_MASK];
-            const int code = (int)(entry >> 26);
-            const int s_j = (int)(entry & LIST_INDEX_MASK);
-            evaluate_neighbor<LJ_ONLY, MODE>(a, sp, pi.x - offset64[code][0], pi.y - offset64[code][1],
-                                             pi.z - offset64[code][2], pi.w, info_i, s_i, s_j, pj, fx, fy, fz, acc);
+        // The column is read four entries (one 16-byte word) at a time.  Software pipeline, per thread: the
+        // list word two iterations ahead and the four neighbour positions one iteration ahead are in flight
+        // while the current four neighbours are evaluated, so neither the HBM latency of the list nor the
+        // L1/L2 latency of the position gathers is exposed.
+        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
+        const int nwords = (count + 3) >> 2;
+        uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
+        uint4 wnext = nwords > 1 ? words[32] : make_uint4(0, 0, 0, 0);
+        double4 pcur[4], pnext[4];
+        {
+            const unsigned e[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) pcur[t] = a.sorted_pos[e[t] & LIST_INDEX_MASK];
+        }
+        // 32-bit shared-memory address of the offset table (one multiply-add per neighbour instead of a
+        // generic-pointer computation)
+        const unsigned offset_base = (unsigned)__cvta_generic_to_shared(&offset64[0][0]);
+        for (int w = 0; w < nwords; w++) {
+            uint4 wafter = make_uint4(0, 0, 0, 0);
+            if (w + 2 < nwords) wafter = words[(w + 2) * 32];
+            {
+                const unsigned e[4] = {wnext.x, wnext.y, wnext.z, wnext.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) pnext[t] = a.sorted_pos[e[t] & LIST_INDEX_MASK];
+            }
+            const unsigned entries[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const bool listed = 4 * w + t < count;  // the last word is padded
+                const unsigned address = offset_base + (entries[t] >> 26) * 24u;
+                double ox, oy, oz;
+                asm("ld.shared.f64 %0, [%1];" : "=d"(ox) : "r"(address));
+                asm("ld.shared.f64 %0, [%1+8];" : "=d"(oy) : "r"(address));
+                asm("ld.shared.f64 %0, [%1+16];" : "=d"(oz) : "r"(address));
+                const int s_j = (int)(entries[t] & LIST_INDEX_MASK);
+                if (LJ_ONLY) {
+                    evaluate_lj<MODE>(a, pi.x - ox, pi.y - oy, pi.z - oz, s_i, s_j, listed, pcur[t], fx, fy, fz, acc);
+                } else if (listed) {
+                    evaluate_neighbor<LJ_ONLY, MODE>(a, sp, pi.x - ox, pi.y - oy, pi.z - oz, pi.w, info_i, s_i, s_j,
+                                                     pcur[t], fx, fy, fz, acc);
+                }
+            }
+            wcur = wnext;
+            wnext = wafter;
+#pragma unroll
+            for (int t = 0; t < 4; t++) pcur[t] = pnext[t];
         }
         if (a.write_forces) {
             a.force[3 * info_i.w] = fx;
@@ -738,7 +797,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.n = n;
     a.o_lo = (int)o_lo;
     a.o_hi = (int)o_hi;
-    a.stride = stride;
+    a.capacity = capacity;
     for (int d = 0; d < 3; d++) a.edge[d] = g.edge[d];
     a.nlist = ctx->nlist.ptr;
     a.ncount = ctx->ncount.ptr;
