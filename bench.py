@@ -212,7 +212,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from lumol_b200 import _ffi, md
+    from lumol_b200 import _ffi, md, parallel
     from lumol_b200.device import device_for
 
     rank = int(os.environ.get("RANK", "0"))
@@ -231,15 +231,7 @@ def main():
     lib, ctx = device.lib, device.ctx
 
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buffer = (ctypes.c_uint8 * 128)()
-            _ffi.check(None, lib.lumol_cuda_comm_unique_id(buffer))
-            uid = torch.tensor(list(buffer), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        buffer = (ctypes.c_uint8 * 128)(*uid.cpu().tolist())
-        _ffi.check(ctx, lib.lumol_cuda_comm_init(ctx, world, rank, buffer))
+        parallel.init_communicator(device, rank, world)
 
     stream = torch.cuda.ExternalStream(lib.lumol_cuda_stream(ctx))
 
@@ -250,11 +242,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(milliseconds):
-        if world == 1:
-            return milliseconds
-        value = torch.tensor([milliseconds], dtype=torch.float64, device="cuda")
-        dist.all_reduce(value, op=dist.ReduceOp.MAX)
-        return float(value.item())
+        return parallel.max_over_ranks(milliseconds, world)
 
     propagator = md.MolecularDynamics(TIMESTEP_FS)
     propagator.setup(system)

@@ -1,0 +1,96 @@
+"""Run under torchrun: compares the sharded evaluation (N ranks, NCCL) with a single-GPU evaluation of the same system.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+import lumol_b200 as lumol
+from lumol_b200 import _ffi, md, parallel, synthetic
+from lumol_b200.device import DeviceSystem
+
+
+def evaluate(system, rank, world, local_rank, sharded):
+    device = DeviceSystem(local_rank)
+    if sharded:
+        parallel.init_communicator(device, rank, world)
+    device.sync(system, velocities=True)
+    result = device.compute(forces=True, energy=True, virial=True)
+    return device, result
+
+
+def check(name, system, rank, world, local_rank):
+    single_device, single = evaluate(system, rank, world, local_rank, sharded=False)
+    sharded_device, sharded = evaluate(system, rank, world, local_rank, sharded=True)
+    scale = max(np.abs(single.forces).max(), 1e-300)
+    force_error = np.abs(sharded.forces - single.forces).max() / scale
+    terms = ("pairs", "pairs_tail", "bonds", "angles", "dihedrals", "coulomb_real", "coulomb_self", "coulomb_kspace")
+    magnitude = sum(abs(getattr(single.energy, t)) for t in terms)
+    energy_error = max(abs(getattr(sharded.energy, t) - getattr(single.energy, t)) for t in terms) / magnitude
+    virial_error = np.abs(sharded.virial - single.virial).max() / np.abs(single.virial).max()
+    assert force_error < 1e-12 and energy_error < 1e-12 and virial_error < 1e-12, (name, force_error, energy_error, virial_error)
+
+    # ten device-resident MD steps: sharded trajectory equals the single-GPU one to summation-order noise
+    def run(device):
+        lib, ctx = device.lib, device.ctx
+        _ffi.check(ctx, lib.lumol_cuda_md_setup(ctx, _ffi.INTEGRATOR_VELOCITY_VERLET, 1.0))
+        _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, 10))
+        x = np.zeros((system.size(), 3))
+        v = np.zeros((system.size(), 3))
+        _ffi.check(ctx, lib.lumol_cuda_get_positions(ctx, _ffi.as_double_pointer(x)))
+        _ffi.check(ctx, lib.lumol_cuda_get_velocities(ctx, _ffi.as_double_pointer(v)))
+        return x, v
+
+    x1, v1 = run(single_device)
+    xs, vs = run(sharded_device)
+    assert np.abs(xs - x1).max() < 1e-10, np.abs(xs - x1).max()
+    assert np.abs(vs - v1).max() < 1e-10 * max(np.abs(v1).max(), 1e-3)
+    if rank == 0:
+        print(f"{name}: {world} ranks vs 1 rank: forces {force_error:.1e} energy {energy_error:.1e} virial {virial_error:.1e}, "
+              f"path {sharded_device.stats().neighbor_path}, MD positions {np.abs(xs - x1).max():.1e}")
+    single_device.close()
+    sharded_device.close()
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import systems
+
+    lj = synthetic.lj_box(24, seed=3)  # 13824 atoms, cell list
+    synthetic.maxwell_boltzmann(lj, 120.0, seed=1)
+    check("lj-13824 (neighbour list)", lj, rank, world, local_rank)
+
+    small = synthetic.lj_box(8, seed=4)  # 512 atoms, all-pairs
+    synthetic.maxwell_boltzmann(small, 120.0, seed=2)
+    check("lj-512 (all-pairs)", small, rank, world, local_rank)
+
+    water = synthetic.spce_box(10, flexible=True)  # 3000 atoms: LJ + Ewald + bonds/angles
+    ewald = lumol.SharedEwald(lumol.Ewald(9.0, 6, 0.32))
+    ewald.set_restriction(lumol.PairRestriction.InterMolecular)
+    water.set_coulomb_potential(ewald)
+    synthetic.maxwell_boltzmann(water, 300.0, seed=5)
+    check("spce-3000 (list + Ewald + bonded)", water, rank, world, local_rank)
+
+    nacl = systems.md_nacl("wolf")
+    nacl.positions += np.random.Generator(np.random.PCG64(9)).uniform(-0.2, 0.2, nacl.positions.shape)  # perfect lattice: zero forces
+    synthetic.maxwell_boltzmann(nacl, 300.0, seed=6)
+    check("nacl-64 (all-pairs, Wolf)", nacl, rank, world, local_rank)
+    dist.barrier()
+    if rank == 0:
+        print("multi-GPU check ok")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
