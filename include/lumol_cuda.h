@@ -278,7 +278,9 @@ int32_t lumol_cuda_comm_init(lumol_cuda_context* ctx, int32_t nranks, int32_t ra
 int32_t lumol_cuda_set_profiling(lumol_cuda_context* ctx, int32_t enabled);
 int32_t lumol_cuda_get_stats(lumol_cuda_context* ctx, lumol_cuda_stats* stats);
 int32_t lumol_cuda_reset_stats(lumol_cuda_context* ctx);
-/* Force the neighbour search path: -1 automatic, 0 all-pairs, 1 cell list (error when a cell edge has < 3 cells). */
+/* Force the neighbour search path: -1 automatic, 0 all-pairs, 1 cell list (error when a cell edge has < 3 cells),
+ * 2 cell list whose Lennard-Jones blocks all keep the global list format (no shared-memory staging; used to
+ * cross-check the staged kernel). */
 int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t path);
 /* Verlet skin of the neighbour list (default 1 A): the list is rebuilt, on the device, when an atom has moved more
  * than skin / 2 since the last build.  Results do not depend on it: every listed pair is re-tested against its

@@ -163,6 +163,10 @@ struct Context {
     DeviceBuffer<float4> sorted_f32;   // the same position in FP32
     DeviceBuffer<int4> sorted_info;    // kind, mol_first, bd_row, original index
     DeviceBuffer<int> scan_scratch;
+    DeviceBuffer<int> sorted_cell;             // linear cell index, sorted order
+    DeviceBuffer<int4> blk_header, blk_entries;  // staging tables of the Lennard-Jones kernel (pairs_cells.cu)
+    DeviceBuffer<unsigned char> blk_map;       // staged slot -> entry number, per block
+    DeviceBuffer<unsigned short> self_local;   // staged slot of each atom inside its own block
 
     // ---- reductions ------------------------------------------------------------------------------
     DeviceBuffer<double> partials, reduce_scratch;

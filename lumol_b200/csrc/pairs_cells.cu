@@ -65,7 +65,7 @@ int choose_neighbor_path(Context* ctx, double cutoff) {
         }
     }
     if (ctx->forced_path == 0) return 0;
-    if (ctx->forced_path == 1) return possible ? 1 : -1;
+    if (ctx->forced_path >= 1) return possible ? 1 : -1;
     return possible && ctx->n >= CELL_PATH_MIN_ATOMS ? 1 : 0;
 }
 
@@ -94,8 +94,9 @@ __device__ __forceinline__ int cell_coordinate(double wrapped, double length, in
     return c;
 }
 
-__global__ void __launch_bounds__(256) cell_zero_kernel(int count, int* __restrict__ cell_count, const int* __restrict__ flags) {
+__global__ void __launch_bounds__(256) cell_zero_kernel(int count, int* __restrict__ cell_count, int* __restrict__ flags) {
     if (flags[FLAG_REBUILD] == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_kernel
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) cell_count[k] = 0;
 }
 
@@ -224,6 +225,7 @@ struct ScatterArgs {
     double4* __restrict__ rel0;
     float4* __restrict__ sorted_f32;
     int4* __restrict__ sorted_info;
+    int* __restrict__ sorted_cell;
     double* __restrict__ xref;
     const int* __restrict__ flags;
 };
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
     a.rel0[dst] = p;
     a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, 0.0f);
     a.sorted_info[dst] = make_int4((int)a.kind[i], a.mol_first[i], a.bd_row[i], i);
+    a.sorted_cell[dst] = c;
     a.xref[3 * i] = px;
     a.xref[3 * i + 1] = py;
     a.xref[3 * i + 2] = pz;
@@ -282,6 +285,153 @@ __global__ void list_finish_kernel(int* __restrict__ flags) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// staging tables
+// ------------------------------------------------------------------------------------------------
+//
+// The Lennard-Jones force kernel works on blocks of TB consecutive atoms of the cell order.  The atoms any of
+// them can interact with live in the 27-cell neighbourhoods of the block's home cells; the kernel copies those
+// once per evaluation into shared memory, in coordinates relative to the block's first cell with the periodic
+// shift already applied, and the list of a staged block holds 16-bit indices into that copy.  The inner loop
+// then has no image arithmetic and no global gathers at all (the previous version was bound by the L1 tag
+// stage: two scattered 32-byte global loads per neighbour and lane).
+//
+// Home cells of a block are the contiguous range [c0, c0 + K) of the x-fastest linear cell order, i.e. up to
+// a few row segments.  Segment g covers x in [xa, xa + len) of row r0 + g and brings the (len + 2) x 3 x 3
+// cells around it, enumerated plane by plane; entry index and staged offset are pure arithmetic of (c0, K),
+// so nothing needs searching.  A block whose neighbourhood does not fit (dense cells, sparse gas, tiny grids)
+// keeps the 32-bit global list format and takes the gather path inside the same kernel.
+
+constexpr int TB = 256;  // atoms per block of the force kernel
+constexpr int STAGE_MAX_ENTRIES = 160;
+constexpr int STAGE_MAX_SEGMENTS = 6;
+constexpr int STAGE_BYTES = 104 * 1024;             // shared memory of the staged copy: two blocks per SM
+constexpr int STAGE_ATOMS_MAX = STAGE_BYTES / 24;   // dummy slot included
+constexpr int STAGE_GROUP = 6;                      // staging loads in flight per thread
+constexpr int STAGE_ROUNDS = 18;                    // slots per thread, a multiple of STAGE_GROUP
+static_assert(STAGE_ROUNDS * TB >= STAGE_ATOMS_MAX && STAGE_ROUNDS % STAGE_GROUP == 0, "staging rounds");
+static_assert(STAGE_MAX_ENTRIES <= 256, "the slot map holds entry numbers in one byte");
+constexpr int FLAG_UNSTAGED = 3;                    // flags[3]: blocks of the last rebuild that were not staged
+
+struct BlockRows {
+    int c0, K, nx, r0, xa0, len0, nseg, nentries;
+
+    __host__ __device__ void init(int first_cell, int cells, int cells_x) {
+        c0 = first_cell;
+        K = cells;
+        nx = cells_x;
+        r0 = c0 / nx;
+        xa0 = c0 - r0 * nx;
+        len0 = min(nx - xa0, K);
+        const int rest = K - len0;
+        const int more = (rest + nx - 1) / nx;
+        nseg = 1 + more;
+        nentries = 9 * (len0 + 2);
+        if (more > 0) {
+            const int last = rest - (more - 1) * nx;
+            nentries += (more - 1) * 9 * (nx + 2) + 9 * (last + 2);
+        }
+    }
+    __host__ __device__ void segment(int g, int& xa, int& len, int& base) const {
+        if (g == 0) {
+            xa = xa0;
+            len = len0;
+            base = 0;
+        } else {
+            xa = 0;
+            len = min(nx, K - len0 - (g - 1) * nx);
+            base = 9 * (len0 + 2) + (g - 1) * 9 * (nx + 2);
+        }
+    }
+};
+
+struct TableArgs {
+    GridView g;
+    int n, nblocks;
+    int allow;            // 0: every block keeps the global format (general kernel)
+    int stage_atoms_max;  // shared-memory capacity of the force kernel in atoms, dummy slot included
+    const int* __restrict__ cell_start;
+    const int* __restrict__ sorted_cell;
+    int4* __restrict__ header;   // c0, K, entries (-1: not staged), staged atoms
+    int4* __restrict__ entries;  // first sorted index, offset | count << 16, shift x | shift y << 16, shift z
+    unsigned char* __restrict__ map;  // per block, per staged slot: entry number
+    size_t map_stride;
+    int* __restrict__ flags;
+};
+
+// one warp per block of TB atoms
+__global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int block = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (block >= a.nblocks) return;
+    const int s_first = block * TB, s_last = min(a.n, s_first + TB) - 1;
+    const int c_first = a.sorted_cell[s_first], c_last = a.sorted_cell[s_last];
+    BlockRows rows;
+    rows.init(c_first, c_last - c_first + 1, a.g.nc[0]);
+    bool staged = a.allow != 0 && rows.nseg <= STAGE_MAX_SEGMENTS && rows.nentries <= STAGE_MAX_ENTRIES;
+    int total = 1;  // slot 0 is the far-away dummy the padding entries point to
+    if (staged) {
+        const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
+        const int y0 = rows.r0 % ny, z0 = rows.r0 / ny;
+        for (int base = 0; base < rows.nentries; base += 32) {
+            const int e = base + lane;
+            int src = 0, count = 0, sx = 0, sy = 0, sz = 0;
+            if (e < rows.nentries) {
+                int g = 0, rem = e;
+                const int first = 9 * (rows.len0 + 2);
+                if (e >= first) {
+                    g = 1 + (e - first) / (9 * (nx + 2));
+                    rem = (e - first) - (g - 1) * 9 * (nx + 2);
+                }
+                int xa, len, seg_base;
+                rows.segment(g, xa, len, seg_base);
+                const int w = len + 2;
+                const int plane = rem / w, k = rem - plane * w;
+                const int r = rows.r0 + g;
+                const int y = r % ny, z = r / ny;
+                const int ux = xa - 1 + k, uy = y + (plane % 3) - 1, uz = z + (plane / 3) - 1;
+                const int ax = ux < 0 ? ux + nx : (ux >= nx ? ux - nx : ux);
+                const int ay = uy < 0 ? uy + ny : (uy >= ny ? uy - ny : uy);
+                const int az = uz < 0 ? uz + nz : (uz >= nz ? uz - nz : uz);
+                const int cell = (az * ny + ay) * nx + ax;
+                src = a.cell_start[cell];
+                count = a.cell_start[cell + 1] - src;
+                sx = ux - rows.xa0;
+                sy = uy - y0;
+                sz = uz - z0;
+            }
+            // exclusive scan of the counts over the warp
+            int scan = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, scan, o);
+                if (lane >= o) scan += t;
+            }
+            const int offset = total + scan - count;
+            total += __shfl_sync(0xffffffffu, scan, 31);
+            if (e < rows.nentries && offset + count <= 65535 && count <= 65535) {
+                a.entries[(size_t)block * STAGE_MAX_ENTRIES + e] =
+                    make_int4(src, offset | (count << 16), (sx & 0xffff) | (sy << 16), sz);
+            }
+        }
+        if (total > a.stage_atoms_max || total > 65535) staged = false;
+        __syncwarp();
+    }
+    if (staged) {
+        // slot -> entry map read by the staging loop of the force kernel
+        unsigned char* map = a.map + (size_t)block * a.map_stride;
+        for (int e = 0; e < rows.nentries; e++) {
+            const int4 entry = a.entries[(size_t)block * STAGE_MAX_ENTRIES + e];  // written by this warp
+            const int offset = entry.y & 0xffff, count = (int)((unsigned)entry.y >> 16);
+            for (int t = lane; t < count; t += 32) map[offset + t] = (unsigned char)e;
+        }
+    } else if (lane == 0 && a.allow != 0) {
+        atomicAdd(a.flags + FLAG_UNSTAGED, 1);
+    }
+    if (lane == 0) a.header[block] = make_int4(rows.c0, rows.K, staged ? rows.nentries : -1, total);
+}
+
+// ------------------------------------------------------------------------------------------------
 // list build
 // ------------------------------------------------------------------------------------------------
 
@@ -294,12 +444,14 @@ struct BuildArgs {
     int ncells;
     int cells_per_warp;
     int o_lo, o_hi;  // original-index range of the atoms this rank owns (lists are built for those)
-    int capacity;
-    size_t stride;
-    float radius2;  // (cut-off + skin)^2, enlarged by 1e-4 relative
+    int capacity;    // 32-bit entries per atom (a staged column holds as many 16-bit ones in half the space)
+    float radius2;   // (cut-off + skin)^2, enlarged by 1e-4 relative
     const int* __restrict__ cell_start;
     const float4* __restrict__ sorted_f32;
     const int4* __restrict__ sorted_info;
+    const int4* __restrict__ blk_header;
+    const int4* __restrict__ blk_entries;
+    unsigned short* __restrict__ self_local;
     unsigned* __restrict__ nlist;
     int* __restrict__ ncount;
     int* __restrict__ flags;
@@ -330,7 +482,25 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
             const int s_i = base + lane;
             bool active = s_i < he;
             float xf = 1.0e18f, yf = 0.0f, zf = 0.0f;  // lanes without an owned atom sit far away
+            // staging table of the lane's block (the lanes of one warp can sit in two blocks)
+            bool staged = false;
+            const int4* entries = a.blk_entries;
+            int entry_first = 0, entry_width = 0;
             if (active) {
+                const int block = s_i / TB;
+                const int4 header = a.blk_header[block];
+                staged = header.z >= 0;
+                if (staged) {
+                    BlockRows rows;
+                    rows.init(header.x, header.y, a.g.nc[0]);
+                    int xa, len, seg_base;
+                    rows.segment(c / a.g.nc[0] - rows.r0, xa, len, seg_base);
+                    entries += (size_t)block * STAGE_MAX_ENTRIES;
+                    entry_width = len + 2;
+                    entry_first = seg_base + (cx - xa);  // entry of offset code 0 (dx = -1, plane 0)
+                    a.self_local[s_i] =
+                        (unsigned short)((entries[entry_first + 4 * entry_width + 1].y & 0xffff) + (s_i - hs));
+                }
                 const int orig = a.sorted_info[s_i].w;
                 active = orig >= a.o_lo && orig < a.o_hi;
                 if (active) {
@@ -344,11 +514,12 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                 if (s_i < he) a.ncount[s_i] = 0;
                 continue;
             }
-            // Entry k of atom i lives in 16-byte word k / 4 of its column; the columns of 32 consecutive atoms are
-            // interleaved word by word in one contiguous slab: word w of atom i is word (w * 32 + i % 32) of slab
-            // i / 32.  A warp of the force kernel therefore streams its slab front to back (DRAM-page and TLB
-            // friendly) with 512-byte coalesced reads.
+            // The columns of 32 consecutive atoms form one contiguous slab of (capacity / 4) x 32 16-byte words,
+            // interleaved word by word: word w of atom i is word (w * 32 + i % 32) of slab i / 32, so that a
+            // warp of the force kernel streams its slab front to back with 512-byte coalesced reads.  A word
+            // holds 4 global entries (offset code << 26) | j, or 8 16-bit indices into the block's staged copy.
             unsigned* column = a.nlist + ((size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31)) * 4;
+            unsigned short* column16 = reinterpret_cast<unsigned short*>(column);
             int count = 0;
             for (int row = 0; row < 9; row++) {
                 int ny = cy + (row % 3) - 1, nz = cz + (row / 3) - 1;
@@ -366,14 +537,23 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                     const int s0 = a.cell_start[row_base + nx], s1 = a.cell_start[row_base + nx + 1];
                     // atom i seen from the neighbour cell's centre
                     const float xr = xf - offset32[code][0], yr = yf - offset32[code][1], zr = zf - offset32[code][2];
-                    const unsigned tag = (unsigned)code << 26;
+                    // what is stored for neighbour s_j: tag + s_j
+                    unsigned tag = (unsigned)code << 26;
+                    if (staged) tag = (unsigned)((entries[entry_first + row * entry_width + dx].y & 0xffff) - s0);
 #pragma unroll 4
                     for (int s_j = s0; s_j < s1; s_j++) {
                         const float4 f = __ldg(a.sorted_f32 + s_j);  // same address in every lane: one broadcast
                         const float ddx = xr - f.x, ddy = yr - f.y, ddz = zr - f.z;
                         const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
                         if (r2 < a.radius2 && s_j != s_i) {
-                            if (count < a.capacity) column[(count >> 2) * 128 + (count & 3)] = tag + (unsigned)s_j;
+                            if (count < a.capacity) {
+                                const unsigned value = tag + (unsigned)s_j;
+                                if (staged) {
+                                    column16[(count >> 3) * 256 + (count & 7)] = (unsigned short)value;
+                                } else {
+                                    column[(count >> 2) * 128 + (count & 3)] = value;
+                                }
+                            }
                             count++;
                         }
                     }
@@ -385,12 +565,77 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                     count = a.capacity;
                 }
                 a.ncount[s_i] = count;
-                // the force kernel reads whole 16-byte words: pad the last one with a valid index
-                for (int k = count; (k & 3) != 0; k++) column[(k >> 2) * 128 + (k & 3)] = (unsigned)s_i;
+                // the force kernel reads whole 16-byte words: pad the last one (global format: a valid index that
+                // fails the listed test; staged format: the dummy slot 0)
+                if (staged) {
+                    for (int k = count; (k & 7) != 0; k++) column16[(k >> 3) * 256 + (k & 7)] = 0;
+                } else {
+                    for (int k = count; (k & 3) != 0; k++) column[(k >> 2) * 128 + (k & 3)] = (unsigned)s_i;
+                }
             } else if (s_i < he) {
                 a.ncount[s_i] = 0;
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bank-aware order of the staged columns
+// ------------------------------------------------------------------------------------------------
+//
+// The staged copy is an array of (x, y, z) doubles, 24 bytes per atom: slot s sits in the 8-byte bank pairs
+// (3 s + c) mod 16, so two lanes of a half warp collide exactly when their slots are different and congruent
+// modulo 16.  In arrival order the 32 columns of a warp hit the banks at random (measured: 5.1 wavefronts per
+// LDS.64 instead of 2; the shared-memory pipe saturated long before the FP64 pipe).  The order of a column is
+// free, so every lane sorts its entries into 16 buckets by slot mod 16 and emits them round robin, lane l
+// starting at bucket l mod 16: while its buckets last, a half warp touches 16 different bank pairs at every
+// step.  An exhausted bucket is replaced by the next non-empty one (simulation: 2.9 wavefronts per LDS.64).
+
+constexpr int REORDER_THREADS = 32;
+
+__global__ void __launch_bounds__(REORDER_THREADS)
+    list_reorder_kernel(int n, int capacity, const int4* __restrict__ blk_header, const int* __restrict__ ncount,
+                        unsigned* __restrict__ nlist, const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    extern __shared__ unsigned short sorted[];  // entry p of thread t at [p * REORDER_THREADS + t]
+    __shared__ unsigned short cursor[16][REORDER_THREADS], last[16][REORDER_THREADS];
+    const int t = threadIdx.x;
+    const int s_i = blockIdx.x * REORDER_THREADS + t;
+    if (s_i >= n) return;
+    if (blk_header[s_i / TB].z < 0) return;  // global format: no shared-memory gathers
+    const int count = ncount[s_i];
+    unsigned short* column16 =
+        reinterpret_cast<unsigned short*>(nlist + ((size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31)) * 4);
+#pragma unroll
+    for (int b = 0; b < 16; b++) last[b][t] = 0;
+    for (int k = 0; k < count; k++) last[column16[(k >> 3) * 256 + (k & 7)] & 15][t]++;
+    int running = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        cursor[b][t] = (unsigned short)running;
+        running += last[b][t];
+        last[b][t] = (unsigned short)running;
+    }
+    // stable scatter into the buckets
+    for (int k = 0; k < count; k++) {
+        const unsigned short e = column16[(k >> 3) * 256 + (k & 7)];
+        const int position = cursor[e & 15][t]++;
+        sorted[position * REORDER_THREADS + t] = e;
+    }
+    // rewind, then emit round robin
+    running = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        cursor[b][t] = (unsigned short)running;
+        running = last[b][t];
+    }
+    int bucket = s_i & 15;
+    for (int k = 0; k < count; k++) {
+        int b = bucket;
+        while (cursor[b][t] == last[b][t]) b = (b + 1) & 15;  // some bucket is non-empty: k < count
+        const int position = cursor[b][t]++;
+        column16[(k >> 3) * 256 + (k & 7)] = sorted[position * REORDER_THREADS + t];
+        bucket = (bucket + 1) & 15;
     }
 }
 
@@ -422,7 +667,12 @@ struct ForceArgs {
     int do_pairs, do_coulomb;
     double cutoff2;  // (largest cut-off)^2: early-out of the general path
     // LJ fast path
-    double lj_sigma2, lj_epsilon24, lj_epsilon4, lj_cutoff2, lj_shift;
+    double lj_sigma2, lj_epsilon24, lj_epsilon48, lj_epsilon4, lj_cutoff2, lj_shift;
+    const int4* __restrict__ blk_header;
+    const int4* __restrict__ blk_entries;
+    const unsigned short* __restrict__ self_local;
+    const unsigned char* __restrict__ blk_map;
+    size_t map_stride;
     int write_forces;            // energy-only queries must not clobber the forces the integrator holds
     double* __restrict__ force;  // original order, n x 3
     double* __restrict__ partials;
@@ -459,8 +709,9 @@ __device__ __forceinline__ void evaluate_lj(const ForceArgs& a, double xi, doubl
     fy += fr * dy;
     fz += fr * dz;
     if (MODE == NL_MODE_FULL) {
-        const bool count = inside && s_j > s_i;
-        const double w = count ? fr : 0.0;
+        // like the staged path of lj_force_kernel: half of the energy and virial from each side of the pair
+        const bool count = inside;
+        const double w = fr;
         acc[0] += count ? a.lj_epsilon4 * (s6 * s6 - s6) - a.lj_shift : 0.0;
         acc[14] += count ? 1.0 : 0.0;
         acc[2] += w * dx * dx;
@@ -545,14 +796,69 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
     }
 }
 
+// Walk of a column in the global format: four entries (one 16-byte word) at a time.  Software pipeline, per
+// thread: the list word two iterations ahead and the four neighbour positions one iteration ahead are in flight
+// while the current four neighbours are evaluated.
 template <bool LJ_ONLY, int MODE>
+__device__ __forceinline__ void walk_global_column(const ForceArgs& a, const PairParams* sp, const double (*offset64)[3],
+                                                   int s_i, const int4& info_i, double& fx, double& fy, double& fz,
+                                                   double (&acc)[NL_NV]) {
+    const double4 pi = a.sorted_pos[s_i];
+    const int count = a.ncount[s_i];
+    const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
+    const int nwords = (count + 3) >> 2;
+    uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
+    uint4 wnext = nwords > 1 ? words[32] : make_uint4(0, 0, 0, 0);
+    double4 pcur[4], pnext[4];
+    {
+        const unsigned e[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) pcur[t] = a.sorted_pos[e[t] & LIST_INDEX_MASK];
+    }
+    // 32-bit shared-memory address of the offset table (one multiply-add per neighbour instead of a
+    // generic-pointer computation)
+    const unsigned offset_base = (unsigned)__cvta_generic_to_shared(&offset64[0][0]);
+    for (int w = 0; w < nwords; w++) {
+        uint4 wafter = make_uint4(0, 0, 0, 0);
+        if (w + 2 < nwords) wafter = words[(w + 2) * 32];
+        {
+            const unsigned e[4] = {wnext.x, wnext.y, wnext.z, wnext.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) pnext[t] = a.sorted_pos[e[t] & LIST_INDEX_MASK];
+        }
+        const unsigned entries[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const bool listed = 4 * w + t < count;  // the last word is padded
+            const unsigned address = offset_base + (entries[t] >> 26) * 24u;
+            double ox, oy, oz;
+            asm("ld.shared.f64 %0, [%1];" : "=d"(ox) : "r"(address));
+            asm("ld.shared.f64 %0, [%1+8];" : "=d"(oy) : "r"(address));
+            asm("ld.shared.f64 %0, [%1+16];" : "=d"(oz) : "r"(address));
+            const int s_j = (int)(entries[t] & LIST_INDEX_MASK);
+            if (LJ_ONLY) {
+                evaluate_lj<MODE>(a, pi.x - ox, pi.y - oy, pi.z - oz, s_i, s_j, listed, pcur[t], fx, fy, fz, acc);
+            } else if (listed) {
+                evaluate_neighbor<LJ_ONLY, MODE>(a, sp, pi.x - ox, pi.y - oy, pi.z - oz, pi.w, info_i, s_i, s_j,
+                                                 pcur[t], fx, fy, fz, acc);
+            }
+        }
+        wcur = wnext;
+        wnext = wafter;
+#pragma unroll
+        for (int t = 0; t < 4; t++) pcur[t] = pnext[t];
+    }
+}
+
+// General kernel (any potential, restrictions, Ewald real space / Wolf): every block uses the global format.
+template <int MODE>
 __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairParams* sp = reinterpret_cast<PairParams*>(smem_raw);
     __shared__ double offset64[27][3];  // (a, b, c) * edge for the 27 neighbour-cell offsets
     __shared__ double scratch[32 * NL_NV];
 
-    if (!LJ_ONLY) {
+    {
         const int words = (int)(sizeof(PairParams) / sizeof(double)) * a.nkinds * a.nkinds;
         const double* src = reinterpret_cast<const double*>(a.pairs);
         double* dst = reinterpret_cast<double*>(sp);
@@ -578,57 +884,8 @@ __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
         active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
     }
     if (active) {
-        const double4 pi = a.sorted_pos[s_i];
-        const int count = a.ncount[s_i];
         double fx = 0.0, fy = 0.0, fz = 0.0;
-
-        // The column is read four entries (one 16-byte word) at a time.  Software pipeline, per thread: the
-        // list word two iterations ahead and the four neighbour positions one iteration ahead are in flight
-        // while the current four neighbours are evaluated, so neither the HBM latency of the list nor the
-        // L1/L2 latency of the position gathers is exposed.
-        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
-        const int nwords = (count + 3) >> 2;
-        uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
-        uint4 wnext = nwords > 1 ? words[32] : make_uint4(0, 0, 0, 0);
-        double4 pcur[4], pnext[4];
-        {
-            const unsigned e[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
-#pragma unroll
-            for (int t = 0; t < 4; t++) pcur[t] = a.sorted_pos[e[t] & LIST_INDEX_MASK];
-        }
-        // 32-bit shared-memory address of the offset table (one multiply-add per neighbour instead of a
-        // generic-pointer computation)
-        const unsigned offset_base = (unsigned)__cvta_generic_to_shared(&offset64[0][0]);
-        for (int w = 0; w < nwords; w++) {
-            uint4 wafter = make_uint4(0, 0, 0, 0);
-            if (w + 2 < nwords) wafter = words[(w + 2) * 32];
-            {
-                const unsigned e[4] = {wnext.x, wnext.y, wnext.z, wnext.w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) pnext[t] = a.sorted_pos[e[t] & LIST_INDEX_MASK];
-            }
-            const unsigned entries[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const bool listed = 4 * w + t < count;  // the last word is padded
-                const unsigned address = offset_base + (entries[t] >> 26) * 24u;
-                double ox, oy, oz;
-                asm("ld.shared.f64 %0, [%1];" : "=d"(ox) : "r"(address));
-                asm("ld.shared.f64 %0, [%1+8];" : "=d"(oy) : "r"(address));
-                asm("ld.shared.f64 %0, [%1+16];" : "=d"(oz) : "r"(address));
-                const int s_j = (int)(entries[t] & LIST_INDEX_MASK);
-                if (LJ_ONLY) {
-                    evaluate_lj<MODE>(a, pi.x - ox, pi.y - oy, pi.z - oz, s_i, s_j, listed, pcur[t], fx, fy, fz, acc);
-                } else if (listed) {
-                    evaluate_neighbor<LJ_ONLY, MODE>(a, sp, pi.x - ox, pi.y - oy, pi.z - oz, pi.w, info_i, s_i, s_j,
-                                                     pcur[t], fx, fy, fz, acc);
-                }
-            }
-            wcur = wnext;
-            wnext = wafter;
-#pragma unroll
-            for (int t = 0; t < 4; t++) pcur[t] = pnext[t];
-        }
+        walk_global_column<false, MODE>(a, sp, offset64, s_i, info_i, fx, fy, fz, acc);
         if (a.write_forces) {
             a.force[3 * info_i.w] = fx;
             a.force[3 * info_i.w + 1] = fy;
@@ -637,6 +894,176 @@ __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
     }
 
     if (MODE == NL_MODE_FULL) {
+        block_sum<NL_NV>(acc, scratch);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < NL_NV; k++) a.partials[(size_t)blockIdx.x * NL_NV + k] = acc[k];
+        }
+    }
+}
+
+// 1 / x by the hardware seed and one cubically convergent step, y (1 + e + e^2) with e = 1 - x y: three
+// FMAs take the seed's 2^-20 to below the FP64 rounding error.
+__device__ __forceinline__ double reciprocal3(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+// One staged neighbour of the Lennard-Jones kernel: 19 FP64 instructions, no branch.  A padding entry points
+// at the dummy slot, far outside any cut-off.
+template <int MODE>
+__device__ __forceinline__ void staged_lj(const ForceArgs& a, const double* __restrict__ stage, unsigned index,
+                                          double xi, double yi, double zi, double& fx, double& fy, double& fz,
+                                          double (&acc)[NL_NV]) {
+    const double* pj = stage + 3u * index;
+    const double dx = xi - pj[0], dy = yi - pj[1], dz = zi - pj[2];
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const bool inside = r2 < a.lj_cutoff2;
+    const double rinv2 = reciprocal3(r2);
+    const double s2 = a.lj_sigma2 * rinv2;
+    const double s6 = s2 * s2 * s2;
+    // force(r) / r = -24 eps (s6 - 2 s6^2) / r^2 (functions.rs:85-88)
+    double fr = (s6 * rinv2) * fma(a.lj_epsilon48, s6, -a.lj_epsilon24);
+    fr = inside ? fr : 0.0;
+    fx = fma(fr, dx, fx);
+    fy = fma(fr, dy, fy);
+    fz = fma(fr, dz, fz);
+    if (MODE == NL_MODE_FULL) {
+        // every pair is visited from both sides: half of the energy and virial from each
+        const double e = a.lj_epsilon4 * fma(s6, s6, -s6) - a.lj_shift;
+        acc[0] += inside ? e : 0.0;
+        acc[14] += inside ? 1.0 : 0.0;
+        acc[2] += fr * dx * dx;
+        acc[3] += fr * dx * dy;
+        acc[4] += fr * dx * dz;
+        acc[5] += fr * dy * dy;
+        acc[6] += fr * dy * dz;
+        acc[7] += fr * dz * dz;
+    }
+}
+
+// Lennard-Jones kernel: TB consecutive atoms per block, neighbourhood staged in shared memory.
+template <int MODE>
+__global__ void __launch_bounds__(TB, 2) lj_force_kernel(ForceArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* stage = reinterpret_cast<double*>(smem_raw);  // x, y, z per staged atom
+    double* scratch = stage;                              // reused by the final reduction
+    __shared__ int table[STAGE_MAX_ENTRIES];              // per entry: source index of its (virtual) slot 0
+    __shared__ double table_shift[3 * STAGE_MAX_ENTRIES];  // per entry: periodic + block-frame shift
+    __shared__ double offset64[27][3];
+
+    double acc[NL_NV];
+#pragma unroll
+    for (int k = 0; k < NL_NV; k++) acc[k] = 0.0;
+
+    const int s_i = blockIdx.x * TB + threadIdx.x;
+    int4 info_i = make_int4(0, 0, 0, -1);
+    bool active = s_i < a.n;
+    if (active) {
+        info_i = a.sorted_info[s_i];
+        active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
+    }
+    const int4 header = a.blk_header[blockIdx.x];
+    const int nentries = header.z;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+
+    if (__syncthreads_or(active) == 0) {
+        // no atom of this rank in the block
+    } else if (nentries < 0) {
+        // ---- block that could not be staged: global gathers ---------------------------------------------
+        if (threadIdx.x < 27) {
+            const int t = threadIdx.x;
+            offset64[t][0] = (double)((t % 3) - 1) * a.edge[0];
+            offset64[t][1] = (double)(((t / 3) % 3) - 1) * a.edge[1];
+            offset64[t][2] = (double)((t / 9) - 1) * a.edge[2];
+        }
+        __syncthreads();
+        if (active) walk_global_column<true, MODE>(a, nullptr, offset64, s_i, info_i, fx, fy, fz, acc);
+    } else {
+        // ---- stage the neighbourhood --------------------------------------------------------------------
+        // the thread's own list head first: its latency hides behind the staging
+        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
+        const int count = active ? a.ncount[s_i] : 0;
+        const unsigned self = active ? a.self_local[s_i] : 0u;
+        const int nwords = (count + 7) >> 3;
+        uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
+        uint4 wnext = nwords > 1 ? words[32] : make_uint4(0, 0, 0, 0);
+
+        // slot -> entry map of the block: every load of the staging is issued before the first one is used
+        const int total = header.w;
+        const unsigned char* map = a.blk_map + (size_t)blockIdx.x * a.map_stride;
+        unsigned char entry_of[STAGE_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < STAGE_ROUNDS; r++) {
+            const int slot = 1 + r * TB + (int)threadIdx.x;
+            entry_of[r] = slot < total ? map[slot] : (unsigned char)0;
+        }
+        const int4* entries = a.blk_entries + (size_t)blockIdx.x * STAGE_MAX_ENTRIES;
+        for (int e = threadIdx.x; e < nentries; e += TB) {
+            const int4 entry = entries[e];
+            table[e] = entry.x - (entry.y & 0xffff);  // source index of slot 0 of the entry
+            table_shift[3 * e] = (double)(short)(entry.z & 0xffff) * a.edge[0];
+            table_shift[3 * e + 1] = (double)(entry.z >> 16) * a.edge[1];
+            table_shift[3 * e + 2] = (double)entry.w * a.edge[2];
+        }
+        if (threadIdx.x < 3) stage[threadIdx.x] = 1.0e9 * (double)(threadIdx.x + 1);  // the dummy
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < STAGE_ROUNDS; g += STAGE_GROUP) {
+            if (1 + g * TB < total) {  // uniform over the block
+                double4 p[STAGE_GROUP];
+#pragma unroll
+                for (int u = 0; u < STAGE_GROUP; u++) {
+                    const int slot = 1 + (g + u) * TB + (int)threadIdx.x;
+                    if (slot < total) p[u] = a.sorted_pos[table[entry_of[g + u]] + slot];
+                }
+#pragma unroll
+                for (int u = 0; u < STAGE_GROUP; u++) {
+                    const int slot = 1 + (g + u) * TB + (int)threadIdx.x;
+                    if (slot < total) {
+                        const double* shift = table_shift + 3 * entry_of[g + u];
+                        double* dst = stage + 3 * slot;
+                        dst[0] = p[u].x + shift[0];
+                        dst[1] = p[u].y + shift[1];
+                        dst[2] = p[u].z + shift[2];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        if (active) {
+            const double* pi = stage + 3u * self;
+            const double xi = pi[0], yi = pi[1], zi = pi[2];
+            // eight 16-bit entries per 16-byte word; the word two iterations ahead is in flight
+            for (int w = 0; w < nwords; w++) {
+                uint4 wafter = make_uint4(0, 0, 0, 0);
+                if (w + 2 < nwords) wafter = words[(w + 2) * 32];
+                const unsigned pairs[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    staged_lj<MODE>(a, stage, pairs[t] & 0xffffu, xi, yi, zi, fx, fy, fz, acc);
+                    staged_lj<MODE>(a, stage, pairs[t] >> 16, xi, yi, zi, fx, fy, fz, acc);
+                }
+                wcur = wnext;
+                wnext = wafter;
+            }
+        }
+    }
+    if (MODE == NL_MODE_FULL) {
+#pragma unroll
+        for (int k = 0; k < NL_NV; k++) acc[k] *= 0.5;
+    }
+    if (active && a.write_forces) {
+        a.force[3 * info_i.w] = fx;
+        a.force[3 * info_i.w + 1] = fy;
+        a.force[3 * info_i.w + 2] = fz;
+    }
+
+    if (MODE == NL_MODE_FULL) {
+        __syncthreads();  // the staged copy is dead: its memory holds the reduction scratch
         block_sum<NL_NV>(acc, scratch);
         if (threadIdx.x == 0) {
 #pragma unroll
@@ -681,8 +1108,8 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     const double volume = g.length[0] * g.length[1] * g.length[2];
     const double mean_neighbors = 4.0 / 3.0 * PI * radius * radius * radius * (double)n / volume;
     int capacity = (int)(2.0 * mean_neighbors) + 64;
-    capacity = (capacity + 7) / 8 * 8;
     if (capacity > n) capacity = n;
+    capacity = (capacity + 7) / 8 * 8;  // whole 16-byte words in both list formats
     const size_t stride = ((size_t)n + 31) / 32 * 32;
     LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(8));
     LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(stride * (size_t)capacity));
@@ -696,6 +1123,18 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_pos.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_info.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_cell.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(stride));
+    const int nblocks = (n + TB - 1) / TB;
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)nblocks));
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)nblocks * STAGE_MAX_ENTRIES));
+    // Lennard-Jones fast path (one LJ interaction, no restriction, no charges in play): staged blocks
+    const bool lj_system = ctx->any_pair && ctx->single_lj && ctx->coulomb.kind == 0;
+    const bool allow_staging = lj_system && ctx->forced_path != 2;
+    const int stage_bytes = STAGE_BYTES;
+    const int stage_atoms_max = STAGE_ATOMS_MAX;
+    const size_t map_stride = ((size_t)STAGE_ATOMS_MAX + 15) / 16 * 16;
+    if (allow_staging) LUMOL_CUDA_CHECK(ctx, ctx->blk_map.reserve((size_t)nblocks * map_stride));
     const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
     LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)scan_blocks + 1));
     int* flags = ctx->nl_flags.ptr;
@@ -713,6 +1152,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     signature = mix(signature, bits);
     signature = mix(signature, (uint64_t)o_lo * 1315423911ull + (uint64_t)o_hi);
     signature = mix(signature, (uint64_t)capacity);
+    signature = mix(signature, lj_system ? 1 : 0);
     const bool reuse = ctx->list_valid && signature == ctx->list_signature;
     const int blocks = (n + 255) / 256;
     {
@@ -755,9 +1195,25 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         s.rel0 = ctx->rel0.ptr;
         s.sorted_f32 = ctx->sorted_f32.ptr;
         s.sorted_info = ctx->sorted_info.ptr;
+        s.sorted_cell = ctx->sorted_cell.ptr;
         s.xref = ctx->xref.ptr;
         s.flags = flags;
         cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
+
+        TableArgs t;
+        t.g = g;
+        t.n = n;
+        t.nblocks = nblocks;
+        t.allow = allow_staging ? 1 : 0;
+        t.stage_atoms_max = stage_atoms_max;
+        t.cell_start = ctx->cell_start.ptr;
+        t.sorted_cell = ctx->sorted_cell.ptr;
+        t.header = ctx->blk_header.ptr;
+        t.entries = ctx->blk_entries.ptr;
+        t.map = ctx->blk_map.ptr;
+        t.map_stride = map_stride;
+        t.flags = flags;
+        block_table_kernel<<<(nblocks + 3) / 4, 128, 0, ctx->stream>>>(t);
 
         BuildArgs b;
         b.g = g;
@@ -770,7 +1226,9 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         b.o_lo = (int)o_lo;
         b.o_hi = (int)o_hi;
         b.capacity = capacity;
-        b.stride = stride;
+        b.blk_header = ctx->blk_header.ptr;
+        b.blk_entries = ctx->blk_entries.ptr;
+        b.self_local = ctx->self_local.ptr;
         b.radius2 = (float)(radius * radius * 1.0001);
         b.cell_start = ctx->cell_start.ptr;
         b.sorted_f32 = ctx->sorted_f32.ptr;
@@ -779,9 +1237,20 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         b.ncount = ctx->ncount.ptr;
         b.flags = flags;
         list_build_kernel<<<build_blocks, BUILD_THREADS, 0, ctx->stream>>>(b);
+        const size_t reorder_smem = (size_t)capacity * REORDER_THREADS * sizeof(unsigned short);
+        if (allow_staging && reorder_smem <= 200 * 1024) {
+            if (reorder_smem > 40 * 1024) {
+                LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           (int)reorder_smem));
+            }
+            list_reorder_kernel<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, reorder_smem, ctx->stream>>>(
+                n, capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, flags);
+            ctx->launches++;
+            ctx->clk_neighbor.launches++;
+        }
         list_finish_kernel<<<1, 1, 0, ctx->stream>>>(flags);
-        ctx->launches += 9;
-        ctx->clk_neighbor.launches += 9;
+        ctx->launches += 10;
+        ctx->clk_neighbor.launches += 10;
         LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
     }
     ctx->list_valid = true;
@@ -816,30 +1285,39 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.force = ctx->force.ptr;
     a.write_forces = req.forces;
 
-    const bool lj_only = do_pairs && !do_coulomb && ctx->single_lj;
-    a.lj_sigma2 = a.lj_epsilon24 = a.lj_epsilon4 = a.lj_cutoff2 = a.lj_shift = 0.0;
+    // the staged kernel needs lists built for it (lj_system); a system with charges whose coulomb part is
+    // not requested still takes the general kernel
+    const bool lj_only = do_pairs && !do_coulomb && lj_system;
+    a.lj_sigma2 = a.lj_epsilon24 = a.lj_epsilon48 = a.lj_epsilon4 = a.lj_cutoff2 = a.lj_shift = 0.0;
     if (lj_only) {
         const lumol_cuda_pair& p = ctx->host_pairs[0];
         a.lj_sigma2 = p.p[0] * p.p[0];
         a.lj_epsilon24 = 24.0 * p.p[1];
+        a.lj_epsilon48 = 48.0 * p.p[1];
         a.lj_epsilon4 = 4.0 * p.p[1];
         a.lj_cutoff2 = p.cutoff * p.cutoff;
         a.lj_shift = p.shift;
     }
-    const size_t smem = lj_only ? 0 : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
-    if (smem > 100 * 1024) {
+    a.blk_header = ctx->blk_header.ptr;
+    a.blk_entries = ctx->blk_entries.ptr;
+    a.self_local = ctx->self_local.ptr;
+    a.blk_map = ctx->blk_map.ptr;
+    a.map_stride = map_stride;
+    const size_t smem = lj_only ? (size_t)stage_bytes : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
+    if (!lj_only && smem > 100 * 1024) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many particle kinds (%d) for the shared pair table", ctx->nkinds);
     }
     const bool full = req.energy || req.virial;
-    const int force_blocks = (n + NL_THREADS - 1) / NL_THREADS;
+    const int threads = lj_only ? TB : NL_THREADS;
+    const int force_blocks = (n + threads - 1) / threads;
     LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)force_blocks * NL_NV));
     a.partials = ctx->partials.ptr;
 
     const void* kernel;
     if (lj_only) {
-        kernel = full ? (const void*)list_force_kernel<true, NL_MODE_FULL> : (const void*)list_force_kernel<true, NL_MODE_FORCES>;
+        kernel = full ? (const void*)lj_force_kernel<NL_MODE_FULL> : (const void*)lj_force_kernel<NL_MODE_FORCES>;
     } else {
-        kernel = full ? (const void*)list_force_kernel<false, NL_MODE_FULL> : (const void*)list_force_kernel<false, NL_MODE_FORCES>;
+        kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL> : (const void*)list_force_kernel<NL_MODE_FORCES>;
     }
     if (smem > 40 * 1024) {
         LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -847,7 +1325,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     {
         ScopedClock clock(ctx, &ctx->clk_pair);
         void* params[] = {&a};
-        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(force_blocks), dim3(NL_THREADS), params, smem, ctx->stream));
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(force_blocks), dim3(threads), params, smem, ctx->stream));
         ctx->launches++;
         ctx->clk_pair.launches++;
     }

@@ -428,6 +428,51 @@ def test_lj_box_cell_list_vs_oracle():
     check_system(general, molecular=False, path=1)
 
 
+def test_staged_lj_kernel_vs_oracle_and_global_format():
+    """32 768-atom argon box (10 x 10 x 10 cells): the Lennard-Jones kernel that stages each block's neighbourhood in
+    shared memory (16-bit list entries) against the oracle and against the same kernel with every block in the
+    global list format (neighbour path 2)."""
+    system = systems.lj_box(32, seed=20240 + 15)
+    device = check_system(system, molecular=False, path=1)
+    assert tuple(device.stats().ncells) == (10, 10, 10)
+    staged = device.compute(forces=True, energy=True, virial=True)
+    device.set_neighbor_path(2)
+    plain = device.compute(forces=True, energy=True, virial=True)
+    scale = np.abs(plain.forces).max()
+    assert np.abs(staged.forces - plain.forces).max() < 1e-12 * scale
+    assert abs(staged.energy.pairs - plain.energy.pairs) < 1e-12 * abs(plain.energy.pairs)
+    assert np.abs(staged.virial - plain.virial).max() < 1e-12 * np.abs(plain.virial).max()
+    # a flat box: blocks span several rows of cells and wrap around the periodic boundary inside a block
+    flat = lumol.System(lumol.UnitCell.ortho(34.0, 35.0, 140.0))
+    rng = np.random.Generator(np.random.PCG64(11))
+    points = np.stack(np.meshgrid(np.arange(9), np.arange(9), np.arange(36), indexing="ij"), axis=-1).reshape(-1, 3)
+    positions = (points + 0.5) * np.array([34.0 / 9, 35.0 / 9, 140.0 / 36]) + rng.uniform(-0.3, 0.3, (len(points), 3))
+    flat.add_particles(["Ar"] * len(positions), positions)
+    potential = lumol.LennardJones(sigma=3.4, epsilon=units.from_(1.0, "kJ/mol"))
+    flat.set_pair_potential(("Ar", "Ar"), lumol.PairInteraction(potential, 10.0))
+    device = check_system(flat, molecular=False, path=1)
+    assert tuple(device.stats().ncells) == (3, 3, 12)
+
+
+def test_staged_lj_kernel_full_size():
+    """The bench box (1 048 576 atoms): staged kernel against the global-format kernel, Newton's third law."""
+    from lumol_b200 import synthetic
+
+    system = synthetic.lj_box((128, 128, 64), seed=20240 + 20)
+    device = device_for(system)
+    staged = device.compute(forces=True, energy=True, virial=True)
+    assert device.stats().neighbor_path == 1
+    pairs_staged = device.stats().pair_count
+    device.set_neighbor_path(2)
+    plain = device.compute(forces=True, energy=True, virial=True)
+    assert device.stats().pair_count == pairs_staged
+    scale = np.abs(plain.forces).max()
+    assert np.abs(staged.forces - plain.forces).max() < 1e-12 * scale
+    assert np.abs(staged.forces.sum(axis=0)).max() < 1e-9 * scale * np.sqrt(system.size())
+    assert abs(staged.energy.pairs - plain.energy.pairs) < 1e-12 * abs(plain.energy.pairs)
+    assert np.abs(staged.virial - plain.virial).max() < 1e-11 * np.abs(plain.virial).max()
+
+
 def test_water_box_cell_list_vs_oracle():
     """5184-atom synthetic SPC/E box: LJ + Ewald real space with intra-molecular exclusions on the cell path."""
     system = systems.spce_box(12)
