@@ -165,6 +165,7 @@ struct Context {
     DeviceBuffer<int> scan_scratch;
     DeviceBuffer<int> sorted_cell;             // linear cell index, sorted order
     DeviceBuffer<int4> blk_header, blk_entries;  // staging tables of the Lennard-Jones kernel (pairs_cells.cu)
+    DeviceBuffer<double> frame_pos;            // x | y | z planes, sorted order, positions in the frame of the box
     DeviceBuffer<unsigned char> blk_map;       // staged slot -> entry number, per block
     DeviceBuffer<unsigned short> self_local;   // staged slot of each atom inside its own block
 

@@ -226,6 +226,8 @@ struct ScatterArgs {
     float4* __restrict__ sorted_f32;
     int4* __restrict__ sorted_info;
     int* __restrict__ sorted_cell;
+    double* __restrict__ frame;  // x, y, z planes of `frame_stride` doubles: positions in the frame of the box
+    size_t frame_stride;
     double* __restrict__ xref;
     const int* __restrict__ flags;
 };
@@ -256,6 +258,10 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
     a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, 0.0f);
     a.sorted_info[dst] = make_int4((int)a.kind[i], a.mol_first[i], a.bd_row[i], i);
     a.sorted_cell[dst] = c;
+    // the same position in the frame of the box (cell centre + relative part), read by the staged kernel
+    a.frame[dst] = x + ((double)cx + 0.5) * a.g.edge[0];
+    a.frame[a.frame_stride + dst] = y + ((double)cy + 0.5) * a.g.edge[1];
+    a.frame[2 * a.frame_stride + dst] = z + ((double)cz + 0.5) * a.g.edge[2];
     a.xref[3 * i] = px;
     a.xref[3 * i + 1] = py;
     a.xref[3 * i + 2] = pz;
@@ -264,9 +270,10 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
 // Between rebuilds: positions in sorted order follow the atoms with the image they had at build time, and any
 // displacement above skin / 2 requests a rebuild.
 __global__ void __launch_bounds__(256)
-    list_update_kernel(int n, const int* __restrict__ order, const double* __restrict__ pos,
+    list_update_kernel(int n, GridView g, const int* __restrict__ order, const double* __restrict__ pos,
                        const double* __restrict__ xref, const double4* __restrict__ rel0,
-                       double4* __restrict__ sorted_pos, double threshold2, int* __restrict__ flags) {
+                       const int* __restrict__ sorted_cell, double4* __restrict__ sorted_pos,
+                       double* __restrict__ frame, size_t frame_stride, double threshold2, int* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int i = order[s];
@@ -275,7 +282,15 @@ __global__ void __launch_bounds__(256)
     const double dz = pos[3 * i + 2] - xref[3 * i + 2];
     if (!(dx * dx + dy * dy + dz * dz <= threshold2)) flags[FLAG_REBUILD] = 1;  // also catches NaN
     const double4 r = rel0[s];
-    sorted_pos[s] = make_double4(r.x + dx, r.y + dy, r.z + dz, r.w);
+    const double x = r.x + dx, y = r.y + dy, z = r.z + dz;
+    sorted_pos[s] = make_double4(x, y, z, r.w);
+    if (frame != nullptr) {
+        const int c = sorted_cell[s];
+        const int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
+        frame[s] = x + ((double)cx + 0.5) * g.edge[0];
+        frame[frame_stride + s] = y + ((double)cy + 0.5) * g.edge[1];
+        frame[2 * frame_stride + s] = z + ((double)cz + 0.5) * g.edge[2];
+    }
 }
 
 __global__ void list_finish_kernel(int* __restrict__ flags) {
@@ -304,12 +319,9 @@ __global__ void list_finish_kernel(int* __restrict__ flags) {
 constexpr int TB = 256;  // atoms per block of the force kernel
 constexpr int STAGE_MAX_ENTRIES = 160;
 constexpr int STAGE_MAX_SEGMENTS = 6;
-constexpr int STAGE_BYTES = 104 * 1024;             // shared memory of the staged copy: two blocks per SM
-constexpr int STAGE_ATOMS_MAX = STAGE_BYTES / 24;   // dummy slot included
-constexpr int STAGE_GROUP = 6;                      // staging loads in flight per thread
-constexpr int STAGE_ROUNDS = 18;                    // slots per thread, a multiple of STAGE_GROUP
-static_assert(STAGE_ROUNDS * TB >= STAGE_ATOMS_MAX && STAGE_ROUNDS % STAGE_GROUP == 0, "staging rounds");
-static_assert(STAGE_MAX_ENTRIES <= 256, "the slot map holds entry numbers in one byte");
+constexpr int STAGE_SLOTS = 4528;                   // atoms of the staged copy, dummy slot 0 included (a multiple of 16)
+constexpr int STAGE_BYTES = 3 * STAGE_SLOTS * 8;    // x | y | z planes: 106 KiB, two blocks per SM
+constexpr int STAGE_ATOMS_MAX = STAGE_SLOTS;
 constexpr int FLAG_UNSTAGED = 3;                    // flags[3]: blocks of the last rebuild that were not staged
 
 struct BlockRows {
@@ -351,10 +363,10 @@ struct TableArgs {
     int stage_atoms_max;  // shared-memory capacity of the force kernel in atoms, dummy slot included
     const int* __restrict__ cell_start;
     const int* __restrict__ sorted_cell;
-    int4* __restrict__ header;   // c0, K, entries (-1: not staged), staged atoms
-    int4* __restrict__ entries;  // first sorted index, offset | count << 16, shift x | shift y << 16, shift z
-    unsigned char* __restrict__ map;  // per block, per staged slot: entry number
-    size_t map_stride;
+    int4* __restrict__ header;   // c0, K (negated when the rank owns no atom of the block), entries (-1: not staged), staged atoms
+    int4* __restrict__ entries;  // first sorted index, offset | count << 16, image x | image y << 16, image z
+    const int4* __restrict__ sorted_info;
+    int o_lo, o_hi;
     int* __restrict__ flags;
 };
 
@@ -372,7 +384,6 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
     int total = 1;  // slot 0 is the far-away dummy the padding entries point to
     if (staged) {
         const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
-        const int y0 = rows.r0 % ny, z0 = rows.r0 / ny;
         for (int base = 0; base < rows.nentries; base += 32) {
             const int e = base + lane;
             int src = 0, count = 0, sx = 0, sy = 0, sz = 0;
@@ -396,9 +407,10 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
                 const int cell = (az * ny + ay) * nx + ax;
                 src = a.cell_start[cell];
                 count = a.cell_start[cell + 1] - src;
-                sx = ux - rows.xa0;
-                sy = uy - y0;
-                sz = uz - z0;
+                // periodic image of the cell as seen from the block (the staged kernel works in the frame of the box)
+                sx = ux < 0 ? -1 : (ux >= nx ? 1 : 0);
+                sy = uy < 0 ? -1 : (uy >= ny ? 1 : 0);
+                sz = uz < 0 ? -1 : (uz >= nz ? 1 : 0);
             }
             // exclusive scan of the counts over the warp
             int scan = count;
@@ -417,18 +429,15 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
         if (total > a.stage_atoms_max || total > 65535) staged = false;
         __syncwarp();
     }
-    if (staged) {
-        // slot -> entry map read by the staging loop of the force kernel
-        unsigned char* map = a.map + (size_t)block * a.map_stride;
-        for (int e = 0; e < rows.nentries; e++) {
-            const int4 entry = a.entries[(size_t)block * STAGE_MAX_ENTRIES + e];  // written by this warp
-            const int offset = entry.y & 0xffff, count = (int)((unsigned)entry.y >> 16);
-            for (int t = lane; t < count; t += 32) map[offset + t] = (unsigned char)e;
-        }
-    } else if (lane == 0 && a.allow != 0) {
-        atomicAdd(a.flags + FLAG_UNSTAGED, 1);
+    if (!staged && lane == 0 && a.allow != 0) atomicAdd(a.flags + FLAG_UNSTAGED, 1);
+    // does this rank own an atom of the block?
+    bool owned = false;
+    for (int s = s_first + lane; s <= s_last; s += 32) {
+        const int orig = a.sorted_info[s].w;
+        owned = owned || (orig >= a.o_lo && orig < a.o_hi);
     }
-    if (lane == 0) a.header[block] = make_int4(rows.c0, rows.K, staged ? rows.nentries : -1, total);
+    owned = __any_sync(0xffffffffu, owned);
+    if (lane == 0) a.header[block] = make_int4(rows.c0, owned ? rows.K : -rows.K, staged ? rows.nentries : -1, total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) 
                 staged = header.z >= 0;
                 if (staged) {
                     BlockRows rows;
-                    rows.init(header.x, header.y, a.g.nc[0]);
+                    rows.init(header.x, abs(header.y), a.g.nc[0]);
                     int xa, len, seg_base;
                     rows.segment(c / a.g.nc[0] - rows.r0, xa, len, seg_base);
                     entries += (size_t)block * STAGE_MAX_ENTRIES;
@@ -671,8 +680,10 @@ struct ForceArgs {
     const int4* __restrict__ blk_header;
     const int4* __restrict__ blk_entries;
     const unsigned short* __restrict__ self_local;
-    const unsigned char* __restrict__ blk_map;
-    size_t map_stride;
+    const double* __restrict__ frame;  // box-frame positions, x | y | z planes (sorted order)
+    size_t frame_stride;
+    int ntiles;
+    double length[3];
     int write_forces;            // energy-only queries must not clobber the forces the integrator holds
     double* __restrict__ force;  // original order, n x 3
     double* __restrict__ partials;
@@ -917,8 +928,8 @@ template <int MODE>
 __device__ __forceinline__ void staged_lj(const ForceArgs& a, const double* __restrict__ stage, unsigned index,
                                           double xi, double yi, double zi, double& fx, double& fy, double& fz,
                                           double (&acc)[NL_NV]) {
-    const double* pj = stage + 3u * index;
-    const double dx = xi - pj[0], dy = yi - pj[1], dz = zi - pj[2];
+    const double* pj = stage + index;
+    const double dx = xi - pj[0], dy = yi - pj[STAGE_SLOTS], dz = zi - pj[2 * STAGE_SLOTS];
     const double r2 = dx * dx + dy * dy + dz * dz;
     const bool inside = r2 < a.lj_cutoff2;
     const double rinv2 = reciprocal3(r2);
@@ -944,99 +955,123 @@ __device__ __forceinline__ void staged_lj(const ForceArgs& a, const double* __re
     }
 }
 
-// Lennard-Jones kernel: TB consecutive atoms per block, neighbourhood staged in shared memory.
+// ---- asynchronous copies (LDGSTS): global -> shared without a register round trip ------------------------
+
+__device__ __forceinline__ void copy_async_8(double* shared_dst, const double* global_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(shared_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(global_src) : "memory");
+}
+__device__ __forceinline__ void copy_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void copy_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+
+constexpr int LJ_THREADS = TB;
+
+// Issues the copies of the block's neighbourhood into the staged copy (x | y | z planes): one warp per cell.
+__device__ __forceinline__ void stage_issue(const ForceArgs& a, const int4* __restrict__ table, int nentries, double* stage) {
+    const int lane = threadIdx.x & 31;
+    for (int e = threadIdx.x >> 5; e < nentries; e += LJ_THREADS / 32) {
+        const int4 entry = table[e];
+        const int offset = entry.y & 0xffff, count = (int)((unsigned)entry.y >> 16);
+        for (int t = lane; t < count; t += 32) {
+            const double* src = a.frame + entry.x + t;
+            double* dst = stage + offset + t;
+            copy_async_8(dst, src);
+            copy_async_8(dst + STAGE_SLOTS, src + a.frame_stride);
+            copy_async_8(dst + 2 * STAGE_SLOTS, src + 2 * a.frame_stride);
+        }
+    }
+}
+
+// Cells seen through a periodic boundary: add the image vector to what the copies brought.
+__device__ __forceinline__ void stage_images(const ForceArgs& a, const int4* __restrict__ table, int nentries, double* stage) {
+    const int lane = threadIdx.x & 31;
+    for (int e = threadIdx.x >> 5; e < nentries; e += LJ_THREADS / 32) {
+        const int4 entry = table[e];
+        if ((entry.z | entry.w) == 0) continue;
+        const int offset = entry.y & 0xffff, count = (int)((unsigned)entry.y >> 16);
+        const double sx = (double)(short)(entry.z & 0xffff) * a.length[0];
+        const double sy = (double)(entry.z >> 16) * a.length[1];
+        const double sz = (double)entry.w * a.length[2];
+        for (int t = lane; t < count; t += 32) {
+            double* p = stage + offset + t;
+            p[0] += sx;
+            p[STAGE_SLOTS] += sy;
+            p[2 * STAGE_SLOTS] += sz;
+        }
+    }
+}
+
+// Lennard-Jones kernel: TB consecutive atoms per block, one thread per atom, two blocks per SM.  The block
+// first issues every load it will wait for (its own list heads, then the LDGSTS copies of its neighbourhood,
+// box-frame coordinates, no arithmetic in flight), so the staging costs one memory round trip.
 template <int MODE>
-__global__ void __launch_bounds__(TB, 2) lj_force_kernel(ForceArgs a) {
+__global__ void __launch_bounds__(LJ_THREADS, 2) lj_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* stage = reinterpret_cast<double*>(smem_raw);  // x, y, z per staged atom
-    double* scratch = stage;                              // reused by the final reduction
-    __shared__ int table[STAGE_MAX_ENTRIES];              // per entry: source index of its (virtual) slot 0
-    __shared__ double table_shift[3 * STAGE_MAX_ENTRIES];  // per entry: periodic + block-frame shift
+    double* stage = reinterpret_cast<double*>(smem_raw);  // x | y | z planes of STAGE_SLOTS doubles
+    __shared__ int4 table[STAGE_MAX_ENTRIES];
     __shared__ double offset64[27][3];
 
     double acc[NL_NV];
 #pragma unroll
     for (int k = 0; k < NL_NV; k++) acc[k] = 0.0;
 
-    const int s_i = blockIdx.x * TB + threadIdx.x;
-    int4 info_i = make_int4(0, 0, 0, -1);
-    bool active = s_i < a.n;
-    if (active) {
-        info_i = a.sorted_info[s_i];
-        active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
-    }
+    const int tid = threadIdx.x;
+    // header: c0, +-K (negative: no atom of this rank), entries (-1: global format), staged atoms
     const int4 header = a.blk_header[blockIdx.x];
-    const int nentries = header.z;
+    const int s_i = blockIdx.x * TB + tid;
+    const bool present = header.y > 0 && s_i < a.n;
     double fx = 0.0, fy = 0.0, fz = 0.0;
+    int orig = -1;
 
-    if (__syncthreads_or(active) == 0) {
+    if (header.y <= 0) {
         // no atom of this rank in the block
-    } else if (nentries < 0) {
+    } else if (header.z < 0) {
         // ---- block that could not be staged: global gathers ---------------------------------------------
-        if (threadIdx.x < 27) {
-            const int t = threadIdx.x;
-            offset64[t][0] = (double)((t % 3) - 1) * a.edge[0];
-            offset64[t][1] = (double)(((t / 3) % 3) - 1) * a.edge[1];
-            offset64[t][2] = (double)((t / 9) - 1) * a.edge[2];
+        if (tid < 27) {
+            offset64[tid][0] = (double)((tid % 3) - 1) * a.edge[0];
+            offset64[tid][1] = (double)(((tid / 3) % 3) - 1) * a.edge[1];
+            offset64[tid][2] = (double)((tid / 9) - 1) * a.edge[2];
         }
         __syncthreads();
-        if (active) walk_global_column<true, MODE>(a, nullptr, offset64, s_i, info_i, fx, fy, fz, acc);
-    } else {
-        // ---- stage the neighbourhood --------------------------------------------------------------------
-        // the thread's own list head first: its latency hides behind the staging
-        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
-        const int count = active ? a.ncount[s_i] : 0;
-        const unsigned self = active ? a.self_local[s_i] : 0u;
-        const int nwords = (count + 7) >> 3;
-        uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
-        uint4 wnext = nwords > 1 ? words[32] : make_uint4(0, 0, 0, 0);
-
-        // slot -> entry map of the block: every load of the staging is issued before the first one is used
-        const int total = header.w;
-        const unsigned char* map = a.blk_map + (size_t)blockIdx.x * a.map_stride;
-        unsigned char entry_of[STAGE_ROUNDS];
-#pragma unroll
-        for (int r = 0; r < STAGE_ROUNDS; r++) {
-            const int slot = 1 + r * TB + (int)threadIdx.x;
-            entry_of[r] = slot < total ? map[slot] : (unsigned char)0;
-        }
-        const int4* entries = a.blk_entries + (size_t)blockIdx.x * STAGE_MAX_ENTRIES;
-        for (int e = threadIdx.x; e < nentries; e += TB) {
-            const int4 entry = entries[e];
-            table[e] = entry.x - (entry.y & 0xffff);  // source index of slot 0 of the entry
-            table_shift[3 * e] = (double)(short)(entry.z & 0xffff) * a.edge[0];
-            table_shift[3 * e + 1] = (double)(entry.z >> 16) * a.edge[1];
-            table_shift[3 * e + 2] = (double)entry.w * a.edge[2];
-        }
-        if (threadIdx.x < 3) stage[threadIdx.x] = 1.0e9 * (double)(threadIdx.x + 1);  // the dummy
-        __syncthreads();
-#pragma unroll
-        for (int g = 0; g < STAGE_ROUNDS; g += STAGE_GROUP) {
-            if (1 + g * TB < total) {  // uniform over the block
-                double4 p[STAGE_GROUP];
-#pragma unroll
-                for (int u = 0; u < STAGE_GROUP; u++) {
-                    const int slot = 1 + (g + u) * TB + (int)threadIdx.x;
-                    if (slot < total) p[u] = a.sorted_pos[table[entry_of[g + u]] + slot];
-                }
-#pragma unroll
-                for (int u = 0; u < STAGE_GROUP; u++) {
-                    const int slot = 1 + (g + u) * TB + (int)threadIdx.x;
-                    if (slot < total) {
-                        const double* shift = table_shift + 3 * entry_of[g + u];
-                        double* dst = stage + 3 * slot;
-                        dst[0] = p[u].x + shift[0];
-                        dst[1] = p[u].y + shift[1];
-                        dst[2] = p[u].z + shift[2];
-                    }
-                }
+        if (present) {
+            const int4 info_i = a.sorted_info[s_i];
+            if (info_i.w >= a.o_lo && info_i.w < a.o_hi) {
+                orig = info_i.w;
+                walk_global_column<true, MODE>(a, nullptr, offset64, s_i, info_i, fx, fy, fz, acc);
             }
         }
+    } else {
+        // ---- every independent load first ------------------------------------------------------------------
+        const int nentries = header.z;
+        if (tid < nentries) table[tid] = a.blk_entries[(size_t)blockIdx.x * STAGE_MAX_ENTRIES + tid];
+        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
+        // atoms of other ranks have empty columns (list_build_kernel)
+        const int count = present ? a.ncount[s_i] : 0;
+        const unsigned self = present ? a.self_local[s_i] : 0u;
+        if (present) orig = a.sorted_info[s_i].w;
+        uint4 wcur = make_uint4(0, 0, 0, 0), wnext = make_uint4(0, 0, 0, 0);
+        if (present) {
+            wcur = words[0];
+            wnext = words[32];  // inside the slab whatever the count
+        }
+        if (tid < 3) stage[tid * STAGE_SLOTS] = 1.0e9 * (double)(tid + 1);  // the dummy, far outside any cut-off
         __syncthreads();
+        stage_issue(a, table, nentries, stage);
+        copy_async_commit();
+        bool images = false;
+        if (tid < nentries) images = (table[tid].z | table[tid].w) != 0;
+        copy_async_wait<0>();
+        if (__syncthreads_or(images)) {
+            stage_images(a, table, nentries, stage);
+            __syncthreads();
+        }
 
-        if (active) {
-            const double* pi = stage + 3u * self;
-            const double xi = pi[0], yi = pi[1], zi = pi[2];
+        const int nwords = (count + 7) >> 3;
+        if (nwords > 0 && orig >= a.o_lo && orig < a.o_hi) {
+            const double xi = stage[self], yi = stage[STAGE_SLOTS + self], zi = stage[2 * STAGE_SLOTS + self];
             // eight 16-bit entries per 16-byte word; the word two iterations ahead is in flight
             for (int w = 0; w < nwords; w++) {
                 uint4 wafter = make_uint4(0, 0, 0, 0);
@@ -1052,19 +1087,17 @@ __global__ void __launch_bounds__(TB, 2) lj_force_kernel(ForceArgs a) {
             }
         }
     }
-    if (MODE == NL_MODE_FULL) {
-#pragma unroll
-        for (int k = 0; k < NL_NV; k++) acc[k] *= 0.5;
-    }
-    if (active && a.write_forces) {
-        a.force[3 * info_i.w] = fx;
-        a.force[3 * info_i.w + 1] = fy;
-        a.force[3 * info_i.w + 2] = fz;
+    if (orig >= a.o_lo && orig < a.o_hi && a.write_forces) {
+        a.force[3 * orig] = fx;
+        a.force[3 * orig + 1] = fy;
+        a.force[3 * orig + 2] = fz;
     }
 
     if (MODE == NL_MODE_FULL) {
-        __syncthreads();  // the staged copy is dead: its memory holds the reduction scratch
-        block_sum<NL_NV>(acc, scratch);
+#pragma unroll
+        for (int k = 0; k < NL_NV; k++) acc[k] *= 0.5;
+        __syncthreads();
+        block_sum<NL_NV>(acc, stage);  // the staged copy is dead: its memory holds the reduction scratch
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int k = 0; k < NL_NV; k++) a.partials[(size_t)blockIdx.x * NL_NV + k] = acc[k];
@@ -1124,6 +1157,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_info.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_cell.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(3 * stride));
     LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(stride));
     const int nblocks = (n + TB - 1) / TB;
     LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)nblocks));
@@ -1133,8 +1167,6 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     const bool allow_staging = lj_system && ctx->forced_path != 2;
     const int stage_bytes = STAGE_BYTES;
     const int stage_atoms_max = STAGE_ATOMS_MAX;
-    const size_t map_stride = ((size_t)STAGE_ATOMS_MAX + 15) / 16 * 16;
-    if (allow_staging) LUMOL_CUDA_CHECK(ctx, ctx->blk_map.reserve((size_t)nblocks * map_stride));
     const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
     LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)scan_blocks + 1));
     int* flags = ctx->nl_flags.ptr;
@@ -1165,8 +1197,10 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
             set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, 1);
         } else {
             const double half = 0.5 * skin;
-            list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
-                                                                ctx->sorted_pos.ptr, half * half, flags);
+            list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
+                                                                ctx->sorted_cell.ptr, ctx->sorted_pos.ptr,
+                                                                allow_staging ? ctx->frame_pos.ptr : nullptr, stride,
+                                                                half * half, flags);
         }
         ctx->launches++;
         ctx->clk_neighbor.launches++;
@@ -1196,6 +1230,8 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         s.sorted_f32 = ctx->sorted_f32.ptr;
         s.sorted_info = ctx->sorted_info.ptr;
         s.sorted_cell = ctx->sorted_cell.ptr;
+        s.frame = ctx->frame_pos.ptr;
+        s.frame_stride = stride;
         s.xref = ctx->xref.ptr;
         s.flags = flags;
         cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
@@ -1210,8 +1246,9 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         t.sorted_cell = ctx->sorted_cell.ptr;
         t.header = ctx->blk_header.ptr;
         t.entries = ctx->blk_entries.ptr;
-        t.map = ctx->blk_map.ptr;
-        t.map_stride = map_stride;
+        t.sorted_info = ctx->sorted_info.ptr;
+        t.o_lo = (int)o_lo;
+        t.o_hi = (int)o_hi;
         t.flags = flags;
         block_table_kernel<<<(nblocks + 3) / 4, 128, 0, ctx->stream>>>(t);
 
@@ -1301,14 +1338,16 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.blk_header = ctx->blk_header.ptr;
     a.blk_entries = ctx->blk_entries.ptr;
     a.self_local = ctx->self_local.ptr;
-    a.blk_map = ctx->blk_map.ptr;
-    a.map_stride = map_stride;
+    a.frame = ctx->frame_pos.ptr;
+    a.frame_stride = stride;
+    a.ntiles = nblocks;
+    for (int d = 0; d < 3; d++) a.length[d] = g.length[d];
     const size_t smem = lj_only ? (size_t)stage_bytes : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
     if (!lj_only && smem > 100 * 1024) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many particle kinds (%d) for the shared pair table", ctx->nkinds);
     }
     const bool full = req.energy || req.virial;
-    const int threads = lj_only ? TB : NL_THREADS;
+    const int threads = lj_only ? LJ_THREADS : NL_THREADS;
     const int force_blocks = (n + threads - 1) / threads;
     LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)force_blocks * NL_NV));
     a.partials = ctx->partials.ptr;
