@@ -164,6 +164,7 @@ struct Context {
     DeviceBuffer<int4> sorted_info;    // kind, mol_first, bd_row, original index
     DeviceBuffer<int> scan_scratch;
     DeviceBuffer<int> sorted_cell;             // linear cell index, sorted order
+    DeviceBuffer<int2> blk_runs;               // runs of consecutive cells: one bulk copy each
     DeviceBuffer<int4> blk_header, blk_entries;  // staging tables of the Lennard-Jones kernel (pairs_cells.cu)
     DeviceBuffer<double> frame_pos;            // x | y | z planes, sorted order, positions in the frame of the box
     DeviceBuffer<unsigned char> blk_map;       // staged slot -> entry number, per block

@@ -87,6 +87,10 @@ __device__ __forceinline__ double wrap_coordinate(double x, double length) {
     return x - floor(x / length) * length;
 }
 
+// Box-frame arrays (read by the bulk copies of the Lennard-Jones kernel, 16-byte granularity): the atoms of cell c
+// start at an even index, one slot of padding per cell at most.
+__host__ __device__ __forceinline__ int frame_start(int cell, int first_sorted) { return (first_sorted + cell + 1) & ~1; }
+
 __device__ __forceinline__ int cell_coordinate(double wrapped, double length, int nc) {
     int c = (int)(wrapped / length * (double)nc);
     if (c >= nc) c = nc - 1;  // wrapped == length after rounding
@@ -259,9 +263,10 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
     a.sorted_info[dst] = make_int4((int)a.kind[i], a.mol_first[i], a.bd_row[i], i);
     a.sorted_cell[dst] = c;
     // the same position in the frame of the box (cell centre + relative part), read by the staged kernel
-    a.frame[dst] = x + ((double)cx + 0.5) * a.g.edge[0];
-    a.frame[a.frame_stride + dst] = y + ((double)cy + 0.5) * a.g.edge[1];
-    a.frame[2 * a.frame_stride + dst] = z + ((double)cz + 0.5) * a.g.edge[2];
+    const int f = frame_start(c, lo) + rank;
+    a.frame[f] = x + ((double)cx + 0.5) * a.g.edge[0];
+    a.frame[a.frame_stride + f] = y + ((double)cy + 0.5) * a.g.edge[1];
+    a.frame[2 * a.frame_stride + f] = z + ((double)cz + 0.5) * a.g.edge[2];
     a.xref[3 * i] = px;
     a.xref[3 * i + 1] = py;
     a.xref[3 * i + 2] = pz;
@@ -272,7 +277,8 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
 __global__ void __launch_bounds__(256)
     list_update_kernel(int n, GridView g, const int* __restrict__ order, const double* __restrict__ pos,
                        const double* __restrict__ xref, const double4* __restrict__ rel0,
-                       const int* __restrict__ sorted_cell, double4* __restrict__ sorted_pos,
+                       const int* __restrict__ sorted_cell, const int* __restrict__ cell_start,
+                       double4* __restrict__ sorted_pos,
                        double* __restrict__ frame, size_t frame_stride, double threshold2, int* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -287,9 +293,11 @@ __global__ void __launch_bounds__(256)
     if (frame != nullptr) {
         const int c = sorted_cell[s];
         const int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
-        frame[s] = x + ((double)cx + 0.5) * g.edge[0];
-        frame[frame_stride + s] = y + ((double)cy + 0.5) * g.edge[1];
-        frame[2 * frame_stride + s] = z + ((double)cz + 0.5) * g.edge[2];
+        const int first = cell_start[c];
+        const int f = frame_start(c, first) + (s - first);
+        frame[f] = x + ((double)cx + 0.5) * g.edge[0];
+        frame[frame_stride + f] = y + ((double)cy + 0.5) * g.edge[1];
+        frame[2 * frame_stride + f] = z + ((double)cz + 0.5) * g.edge[2];
     }
 }
 
@@ -363,8 +371,10 @@ struct TableArgs {
     int stage_atoms_max;  // shared-memory capacity of the force kernel in atoms, dummy slot included
     const int* __restrict__ cell_start;
     const int* __restrict__ sorted_cell;
-    int4* __restrict__ header;   // c0, K (negated when the rank owns no atom of the block), entries (-1: not staged), staged atoms
-    int4* __restrict__ entries;  // first sorted index, offset | count << 16, image x | image y << 16, image z
+    int2* __restrict__ runs;     // first box-frame index, first slot | periodic image << 16 of every run
+    int4* __restrict__ header;   // c0, K (negated when the rank owns no atom of the block), entries | runs << 16 (-1: not staged),
+                                 // staged slots (negated when some cell is seen through a periodic boundary)
+    int4* __restrict__ entries;  // first box-frame index, slot offset | count << 16, image x | image y << 16, image z
     const int4* __restrict__ sorted_info;
     int o_lo, o_hi;
     int* __restrict__ flags;
@@ -381,12 +391,18 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
     BlockRows rows;
     rows.init(c_first, c_last - c_first + 1, a.g.nc[0]);
     bool staged = a.allow != 0 && rows.nseg <= STAGE_MAX_SEGMENTS && rows.nentries <= STAGE_MAX_ENTRIES;
-    int total = 1;  // slot 0 is the far-away dummy the padding entries point to
+    // Slot 0 is the far-away dummy the padding entries point to.  The cells of one row that follow each other in
+    // the box-frame arrays form a run: one bulk copy per run and coordinate plane, so the slots of a run mirror
+    // the layout of the frame arrays (even starts, up to two slots of padding between cells).
+    int total = 2, nruns = 0;
+    bool images = false;
     if (staged) {
         const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
         for (int base = 0; base < rows.nentries; base += 32) {
             const int e = base + lane;
             int src = 0, count = 0, sx = 0, sy = 0, sz = 0;
+            int slots = 0;          // distance to the slot of the next entry
+            bool run_start = false;
             if (e < rows.nentries) {
                 int g = 0, rem = e;
                 const int first = 9 * (rows.len0 + 2);
@@ -405,26 +421,40 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
                 const int ay = uy < 0 ? uy + ny : (uy >= ny ? uy - ny : uy);
                 const int az = uz < 0 ? uz + nz : (uz >= nz ? uz - nz : uz);
                 const int cell = (az * ny + ay) * nx + ax;
-                src = a.cell_start[cell];
-                count = a.cell_start[cell + 1] - src;
+                const int first_sorted = a.cell_start[cell];
+                count = a.cell_start[cell + 1] - first_sorted;
+                src = frame_start(cell, first_sorted);  // index into the box-frame arrays
                 // periodic image of the cell as seen from the block (the staged kernel works in the frame of the box)
                 sx = ux < 0 ? -1 : (ux >= nx ? 1 : 0);
                 sy = uy < 0 ? -1 : (uy >= ny ? 1 : 0);
                 sz = uz < 0 ? -1 : (uz >= nz ? 1 : 0);
+                // the run continues into the next entry when that is the next cell of the same row of the grid
+                run_start = k == 0 || ax == 0;
+                const bool run_end = k == w - 1 || ax == nx - 1;
+                slots = run_end ? ((count + 1) & ~1) : frame_start(cell + 1, a.cell_start[cell + 1]) - src;
             }
-            // exclusive scan of the counts over the warp
-            int scan = count;
+            images = images || (sx | sy | sz) != 0;
+            // exclusive scan of the slot counts over the warp
+            int scan = slots;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, scan, o);
                 if (lane >= o) scan += t;
             }
-            const int offset = total + scan - count;
+            const int offset = total + scan - slots;
             total += __shfl_sync(0xffffffffu, scan, 31);
-            if (e < rows.nentries && offset + count <= 65535 && count <= 65535) {
+            const unsigned starts = __ballot_sync(0xffffffffu, run_start);
+            if (e < rows.nentries && offset + slots <= 65535) {
                 a.entries[(size_t)block * STAGE_MAX_ENTRIES + e] =
                     make_int4(src, offset | (count << 16), (sx & 0xffff) | (sy << 16), sz);
+                if (run_start) {
+                    const int r = nruns + __popc(starts & ((1u << lane) - 1u));
+                    // bits 16..21: periodic image of the run, two bits per axis (0: none, 1: +L, 3: -L)
+                    const int image = (sx & 3) | ((sy & 3) << 2) | ((sz & 3) << 4);
+                    a.runs[(size_t)block * STAGE_MAX_ENTRIES + r] = make_int2(src, offset | (image << 16));
+                }
             }
+            nruns += __popc(starts);
         }
         if (total > a.stage_atoms_max || total > 65535) staged = false;
         __syncwarp();
@@ -437,7 +467,11 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
         owned = owned || (orig >= a.o_lo && orig < a.o_hi);
     }
     owned = __any_sync(0xffffffffu, owned);
-    if (lane == 0) a.header[block] = make_int4(rows.c0, owned ? rows.K : -rows.K, staged ? rows.nentries : -1, total);
+    images = __any_sync(0xffffffffu, images);
+    if (lane == 0) {
+        a.header[block] =
+            make_int4(rows.c0, owned ? rows.K : -rows.K, staged ? (rows.nentries | (nruns << 16)) : -1, images ? -total : total);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -679,6 +713,7 @@ struct ForceArgs {
     double lj_sigma2, lj_epsilon24, lj_epsilon48, lj_epsilon4, lj_cutoff2, lj_shift;
     const int4* __restrict__ blk_header;
     const int4* __restrict__ blk_entries;
+    const int2* __restrict__ blk_runs;
     const unsigned short* __restrict__ self_local;
     const double* __restrict__ frame;  // box-frame positions, x | y | z planes (sorted order)
     size_t frame_stride;
@@ -955,76 +990,70 @@ __device__ __forceinline__ void staged_lj(const ForceArgs& a, const double* __re
     }
 }
 
-// ---- asynchronous copies (LDGSTS): global -> shared without a register round trip ------------------------
-
-__device__ __forceinline__ void copy_async_8(double* shared_dst, const double* global_src) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(shared_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(global_src) : "memory");
-}
-__device__ __forceinline__ void copy_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void copy_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
-}
-
 constexpr int LJ_THREADS = TB;
 
-// Issues the copies of the block's neighbourhood into the staged copy (x | y | z planes): one warp per cell.
-__device__ __forceinline__ void stage_issue(const ForceArgs& a, const int4* __restrict__ table, int nentries, double* stage) {
-    const int lane = threadIdx.x & 31;
-    for (int e = threadIdx.x >> 5; e < nentries; e += LJ_THREADS / 32) {
-        const int4 entry = table[e];
-        const int offset = entry.y & 0xffff, count = (int)((unsigned)entry.y >> 16);
-        for (int t = lane; t < count; t += 32) {
-            const double* src = a.frame + entry.x + t;
-            double* dst = stage + offset + t;
-            copy_async_8(dst, src);
-            copy_async_8(dst + STAGE_SLOTS, src + a.frame_stride);
-            copy_async_8(dst + 2 * STAGE_SLOTS, src + 2 * a.frame_stride);
-        }
-    }
-}
+// ---- bulk asynchronous copies (TMA, UBLKCP): global -> shared, completion counted on an mbarrier ---------------
 
-// Cells seen through a periodic boundary: add the image vector to what the copies brought.
-__device__ __forceinline__ void stage_images(const ForceArgs& a, const int4* __restrict__ table, int nentries, double* stage) {
-    const int lane = threadIdx.x & 31;
-    for (int e = threadIdx.x >> 5; e < nentries; e += LJ_THREADS / 32) {
-        const int4 entry = table[e];
-        if ((entry.z | entry.w) == 0) continue;
-        const int offset = entry.y & 0xffff, count = (int)((unsigned)entry.y >> 16);
-        const double sx = (double)(short)(entry.z & 0xffff) * a.length[0];
-        const double sy = (double)(entry.z >> 16) * a.length[1];
-        const double sz = (double)entry.w * a.length[2];
-        for (int t = lane; t < count; t += 32) {
-            double* p = stage + offset + t;
-            p[0] += sx;
-            p[STAGE_SLOTS] += sy;
-            p[2 * STAGE_SLOTS] += sz;
-        }
-    }
+__device__ __forceinline__ unsigned shared_address(const void* pointer) { return (unsigned)__cvta_generic_to_shared(pointer); }
+
+__device__ __forceinline__ void barrier_init(unsigned long long* barrier, unsigned arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(shared_address(barrier)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void barrier_expect_bytes(unsigned long long* barrier, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(shared_address(barrier)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(double* shared_dst, const double* global_src, unsigned bytes, unsigned long long* barrier) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     shared_address(shared_dst)),
+                 "l"(global_src), "r"(bytes), "r"(shared_address(barrier))
+                 : "memory");
+}
+__device__ __forceinline__ void barrier_wait(unsigned long long* barrier, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred done;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+        "@done bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(shared_address(barrier)),
+        "r"(parity)
+        : "memory");
 }
 
 // Lennard-Jones kernel: TB consecutive atoms per block, one thread per atom, two blocks per SM.  The block
-// first issues every load it will wait for (its own list heads, then the LDGSTS copies of its neighbourhood,
-// box-frame coordinates, no arithmetic in flight), so the staging costs one memory round trip.
+// issues every load it will wait for at once: each thread the head of its own column, warp 0 the bulk copies
+// (one UBLKCP per cell and coordinate plane, box-frame coordinates, completion counted on an mbarrier) of the
+// whole neighbourhood.  The staging costs a few hundred instructions and one memory round trip per block.
 template <int MODE>
 __global__ void __launch_bounds__(LJ_THREADS, 2) lj_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* stage = reinterpret_cast<double*>(smem_raw);  // x | y | z planes of STAGE_SLOTS doubles
-    __shared__ int4 table[STAGE_MAX_ENTRIES];
     __shared__ double offset64[27][3];
+    __shared__ __align__(8) unsigned long long arrived;
+    __shared__ int4 images[STAGE_MAX_ENTRIES];  // runs seen through a periodic boundary: first slot, end, image code
+    __shared__ int nimages;
 
     double acc[NL_NV];
 #pragma unroll
     for (int k = 0; k < NL_NV; k++) acc[k] = 0.0;
 
     const int tid = threadIdx.x;
-    // header: c0, +-K (negative: no atom of this rank), entries (-1: global format), staged atoms
-    const int4 header = a.blk_header[blockIdx.x];
     const int s_i = blockIdx.x * TB + tid;
-    const bool present = header.y > 0 && s_i < a.n;
+    const bool present = s_i < a.n;
+    // loads that do not depend on the header: atoms of other ranks have empty columns (list_build_kernel)
+    const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
+    const int count = present ? a.ncount[s_i] : 0;
+    const unsigned self = present ? a.self_local[s_i] : 0u;
+    const int orig = present ? a.sorted_info[s_i].w : -1;
+    // header: c0, +-K (negative: no atom of this rank), entries (-1: global format), +-staged slots (negative:
+    // periodic images among them)
+    const int4 header = a.blk_header[blockIdx.x];
+    const int2* runs = a.blk_runs + (size_t)blockIdx.x * STAGE_MAX_ENTRIES;
+    const bool mine = orig >= a.o_lo && orig < a.o_hi;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    int orig = -1;
 
     if (header.y <= 0) {
         // no atom of this rank in the block
@@ -1036,41 +1065,71 @@ __global__ void __launch_bounds__(LJ_THREADS, 2) lj_force_kernel(ForceArgs a) {
             offset64[tid][2] = (double)((tid / 9) - 1) * a.edge[2];
         }
         __syncthreads();
-        if (present) {
-            const int4 info_i = a.sorted_info[s_i];
-            if (info_i.w >= a.o_lo && info_i.w < a.o_hi) {
-                orig = info_i.w;
-                walk_global_column<true, MODE>(a, nullptr, offset64, s_i, info_i, fx, fy, fz, acc);
-            }
-        }
+        if (mine) walk_global_column<true, MODE>(a, nullptr, offset64, s_i, a.sorted_info[s_i], fx, fy, fz, acc);
     } else {
-        // ---- every independent load first ------------------------------------------------------------------
-        const int nentries = header.z;
-        if (tid < nentries) table[tid] = a.blk_entries[(size_t)blockIdx.x * STAGE_MAX_ENTRIES + tid];
-        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
-        // atoms of other ranks have empty columns (list_build_kernel)
-        const int count = present ? a.ncount[s_i] : 0;
-        const unsigned self = present ? a.self_local[s_i] : 0u;
-        if (present) orig = a.sorted_info[s_i].w;
+        const int nruns = header.z >> 16;
         uint4 wcur = make_uint4(0, 0, 0, 0), wnext = make_uint4(0, 0, 0, 0);
         if (present) {
             wcur = words[0];
             wnext = words[32];  // inside the slab whatever the count
         }
+        if (tid == 0) {
+            barrier_init(&arrived, 1);
+            nimages = 0;
+        }
         if (tid < 3) stage[tid * STAGE_SLOTS] = 1.0e9 * (double)(tid + 1);  // the dummy, far outside any cut-off
         __syncthreads();
-        stage_issue(a, table, nentries, stage);
-        copy_async_commit();
-        bool images = false;
-        if (tid < nentries) images = (table[tid].z | table[tid].w) != 0;
-        copy_async_wait<0>();
-        if (__syncthreads_or(images)) {
-            stage_images(a, table, nentries, stage);
+        if (tid < 32) {
+            // one bulk copy per run and plane; a run ends where the next one starts
+            const int total = abs(header.w);
+            int2 run[STAGE_MAX_ENTRIES / 32];
+            int end[STAGE_MAX_ENTRIES / 32];
+#pragma unroll
+            for (int k = 0; k < STAGE_MAX_ENTRIES / 32; k++) {
+                const int r = tid + 32 * k;
+                run[k] = r < nruns ? runs[r] : make_int2(0, 0);
+                end[k] = r + 1 < nruns ? (runs[r + 1].y & 0xffff) : total;
+            }
+            if (tid == 0) barrier_expect_bytes(&arrived, 24u * (unsigned)(total - 2));
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < STAGE_MAX_ENTRIES / 32; k++) {
+                if (tid + 32 * k < nruns) {
+                    const int first = run[k].y & 0xffff;
+                    const unsigned bytes = (unsigned)(end[k] - first) * 8u;
+                    const double* src = a.frame + run[k].x;
+                    double* dst = stage + first;
+                    bulk_copy(dst, src, bytes, &arrived);
+                    bulk_copy(dst + STAGE_SLOTS, src + a.frame_stride, bytes, &arrived);
+                    bulk_copy(dst + 2 * STAGE_SLOTS, src + 2 * a.frame_stride, bytes, &arrived);
+                    if ((run[k].y >> 16) != 0) {
+                        // seen through a periodic boundary: remembered for the fix-up below
+                        const int position = atomicAdd(&nimages, 1);
+                        images[position] = make_int4(first, end[k], run[k].y >> 16, 0);
+                    }
+                }
+            }
+        }
+        barrier_wait(&arrived, 0);
+        if (header.w < 0) {
+            // add the image vector to what the copies brought for cells across a periodic boundary
+            __syncthreads();
+            const int lane = tid & 31;
+            for (int m = tid >> 5; m < nimages; m += LJ_THREADS / 32) {
+                const int4 image = images[m];
+                const int ix = (image.z << 30) >> 30, iy = (image.z << 28) >> 30, iz = (image.z << 26) >> 30;
+                const double sx = (double)ix * a.length[0], sy = (double)iy * a.length[1], sz = (double)iz * a.length[2];
+                for (int t = image.x + lane; t < image.y; t += 32) {
+                    stage[t] += sx;
+                    stage[STAGE_SLOTS + t] += sy;
+                    stage[2 * STAGE_SLOTS + t] += sz;
+                }
+            }
             __syncthreads();
         }
 
         const int nwords = (count + 7) >> 3;
-        if (nwords > 0 && orig >= a.o_lo && orig < a.o_hi) {
+        if (nwords > 0 && mine) {
             const double xi = stage[self], yi = stage[STAGE_SLOTS + self], zi = stage[2 * STAGE_SLOTS + self];
             // eight 16-bit entries per 16-byte word; the word two iterations ahead is in flight
             for (int w = 0; w < nwords; w++) {
@@ -1087,7 +1146,7 @@ __global__ void __launch_bounds__(LJ_THREADS, 2) lj_force_kernel(ForceArgs a) {
             }
         }
     }
-    if (orig >= a.o_lo && orig < a.o_hi && a.write_forces) {
+    if (mine && header.y > 0 && a.write_forces) {
         a.force[3 * orig] = fx;
         a.force[3 * orig + 1] = fy;
         a.force[3 * orig + 2] = fz;
@@ -1157,11 +1216,13 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_info.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_cell.reserve((size_t)n));
-    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(3 * stride));
+    const size_t frame_stride = ((size_t)n + (size_t)ncells + 2 + 31) / 32 * 32;
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(3 * frame_stride));
     LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(stride));
     const int nblocks = (n + TB - 1) / TB;
     LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)nblocks));
     LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)nblocks * STAGE_MAX_ENTRIES));
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_runs.reserve((size_t)nblocks * STAGE_MAX_ENTRIES + 1));
     // Lennard-Jones fast path (one LJ interaction, no restriction, no charges in play): staged blocks
     const bool lj_system = ctx->any_pair && ctx->single_lj && ctx->coulomb.kind == 0;
     const bool allow_staging = lj_system && ctx->forced_path != 2;
@@ -1194,12 +1255,13 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
                 LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(flags, 0, 8 * sizeof(int), ctx->stream));
                 ctx->flags_initialised = true;
             }
+            LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->frame_pos.ptr, 0, 3 * frame_stride * sizeof(double), ctx->stream));
             set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, 1);
         } else {
             const double half = 0.5 * skin;
             list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
-                                                                ctx->sorted_cell.ptr, ctx->sorted_pos.ptr,
-                                                                allow_staging ? ctx->frame_pos.ptr : nullptr, stride,
+                                                                ctx->sorted_cell.ptr, ctx->cell_start.ptr, ctx->sorted_pos.ptr,
+                                                                allow_staging ? ctx->frame_pos.ptr : nullptr, frame_stride,
                                                                 half * half, flags);
         }
         ctx->launches++;
@@ -1231,7 +1293,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         s.sorted_info = ctx->sorted_info.ptr;
         s.sorted_cell = ctx->sorted_cell.ptr;
         s.frame = ctx->frame_pos.ptr;
-        s.frame_stride = stride;
+        s.frame_stride = frame_stride;
         s.xref = ctx->xref.ptr;
         s.flags = flags;
         cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
@@ -1246,6 +1308,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         t.sorted_cell = ctx->sorted_cell.ptr;
         t.header = ctx->blk_header.ptr;
         t.entries = ctx->blk_entries.ptr;
+        t.runs = ctx->blk_runs.ptr;
         t.sorted_info = ctx->sorted_info.ptr;
         t.o_lo = (int)o_lo;
         t.o_hi = (int)o_hi;
@@ -1337,9 +1400,10 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     }
     a.blk_header = ctx->blk_header.ptr;
     a.blk_entries = ctx->blk_entries.ptr;
+    a.blk_runs = ctx->blk_runs.ptr;
     a.self_local = ctx->self_local.ptr;
     a.frame = ctx->frame_pos.ptr;
-    a.frame_stride = stride;
+    a.frame_stride = frame_stride;
     a.ntiles = nblocks;
     for (int d = 0; d < 3; d++) a.length[d] = g.length[d];
     const size_t smem = lj_only ? (size_t)stage_bytes : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
