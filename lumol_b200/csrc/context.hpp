@@ -151,6 +151,8 @@ struct Context {
     double skin_effective = 0.0;   // what fits in the box
     bool list_valid = false;
     bool flags_initialised = false;
+    int list_epoch = 0;     // evaluation counter; flags[FLAG_REBUILD] == epoch requests a rebuild
+    int rebuild_grid = 0;   // co-resident blocks of the cooperative rebuild kernel
     uint64_t list_signature = 0;
     uint64_t structure_generation = 0;  // bumped by every change the list depends on besides positions
     DeviceBuffer<int> nl_flags;         // rebuild flag, overflow flag, rebuild counter

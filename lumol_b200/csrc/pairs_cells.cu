@@ -32,6 +32,8 @@
 //     energies / virials are taken from the side with the larger sorted index.
 #include "context.hpp"
 
+#include <cooperative_groups.h>
+
 #include <cstring>
 
 namespace lumol {
@@ -98,17 +100,20 @@ __device__ __forceinline__ int cell_coordinate(double wrapped, double length, in
     return c;
 }
 
-__global__ void __launch_bounds__(256) cell_zero_kernel(int count, int* __restrict__ cell_count, int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_kernel
+// The rebuild runs as the phases of ONE cooperative kernel (rebuild_kernel below) separated by grid-wide
+// barriers; `vb` is the virtual block a resident block is working on.
+constexpr int REBUILD_THREADS = 256;
+constexpr int REBUILD_WARPS = REBUILD_THREADS / 32;
+
+__device__ __forceinline__ void cell_zero_phase(int count, int* __restrict__ cell_count, int* __restrict__ flags) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_phase
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) cell_count[k] = 0;
 }
 
-__global__ void __launch_bounds__(256)
-    cell_assign_kernel(int n, GridView g, const double* __restrict__ pos, int* __restrict__ cell_of,
-                       int* __restrict__ slot_of, int* __restrict__ cell_count, const int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void cell_assign_phase(int vb, int n, const GridView& g, const double* __restrict__ pos,
+                                                  int* __restrict__ cell_of, int* __restrict__ slot_of,
+                                                  int* __restrict__ cell_count) {
+    const int i = vb * REBUILD_THREADS + threadIdx.x;
     if (i >= n) return;
     const int cx = cell_coordinate(wrap_coordinate(pos[3 * i], g.length[0]), g.length[0], g.nc[0]);
     const int cy = cell_coordinate(wrap_coordinate(pos[3 * i + 1], g.length[1]), g.length[1], g.nc[1]);
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // exclusive scan of `count` ints in three passes (block scan, scan of block sums, add back)
-constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_THREADS = REBUILD_THREADS;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
 
@@ -149,12 +154,9 @@ __device__ __forceinline__ int block_exclusive_scan(int value, int* shared, int&
     return warp_offset + v - value;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-    scan_blocks_kernel(int count, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ block_sums,
-                       const int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    __shared__ int shared[32];
-    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+__device__ __forceinline__ void scan_blocks_phase(int vb, int count, const int* __restrict__ in, int* __restrict__ out,
+                                                  int* __restrict__ block_sums, int* shared) {
+    const int base = vb * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     int items[SCAN_ITEMS];
     int sum = 0;
 #pragma unroll
@@ -169,13 +171,12 @@ __global__ void __launch_bounds__(SCAN_THREADS)
         if (base + k < count) out[base + k] = offset;
         offset += items[k];
     }
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) block_sums[vb] = total;
 }
 
-__global__ void __launch_bounds__(1024) scan_sums_kernel(int nblocks, int* __restrict__ block_sums, const int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    __shared__ int shared[32];
-    __shared__ int carry;
+// one block
+__device__ __forceinline__ void scan_sums_phase(int nblocks, int* __restrict__ block_sums, int* shared) {
+    int& carry = shared[32];
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < nblocks; base += blockDim.x) {
@@ -190,25 +191,21 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(int nblocks, int* __res
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-    scan_add_kernel(int count, int* __restrict__ out, const int* __restrict__ block_sums, int total_count,
-                    const int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    const int add = block_sums[blockIdx.x];
+__device__ __forceinline__ void scan_add_phase(int vb, int count, int* __restrict__ out, const int* __restrict__ block_sums,
+                                               int total_count) {
+    const int base = vb * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    const int add = block_sums[vb];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         if (base + k < count) out[base + k] += add;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[count] = total_count;
+    if (vb == 0 && threadIdx.x == 0) out[count] = total_count;
 }
 
 // first pass of the scatter: original indices grouped by cell, arrival order
-__global__ void __launch_bounds__(256)
-    cell_group_kernel(int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
-                      const int* __restrict__ cell_start, int* __restrict__ grouped, const int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void cell_group_phase(int vb, int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
+                                                 const int* __restrict__ cell_start, int* __restrict__ grouped) {
+    const int i = vb * REBUILD_THREADS + threadIdx.x;
     if (i >= n) return;
     grouped[cell_start[cell_of[i]] + slot_of[i]] = i;
 }
@@ -233,13 +230,11 @@ struct ScatterArgs {
     double* __restrict__ frame;  // x, y, z planes of `frame_stride` doubles: positions in the frame of the box
     size_t frame_stride;
     double* __restrict__ xref;
-    const int* __restrict__ flags;
 };
 
 // second pass: rank inside the cell = number of cell mates with a smaller original index
-__global__ void __launch_bounds__(256) cell_scatter_kernel(ScatterArgs a) {
-    if (a.flags[FLAG_REBUILD] == 0) return;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void cell_scatter_phase(int vb, const ScatterArgs& a) {
+    const int s = vb * REBUILD_THREADS + threadIdx.x;
     if (s >= a.n) return;
     const int i = a.grouped[s];
     const int c = a.cell_of[i];
@@ -279,14 +274,15 @@ __global__ void __launch_bounds__(256)
                        const double* __restrict__ xref, const double4* __restrict__ rel0,
                        const int* __restrict__ sorted_cell, const int* __restrict__ cell_start,
                        double4* __restrict__ sorted_pos,
-                       double* __restrict__ frame, size_t frame_stride, double threshold2, int* __restrict__ flags) {
+                       double* __restrict__ frame, size_t frame_stride, double threshold2, int epoch,
+                       int* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int i = order[s];
     const double dx = pos[3 * i] - xref[3 * i];
     const double dy = pos[3 * i + 1] - xref[3 * i + 1];
     const double dz = pos[3 * i + 2] - xref[3 * i + 2];
-    if (!(dx * dx + dy * dy + dz * dz <= threshold2)) flags[FLAG_REBUILD] = 1;  // also catches NaN
+    if (!(dx * dx + dy * dy + dz * dz <= threshold2)) flags[FLAG_REBUILD] = epoch;  // also catches NaN
     const double4 r = rel0[s];
     const double x = r.x + dx, y = r.y + dy, z = r.z + dz;
     sorted_pos[s] = make_double4(x, y, z, r.w);
@@ -301,11 +297,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__global__ void list_finish_kernel(int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
-    flags[FLAG_REBUILD] = 0;
-    flags[FLAG_COUNT] += 1;
-}
 
 // ------------------------------------------------------------------------------------------------
 // staging tables
@@ -381,10 +372,9 @@ struct TableArgs {
 };
 
 // one warp per block of TB atoms
-__global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
-    if (a.flags[FLAG_REBUILD] == 0) return;
+__device__ __forceinline__ void block_table_phase(int vb, const TableArgs& a) {
     const int lane = threadIdx.x & 31;
-    const int block = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int block = vb * REBUILD_WARPS + (threadIdx.x >> 5);
     if (block >= a.nblocks) return;
     const int s_first = block * TB, s_last = min(a.n, s_first + TB) - 1;
     const int c_first = a.sorted_cell[s_first], c_last = a.sorted_cell[s_last];
@@ -479,8 +469,7 @@ __global__ void __launch_bounds__(128) block_table_kernel(TableArgs a) {
 // ------------------------------------------------------------------------------------------------
 
 constexpr unsigned LIST_INDEX_MASK = (1u << 26) - 1u;
-constexpr int BUILD_THREADS = 128;
-constexpr int BUILD_WARPS = BUILD_THREADS / 32;
+constexpr int BUILD_WARPS = REBUILD_WARPS;
 
 struct BuildArgs {
     GridView g;
@@ -500,18 +489,10 @@ struct BuildArgs {
     int* __restrict__ flags;
 };
 
-__global__ void __launch_bounds__(BUILD_THREADS) list_build_kernel(BuildArgs a) {
-    if (a.flags[FLAG_REBUILD] == 0) return;
-    __shared__ float offset32[27][3];
-    if (threadIdx.x < 27) {
-        const int t = threadIdx.x;
-        offset32[t][0] = (float)((double)((t % 3) - 1) * a.g.edge[0]);
-        offset32[t][1] = (float)((double)(((t / 3) % 3) - 1) * a.g.edge[1]);
-        offset32[t][2] = (float)((double)((t / 9) - 1) * a.g.edge[2]);
-    }
-    __syncthreads();
+// offset32: (a, b, c) * edge of the 27 neighbour-cell offsets, in shared memory
+__device__ __forceinline__ void list_build_phase(int vb, const BuildArgs& a, const float (*offset32)[3]) {
     const int lane = threadIdx.x & 31;
-    const int global_warp = blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5);
+    const int global_warp = vb * BUILD_WARPS + (threadIdx.x >> 5);
     const int cell_lo = global_warp * a.cells_per_warp;
     const int cell_hi = min(a.ncells, cell_lo + a.cells_per_warp);
 
@@ -638,14 +619,15 @@ constexpr int REORDER_THREADS = 32;
 
 __global__ void __launch_bounds__(REORDER_THREADS)
     list_reorder_kernel(int n, int capacity, const int4* __restrict__ blk_header, const int* __restrict__ ncount,
-                        unsigned* __restrict__ nlist, const int* __restrict__ flags) {
-    if (flags[FLAG_REBUILD] == 0) return;
+                        unsigned* __restrict__ nlist, int epoch, const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] != epoch) return;
     extern __shared__ unsigned short sorted[];  // entry p of thread t at [p * REORDER_THREADS + t]
     __shared__ unsigned short cursor[16][REORDER_THREADS], last[16][REORDER_THREADS];
     const int t = threadIdx.x;
-    const int s_i = blockIdx.x * REORDER_THREADS + t;
-    if (s_i >= n) return;
-    if (blk_header[s_i / TB].z < 0) return;  // global format: no shared-memory gathers
+    for (int slab = blockIdx.x; slab * REORDER_THREADS < n; slab += gridDim.x) {
+    const int s_i = slab * REORDER_THREADS + t;
+    if (s_i >= n) continue;
+    if (blk_header[s_i / TB].z < 0) continue;  // global format: no shared-memory gathers
     const int count = ncount[s_i];
     unsigned short* column16 =
         reinterpret_cast<unsigned short*>(nlist + ((size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31)) * 4);
@@ -680,6 +662,71 @@ __global__ void __launch_bounds__(REORDER_THREADS)
         column16[(k >> 3) * 256 + (k & 7)] = sorted[position * REORDER_THREADS + t];
         bucket = (bucket + 1) & 15;
     }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the rebuild as one cooperative kernel
+// ------------------------------------------------------------------------------------------------
+//
+// Whether to rebuild is decided on the device: list_update_kernel writes the current epoch into
+// flags[FLAG_REBUILD] when an atom moved too far.  The rebuild used to be eleven kernels launched every step,
+// each returning at once while no rebuild was due: about 50 us per step of the 1M-atom box (empty grids of
+// thousands of blocks are not free).  It is now ONE cooperative kernel whose phases are separated by grid-wide
+// barriers, followed by the reorder kernel on a small persistent grid: two cheap launches when nothing is due.
+
+struct RebuildArgs {
+    int n, ncells, scan_blocks, nblocks, epoch;
+    GridView g;
+    const double* position;
+    int *cell_of, *slot_of, *cell_count, *cell_start, *scan_scratch, *grouped;
+    ScatterArgs scatter;
+    TableArgs table;
+    BuildArgs build;
+    int* flags;
+};
+
+__global__ void __launch_bounds__(REBUILD_THREADS) rebuild_kernel(RebuildArgs r) {
+    if (r.flags[FLAG_REBUILD] != r.epoch) return;  // every block takes the same decision: nobody waits at a barrier
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ int scan_shared[33];
+    __shared__ float offset32[27][3];
+    if (threadIdx.x < 27) {
+        const int t = threadIdx.x;
+        offset32[t][0] = (float)((double)((t % 3) - 1) * r.g.edge[0]);
+        offset32[t][1] = (float)((double)(((t / 3) % 3) - 1) * r.g.edge[1]);
+        offset32[t][2] = (float)((double)((t / 9) - 1) * r.g.edge[2]);
+    }
+    const int atom_blocks = (r.n + REBUILD_THREADS - 1) / REBUILD_THREADS;
+
+    cell_zero_phase(r.ncells + 1, r.cell_count, r.flags);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
+        cell_assign_phase(vb, r.n, r.g, r.position, r.cell_of, r.slot_of, r.cell_count);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < r.scan_blocks; vb += gridDim.x) {
+        scan_blocks_phase(vb, r.ncells, r.cell_count, r.cell_start, r.scan_scratch, scan_shared);
+    }
+    grid.sync();
+    if (blockIdx.x == 0) scan_sums_phase(r.scan_blocks, r.scan_scratch, scan_shared);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < r.scan_blocks; vb += gridDim.x) {
+        scan_add_phase(vb, r.ncells, r.cell_start, r.scan_scratch, r.n);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
+        cell_group_phase(vb, r.n, r.cell_of, r.slot_of, r.cell_start, r.grouped);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) cell_scatter_phase(vb, r.scatter);
+    grid.sync();
+    for (int vb = blockIdx.x; vb * REBUILD_WARPS < r.nblocks; vb += gridDim.x) block_table_phase(vb, r.table);
+    grid.sync();
+    for (int vb = blockIdx.x; vb * BUILD_WARPS * r.build.cells_per_warp < r.ncells; vb += gridDim.x) {
+        list_build_phase(vb, r.build, offset32);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) r.flags[FLAG_COUNT] += 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1248,6 +1295,9 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     signature = mix(signature, lj_system ? 1 : 0);
     const bool reuse = ctx->list_valid && signature == ctx->list_signature;
     const int blocks = (n + 255) / 256;
+    // a rebuild is requested by writing the epoch of the evaluation into flags[FLAG_REBUILD] (never 0)
+    ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
+    const int epoch = ctx->list_epoch;
     {
         ScopedClock clock(ctx, &ctx->clk_neighbor);
         if (!reuse) {
@@ -1256,25 +1306,18 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
                 ctx->flags_initialised = true;
             }
             LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->frame_pos.ptr, 0, 3 * frame_stride * sizeof(double), ctx->stream));
-            set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, 1);
+            set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, epoch);
         } else {
             const double half = 0.5 * skin;
             list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
                                                                 ctx->sorted_cell.ptr, ctx->cell_start.ptr, ctx->sorted_pos.ptr,
                                                                 allow_staging ? ctx->frame_pos.ptr : nullptr, frame_stride,
-                                                                half * half, flags);
+                                                                half * half, epoch, flags);
         }
         ctx->launches++;
         ctx->clk_neighbor.launches++;
 
-        // ---- rebuild pipeline (no-ops while flags[FLAG_REBUILD] == 0) -----------------------------------
-        cell_zero_kernel<<<64, 256, 0, ctx->stream>>>(ncells + 1, ctx->cell_count.ptr, flags);
-        cell_assign_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, ctx->position.ptr, cell_of, slot_of, ctx->cell_count.ptr, flags);
-        scan_blocks_kernel<<<scan_blocks, SCAN_THREADS, 0, ctx->stream>>>(ncells, ctx->cell_count.ptr, ctx->cell_start.ptr,
-                                                                          ctx->scan_scratch.ptr, flags);
-        scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(scan_blocks, ctx->scan_scratch.ptr, flags);
-        scan_add_kernel<<<scan_blocks, SCAN_THREADS, 0, ctx->stream>>>(ncells, ctx->cell_start.ptr, ctx->scan_scratch.ptr, n, flags);
-        cell_group_kernel<<<blocks, 256, 0, ctx->stream>>>(n, cell_of, slot_of, ctx->cell_start.ptr, grouped, flags);
+        // ---- rebuild pipeline: does nothing unless flags[FLAG_REBUILD] holds this epoch ---------------------------
         ScatterArgs s;
         s.n = n;
         s.g = g;
@@ -1295,8 +1338,6 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         s.frame = ctx->frame_pos.ptr;
         s.frame_stride = frame_stride;
         s.xref = ctx->xref.ptr;
-        s.flags = flags;
-        cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(s);
 
         TableArgs t;
         t.g = g;
@@ -1313,16 +1354,12 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         t.o_lo = (int)o_lo;
         t.o_hi = (int)o_hi;
         t.flags = flags;
-        block_table_kernel<<<(nblocks + 3) / 4, 128, 0, ctx->stream>>>(t);
 
         BuildArgs b;
         b.g = g;
         b.ncells = ncells;
-        int build_blocks = ctx->sm_count * 8;
-        int warps = build_blocks * BUILD_WARPS;
-        b.cells_per_warp = (ncells + warps - 1) / warps;
-        if (b.cells_per_warp < 1) b.cells_per_warp = 1;
-        build_blocks = (ncells + b.cells_per_warp * BUILD_WARPS - 1) / (b.cells_per_warp * BUILD_WARPS);
+        // one warp per `cells_per_warp` consecutive cells: about sixteen work items per resident warp
+        b.cells_per_warp = ncells / (ctx->sm_count * 8 * BUILD_WARPS * 16) + 1;
         b.o_lo = (int)o_lo;
         b.o_hi = (int)o_hi;
         b.capacity = capacity;
@@ -1336,21 +1373,50 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         b.nlist = ctx->nlist.ptr;
         b.ncount = ctx->ncount.ptr;
         b.flags = flags;
-        list_build_kernel<<<build_blocks, BUILD_THREADS, 0, ctx->stream>>>(b);
+        RebuildArgs r;
+        r.n = n;
+        r.ncells = ncells;
+        r.scan_blocks = scan_blocks;
+        r.nblocks = nblocks;
+        r.epoch = epoch;
+        r.g = g;
+        r.position = ctx->position.ptr;
+        r.cell_of = cell_of;
+        r.slot_of = slot_of;
+        r.cell_count = ctx->cell_count.ptr;
+        r.cell_start = ctx->cell_start.ptr;
+        r.scan_scratch = ctx->scan_scratch.ptr;
+        r.grouped = grouped;
+        r.scatter = s;
+        r.table = t;
+        r.build = b;
+        r.flags = flags;
+        if (ctx->rebuild_grid == 0) {
+            int per_sm = 0;
+            LUMOL_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rebuild_kernel, REBUILD_THREADS, 0));
+            if (per_sm < 1) return ctx->fail(LUMOL_CUDA_ERROR_CUDA, "the rebuild kernel does not fit on the device");
+            ctx->rebuild_grid = per_sm * ctx->sm_count;
+        }
+        {
+            void* params[] = {&r};
+            LUMOL_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)rebuild_kernel, dim3(ctx->rebuild_grid),
+                                                              dim3(REBUILD_THREADS), params, 0, ctx->stream));
+        }
+        ctx->launches++;
+        ctx->clk_neighbor.launches++;
         const size_t reorder_smem = (size_t)capacity * REORDER_THREADS * sizeof(unsigned short);
         if (allow_staging && reorder_smem <= 200 * 1024) {
             if (reorder_smem > 40 * 1024) {
                 LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                            (int)reorder_smem));
             }
-            list_reorder_kernel<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, reorder_smem, ctx->stream>>>(
-                n, capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, flags);
+            const int slabs = (n + REORDER_THREADS - 1) / REORDER_THREADS;
+            const int reorder_grid = slabs < ctx->sm_count * 10 ? slabs : ctx->sm_count * 10;
+            list_reorder_kernel<<<reorder_grid, REORDER_THREADS, reorder_smem, ctx->stream>>>(
+                n, capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, epoch, flags);
             ctx->launches++;
             ctx->clk_neighbor.launches++;
         }
-        list_finish_kernel<<<1, 1, 0, ctx->stream>>>(flags);
-        ctx->launches += 10;
-        ctx->clk_neighbor.launches += 10;
         LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
     }
     ctx->list_valid = true;
