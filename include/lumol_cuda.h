@@ -286,6 +286,10 @@ int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t path);
  * than skin / 2 since the last build.  Results do not depend on it: every listed pair is re-tested against its
  * cut-off in FP64 at every evaluation. */
 int32_t lumol_cuda_set_neighbor_skin(lumol_cuda_context* ctx, double skin);
+/* Kernels of the Ewald reciprocal-space sums (eik_dot_r and k_space_*, ewald.rs:633-733): -1 automatic (tiled for
+ * large N x Nk), 0 direct (one thread per k-vector / per atom), 1 tiled (register-tiled contractions sharing the
+ * +l / -l products).  Same sums, different summation order. */
+int32_t lumol_cuda_set_kspace_algorithm(lumol_cuda_context* ctx, int32_t algorithm);
 /* cudaStream_t the context launches on, for event timing by the harness. */
 void* lumol_cuda_stream(lumol_cuda_context* ctx);
 int32_t lumol_cuda_synchronize(lumol_cuda_context* ctx);

@@ -156,6 +156,7 @@ SIGNATURES = {
     "lumol_cuda_reset_stats": (_c.c_int32, [_ctx]),
     "lumol_cuda_set_neighbor_path": (_c.c_int32, [_ctx, _c.c_int32]),
     "lumol_cuda_set_neighbor_skin": (_c.c_int32, [_ctx, _c.c_double]),
+    "lumol_cuda_set_kspace_algorithm": (_c.c_int32, [_ctx, _c.c_int32]),
     "lumol_cuda_stream": (_c.c_void_p, [_ctx]),
     "lumol_cuda_synchronize": (_c.c_int32, [_ctx]),
     "lumol_cuda_measure_fp64_peak": (_c.c_int32, [_ctx, _dp]),

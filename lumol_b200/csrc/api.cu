@@ -89,6 +89,7 @@ extern "C" int32_t lumol_cuda_destroy(lumol_cuda_context* ctx) {
     c->angles.release(); c->dihedrals.release(); c->kindex.release(); c->kenergy.release(); c->kvirial.release();
     c->rho.release(); c->rho_partial.release(); c->cell_of.release(); c->cell_count.release();
     c->cell_start.release(); c->order.release(); c->sorted_pos.release(); c->sorted_f32.release(); c->sorted_info.release();
+    c->krows.release(); c->kgmat.release(); c->kforce_partial.release();
     c->sorted_cell.release(); c->frame_pos.release(); c->blk_map.release(); c->blk_runs.release(); c->blk_header.release(); c->blk_entries.release(); c->self_local.release();
     c->nl_flags.release(); c->nlist.release(); c->ncount.release(); c->xref.release(); c->rel0.release();
     c->scan_scratch.release(); c->partials.release(); c->reduce_scratch.release(); c->results.release();
@@ -1000,6 +1001,15 @@ extern "C" int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t
     if (path < -1 || path > 2) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "neighbour path must be -1, 0, 1 or 2");
     c->forced_path = path;
     c->structure_generation++;
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_set_kspace_algorithm(lumol_cuda_context* ctx, int32_t algorithm) {
+    CTX_OR_FAIL(ctx);
+    if (algorithm < -1 || algorithm > 1) {
+        return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "the k-space algorithm must be -1, 0 or 1");
+    }
+    c->kspace_algorithm = algorithm;
     return LUMOL_CUDA_SUCCESS;
 }
 

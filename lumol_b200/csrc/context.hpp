@@ -141,6 +141,11 @@ struct Context {
     DeviceBuffer<double> kenergy;  // EwaldFactor::energy
     DeviceBuffer<double> kvirial;  // 6 per k
     DeviceBuffer<double2> rho, rho_partial;
+    DeviceBuffer<int4> krows;        // (h, k) rows of the k list (KRow, ewald.cu)
+    int64_t nkrows = 0;
+    bool krows_regular = false;
+    int kspace_algorithm = -1;       // -1 automatic, 0 direct kernels, 1 tiled kernels
+    DeviceBuffer<double> kgmat, kforce_partial;
     double kbasis[9] = {0};  // k_vector of the three unit indices, one per row
 
     // ---- neighbour search ----------------------------------------------------------------------

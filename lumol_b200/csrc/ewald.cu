@@ -18,6 +18,14 @@
 
 namespace lumol {
 
+// One (h, k) row of the k list for the tiled kernels: its entries are contiguous, l in [l_lo, l_hi].
+struct KRow {
+    int h, k;
+    int base;     // list index of (h, k, l_lo)
+    int l_lo_hi;  // l_lo | l_hi << 16 (both as 16-bit signed)
+};
+static_assert(sizeof(KRow) == sizeof(int4), "KRow is stored in an int4 buffer");
+
 // ------------------------------------------------------------------------------------------------
 // factor table (host, FP64, same enumeration order and arithmetic as the reference)
 // ------------------------------------------------------------------------------------------------
@@ -97,6 +105,35 @@ int ewald_prepare(Context* ctx) {
     for (int ikz = 1; ikz < kmax; ikz++) push(0, 0, ikz);
 
     ctx->nk = (int64_t)index.size();
+    // rows of the tiled kernels: the entries of one (h, k) are contiguous with l increasing by one
+    {
+        std::vector<KRow> rows;
+        bool regular = true;
+        for (size_t e = 0; e < index.size(); e++) {
+            const short4 v = index[e];
+            if (!rows.empty() && rows.back().h == v.x && rows.back().k == v.y) {
+                const int l_hi = rows.back().l_lo_hi >> 16;
+                if (v.z != l_hi + 1) regular = false;
+                rows.back().l_lo_hi = (rows.back().l_lo_hi & 0xffff) | ((int)v.z << 16);
+            } else {
+                KRow row;
+                row.h = v.x;
+                row.k = v.y;
+                row.base = (int)e;
+                row.l_lo_hi = ((int)v.z & 0xffff) | ((int)v.z << 16);
+                if (v.x < 0) regular = false;
+                rows.push_back(row);
+            }
+        }
+        ctx->krows_regular = regular && !rows.empty();
+        ctx->nkrows = (int64_t)rows.size();
+        LUMOL_CUDA_CHECK(ctx, ctx->krows.reserve(rows.size() + 1));
+        if (!rows.empty()) {
+            LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(reinterpret_cast<KRow*>(ctx->krows.ptr), rows.data(), rows.size() * sizeof(KRow), cudaMemcpyHostToDevice,
+                                                  ctx->stream));
+            LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
     const double e0[3] = {1, 0, 0}, e1[3] = {0, 1, 0}, e2[3] = {0, 0, 1};
     host_k_vector(inv, e0, ctx->kbasis);
     host_k_vector(inv, e1, ctx->kbasis + 3);
@@ -406,6 +443,375 @@ __global__ void __launch_bounds__(KFORCE_THREADS) ewald_force_kernel(KForceArgs 
     }
 }
 
+// ================================================================================================
+// Tiled reciprocal space (large N x Nk)
+// ================================================================================================
+//
+// rho(h,k,l) = sum_i q_i e_x(h,i) e_y(k,i) e_z(l,i) is a contraction over atoms of A[(h,k), i] = q_i e_x e_y with
+// B[i, l] = e_z(l, i), and the force needs W0[i,(h,k)] = sum_l e_z(l,i) G(h,k,l), W1 = sum_l l e_z(l,i) G(h,k,l),
+// G = 2 e_k conj(rho_k): a contraction over l.  Both are register-tiled here like a GEMM, with the phase tables of a
+// tile of atoms rebuilt in shared memory by the reference's recursion (ewald.rs:655-662).  e_z(-l) = conj e_z(l)
+// makes +l and -l share their four real products, so a complex (atom, k) pair costs 2 DFMA for rho and 4 for the
+// forces instead of the 10 + 15 FP64 instructions of the direct kernels above.
+//
+// The k list is enumerated with l fastest (ewald.rs:144-182): the entries of one (h, k) "row" are contiguous,
+// l in [l_lo, l_hi]; rows carry the list index of their first entry.
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_ATOMS = 32;  // atoms per shared-memory tile of the rho kernel
+constexpr int TK_TR = 2;      // rows per thread
+constexpr int TK_TL = 4;      // |l| values per thread
+
+__device__ __forceinline__ int row_index(const KRow& row, int l) {
+    const int l_lo = (short)(row.l_lo_hi & 0xffff), l_hi = row.l_lo_hi >> 16;
+    return (l >= l_lo && l <= l_hi) ? row.base + (l - l_lo) : -1;
+}
+
+struct TiledRhoArgs {
+    const double* __restrict__ pos;
+    const double* __restrict__ charge;
+    int a_lo, a_hi;
+    int nchunks;
+    int kmax;
+    int nk, nrows;
+    int lq;          // thread columns: ceil((kmax + 1) / TK_TL)
+    int row_groups;  // thread rows: TK_THREADS / lq
+    KBasis basis;
+    const KRow* __restrict__ rows;
+    double2* __restrict__ rho_partial;  // nchunks x nk
+};
+
+// Shared: tables [atom][axis][m] (TK_ATOMS x 3 x lpad complex, lpad = lq * TK_TL >= kmax + 1) and A [atom][row]
+// (TK_ATOMS x rows per block): in the main loop every thread of a warp reads the same atom, so rows and |l|
+// values must be the fastest index for the reads to be conflict-free.
+// grid: (row tiles, atom chunks)
+__global__ void __launch_bounds__(TK_THREADS) ewald_rho_tiled_kernel(TiledRhoArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lpad = a.lq * TK_TL;
+    double2* table = reinterpret_cast<double2*>(smem_raw);
+    double2* amat = table + (size_t)TK_ATOMS * 3 * lpad;
+    const int rows_per_block = a.row_groups * TK_TR;
+    __shared__ KRow s_rows[TK_THREADS];  // rows_per_block <= TK_THREADS (checked on the host)
+
+    const int t = threadIdx.x;
+    const int row0 = blockIdx.x * rows_per_block;
+    for (int r = t; r < rows_per_block; r += TK_THREADS) {
+        KRow row;
+        row.h = row.k = 0;
+        row.base = 0;
+        row.l_lo_hi = (0 << 16) | 1;  // empty interval: l_lo = 1 > l_hi = 0
+        if (row0 + r < a.nrows) row = a.rows[row0 + r];
+        s_rows[r] = row;
+    }
+    __syncthreads();  // also for blocks whose atom chunk is empty: they still write zeros for their rows
+    const int lq = t % a.lq, rg = t / a.lq;
+    const bool worker = rg < a.row_groups;
+
+    const int owned = a.a_hi - a.a_lo;
+    const int per_chunk = (owned + a.nchunks - 1) / a.nchunks;
+    const int c_lo = a.a_lo + blockIdx.y * per_chunk;
+    const int c_hi = min(a.a_hi, c_lo + per_chunk);
+
+    // P1 = sum ar br, P2 = sum ai bi, P3 = sum ar bi, P4 = sum ai br per (row, |l|)
+    double acc[TK_TR][TK_TL][4];
+#pragma unroll
+    for (int r = 0; r < TK_TR; r++)
+#pragma unroll
+        for (int l = 0; l < TK_TL; l++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][l][c] = 0.0;
+
+    for (int base = c_lo; base < c_hi; base += TK_ATOMS) {
+        const int count = min(TK_ATOMS, c_hi - base);
+        __syncthreads();
+        // phase tables: 3 * TK_ATOMS independent recursions; missing atoms get zero charge below
+        if (t < 3 * TK_ATOMS) {
+            const int atom = t % TK_ATOMS, axis = t / TK_ATOMS;
+            const int i = base + min(atom, count - 1);
+            const double phase = a.basis.b[3 * axis] * a.pos[3 * i] + a.basis.b[3 * axis + 1] * a.pos[3 * i + 1] +
+                                 a.basis.b[3 * axis + 2] * a.pos[3 * i + 2];
+            double sn, cs;
+            sincos(phase, &sn, &cs);
+            double2* column = table + (size_t)(atom * 3 + axis) * lpad;
+            const double2 e1 = make_double2(cs, sn);
+            double2 e = make_double2(1.0, 0.0);
+            column[0] = e;
+            for (int m = 1; m < lpad; m++) {  // entries beyond kmax are computed but never stored in rho
+                e = m == 1 ? e1 : cmul(e, e1);
+                column[m] = e;
+            }
+        }
+        __syncthreads();
+        // A[atom][row] = q e_x(h) e_y(k); h >= 0 in the half space, e_y(-k) = conj e_y(k)
+        for (int w = t; w < rows_per_block * TK_ATOMS; w += TK_THREADS) {
+            const int atom = w / rows_per_block, r = w - atom * rows_per_block;
+            const KRow row = s_rows[r];
+            const double2* tables = table + (size_t)atom * 3 * lpad;
+            const double2 ex = tables[row.h];
+            double2 ey = tables[lpad + abs(row.k)];
+            if (row.k < 0) ey.y = -ey.y;
+            const double q = atom < count ? a.charge[base + atom] : 0.0;
+            const double2 e = cmul(ex, ey);
+            amat[w] = make_double2(q * e.x, q * e.y);
+        }
+        __syncthreads();
+        if (worker) {
+            // thread (rg, lq) owns rows rg + r * row_groups and |l| = lq + l * a.lq: for a given r or l the threads of
+            // a warp read consecutive 16-byte words
+            const double2* arow = amat + rg;
+            const double2* bcol = table + 2 * lpad + lq;
+#pragma unroll 2
+            for (int atom = 0; atom < TK_ATOMS; atom++) {
+                double2 av[TK_TR], bv[TK_TL];
+#pragma unroll
+                for (int r = 0; r < TK_TR; r++) av[r] = arow[(size_t)atom * rows_per_block + r * a.row_groups];
+#pragma unroll
+                for (int l = 0; l < TK_TL; l++) bv[l] = bcol[(size_t)atom * 3 * lpad + l * a.lq];
+#pragma unroll
+                for (int r = 0; r < TK_TR; r++)
+#pragma unroll
+                    for (int l = 0; l < TK_TL; l++) {
+                        acc[r][l][0] = fma(av[r].x, bv[l].x, acc[r][l][0]);
+                        acc[r][l][1] = fma(av[r].y, bv[l].y, acc[r][l][1]);
+                        acc[r][l][2] = fma(av[r].x, bv[l].y, acc[r][l][2]);
+                        acc[r][l][3] = fma(av[r].y, bv[l].x, acc[r][l][3]);
+                    }
+            }
+        }
+    }
+    if (worker) {
+        double2* out = a.rho_partial + (size_t)blockIdx.y * a.nk;
+#pragma unroll
+        for (int r = 0; r < TK_TR; r++) {
+            const KRow row = s_rows[rg + r * a.row_groups];
+#pragma unroll
+            for (int l = 0; l < TK_TL; l++) {
+                const int m = lq + l * a.lq;
+                if (m > a.kmax) continue;
+                const int plus = row_index(row, m);
+                if (plus >= 0) out[plus] = make_double2(acc[r][l][0] - acc[r][l][1], acc[r][l][2] + acc[r][l][3]);
+                const int minus = m > 0 ? row_index(row, -m) : -1;
+                if (minus >= 0) out[minus] = make_double2(acc[r][l][0] + acc[r][l][1], acc[r][l][3] - acc[r][l][2]);
+            }
+        }
+    }
+}
+
+// G matrix of the force kernel: per (row, |l|) eight doubles
+//   S = g+ + g-, D = g+ - g-, g = 2 e_k conj(rho_k) (0 outside the list; for l = 0 only g+):
+//   {S.re, D.im, S.im, D.re, l D.re, l S.im, l D.im, l S.re}
+__global__ void __launch_bounds__(256)
+    ewald_gmat_kernel(int nrows, int kmax, const KRow* __restrict__ rows, const double2* __restrict__ rho,
+                      const double* __restrict__ kenergy, double* __restrict__ gmat) {
+    const int lp = kmax + 1;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nrows * lp) return;
+    const int r = w / lp, m = w % lp;
+    const KRow row = rows[r];
+    double2 gp = make_double2(0.0, 0.0), gm = make_double2(0.0, 0.0);
+    const int plus = row_index(row, m);
+    if (plus >= 0) {
+        const double2 v = rho[plus];
+        const double f = 2.0 * kenergy[plus];
+        gp = make_double2(f * v.x, -f * v.y);
+    }
+    const int minus = m > 0 ? row_index(row, -m) : -1;
+    if (minus >= 0) {
+        const double2 v = rho[minus];
+        const double f = 2.0 * kenergy[minus];
+        gm = make_double2(f * v.x, -f * v.y);
+    }
+    const double sr = gp.x + gm.x, si = gp.y + gm.y, dr = gp.x - gm.x, di = gp.y - gm.y;
+    const double l = (double)m;
+    double* g = gmat + (size_t)w * 8;
+    g[0] = sr;
+    g[1] = di;
+    g[2] = si;
+    g[3] = dr;
+    g[4] = l * dr;
+    g[5] = l * si;
+    g[6] = l * di;
+    g[7] = l * sr;
+}
+
+constexpr int TF_TA = 4;          // atoms per thread
+constexpr int TF_TR = 2;          // rows per thread
+constexpr int TF_ROW_GROUPS = 8;  // thread rows
+constexpr int TF_ROWS = TF_ROW_GROUPS * TF_TR;  // rows per staged tile: 16
+
+struct TiledForceArgs {
+    const double* __restrict__ pos;
+    const double* __restrict__ charge;
+    int a_lo, a_hi;
+    int kmax;
+    int nrows;
+    int nsplit;  // gridDim.y: the rows are split between blocks of the same atoms
+    KBasis basis;
+    const KRow* __restrict__ rows;
+    const double* __restrict__ gmat;
+    double* __restrict__ force;    // nsplit == 1: accumulated directly
+    double* __restrict__ partial;  // nsplit > 1: [split][owned atom][3] (sum_h, sum_k, sum_l), reduced afterwards
+};
+
+// Shared: tables [axis][m][atom] (3 x (kmax + 1) x TF_ATOMS complex) + G tile (TF_ROWS x (kmax + 1) x 8 doubles).
+// TF_ATOMS atoms per block (64, or 32 when kmax is large), TF_ATOMS / TF_TA x TF_ROW_GROUPS threads.
+template <int TF_ATOMS>
+__global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_tiled_kernel(TiledForceArgs a) {
+    constexpr int TF_THREADS = TF_ATOMS / TF_TA * TF_ROW_GROUPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lp = a.kmax + 1;
+    double2* table = reinterpret_cast<double2*>(smem_raw);
+    double* gtile = reinterpret_cast<double*>(table + (size_t)3 * lp * TF_ATOMS);
+    const int gstride = lp * 8 + 4;  // doubles per row of the staged G tile: neighbouring rows in different banks
+    __shared__ KRow s_rows[TF_ROWS];
+
+    const int t = threadIdx.x;
+    const int base = a.a_lo + blockIdx.x * TF_ATOMS;
+    const int count = min(TF_ATOMS, a.a_hi - base);
+    for (int w = t; w < 3 * TF_ATOMS; w += TF_THREADS) {
+        const int atom = w % TF_ATOMS, axis = w / TF_ATOMS;
+        const int i = base + min(atom, count - 1);
+        const double phase = a.basis.b[3 * axis] * a.pos[3 * i] + a.basis.b[3 * axis + 1] * a.pos[3 * i + 1] +
+                             a.basis.b[3 * axis + 2] * a.pos[3 * i + 2];
+        double sn, cs;
+        sincos(phase, &sn, &cs);
+        double2* column = table + (size_t)axis * lp * TF_ATOMS + atom;
+        const double2 e1 = make_double2(cs, sn);
+        double2 e = make_double2(1.0, 0.0);
+        column[0] = e;
+        if (a.kmax >= 1) {
+            e = e1;
+            column[TF_ATOMS] = e;
+        }
+        for (int m = 2; m <= a.kmax; m++) {
+            e = cmul(e, e1);
+            column[(size_t)m * TF_ATOMS] = e;
+        }
+    }
+
+    // thread (ag, rg) owns atoms ag + x * AG and rows rg + r * TF_ROW_GROUPS: for a given x the threads of a warp
+    // read consecutive 16-byte words of the phase tables
+    constexpr int AG = TF_ATOMS / TF_TA;
+    const int ag = t % AG, rg = t / AG;
+    double sh[TF_TA], sk[TF_TA], sl[TF_TA];
+#pragma unroll
+    for (int x = 0; x < TF_TA; x++) sh[x] = sk[x] = sl[x] = 0.0;
+
+    // rows of this block: [row_lo, row_hi), walked in tiles of TF_ROWS
+    const int rows_per_split = ((a.nrows + a.nsplit - 1) / a.nsplit + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
+    const int row_lo = blockIdx.y * rows_per_split;
+    const int row_hi = min(a.nrows, row_lo + rows_per_split);
+    const double2* ez = table + (size_t)2 * lp * TF_ATOMS + ag;
+    for (int tile = row_lo; tile < row_hi; tile += TF_ROWS) {
+        __syncthreads();
+        const int nrows = min(TF_ROWS, row_hi - tile);
+        {
+            const double* src = a.gmat + (size_t)tile * lp * 8;
+            for (int w = t; w < TF_ROWS * lp * 8; w += TF_THREADS) {
+                const int r = w / (lp * 8), c = w - r * (lp * 8);
+                gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
+            }
+            if (t < TF_ROWS) {
+                KRow row;
+                row.h = row.k = row.base = 0;
+                row.l_lo_hi = 1;
+                if (t < nrows) row = a.rows[tile + t];
+                s_rows[t] = row;
+            }
+        }
+        __syncthreads();
+        double w0[TF_TR][TF_TA][2], w1[TF_TR][TF_TA][2];
+#pragma unroll
+        for (int r = 0; r < TF_TR; r++)
+#pragma unroll
+            for (int x = 0; x < TF_TA; x++) w0[r][x][0] = w0[r][x][1] = w1[r][x][0] = w1[r][x][1] = 0.0;
+        const double* g0 = gtile + (size_t)rg * gstride;
+        for (int m = 0; m < lp; m++) {
+            double2 z[TF_TA];
+#pragma unroll
+            for (int x = 0; x < TF_TA; x++) z[x] = ez[(size_t)m * TF_ATOMS + x * AG];
+#pragma unroll
+            for (int r = 0; r < TF_TR; r++) {
+                const double4 ga = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 8);
+                const double4 gb = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 8 + 4);
+#pragma unroll
+                for (int x = 0; x < TF_TA; x++) {
+                    w0[r][x][0] = fma(z[x].x, ga.x, fma(-z[x].y, ga.y, w0[r][x][0]));
+                    w0[r][x][1] = fma(z[x].x, ga.z, fma(z[x].y, ga.w, w0[r][x][1]));
+                    w1[r][x][0] = fma(z[x].x, gb.x, fma(-z[x].y, gb.y, w1[r][x][0]));
+                    w1[r][x][1] = fma(z[x].x, gb.z, fma(z[x].y, gb.w, w1[r][x][1]));
+                }
+            }
+        }
+        // Im(u W) with u = e_x(h) e_y(k)
+#pragma unroll
+        for (int r = 0; r < TF_TR; r++) {
+            const KRow row = s_rows[rg + r * TF_ROW_GROUPS];
+#pragma unroll
+            for (int x = 0; x < TF_TA; x++) {
+                const double2 ex = table[(size_t)row.h * TF_ATOMS + ag + x * AG];
+                double2 ey = table[(size_t)(lp + abs(row.k)) * TF_ATOMS + ag + x * AG];
+                if (row.k < 0) ey.y = -ey.y;
+                const double2 u = cmul(ex, ey);
+                const double t0 = u.x * w0[r][x][1] + u.y * w0[r][x][0];
+                const double t1 = u.x * w1[r][x][1] + u.y * w1[r][x][0];
+                sh[x] = fma(t0, (double)row.h, sh[x]);
+                sk[x] = fma(t0, (double)row.k, sk[x]);
+                sl[x] += t1;
+            }
+        }
+    }
+    // sum over the row groups of the block, in a fixed order (the phase tables are dead: reuse their memory)
+    __syncthreads();
+    double (*s_sum)[TF_ATOMS][3] = reinterpret_cast<double (*)[TF_ATOMS][3]>(smem_raw);
+#pragma unroll
+    for (int x = 0; x < TF_TA; x++) {
+        s_sum[rg][ag + x * AG][0] = sh[x];
+        s_sum[rg][ag + x * AG][1] = sk[x];
+        s_sum[rg][ag + x * AG][2] = sl[x];
+    }
+    __syncthreads();
+    if (t < count) {
+        double th = 0.0, tk = 0.0, tl = 0.0;
+#pragma unroll
+        for (int g = 0; g < TF_ROW_GROUPS; g++) {
+            th += s_sum[g][t][0];
+            tk += s_sum[g][t][1];
+            tl += s_sum[g][t][2];
+        }
+        const int i = base + t;
+        if (a.nsplit == 1) {
+            const double scale = a.charge[i] / FOUR_PI_EPSILON_0;  // ewald.rs:716-718
+            a.force[3 * i] += scale * (th * a.basis.b[0] + tk * a.basis.b[3] + tl * a.basis.b[6]);
+            a.force[3 * i + 1] += scale * (th * a.basis.b[1] + tk * a.basis.b[4] + tl * a.basis.b[7]);
+            a.force[3 * i + 2] += scale * (th * a.basis.b[2] + tk * a.basis.b[5] + tl * a.basis.b[8]);
+        } else {
+            double* out = a.partial + ((size_t)blockIdx.y * (a.a_hi - a.a_lo) + (i - a.a_lo)) * 3;
+            out[0] = th;
+            out[1] = tk;
+            out[2] = tl;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    ewald_force_combine_kernel(int a_lo, int a_hi, int nsplit, KBasis basis, const double* __restrict__ charge,
+                               const double* __restrict__ partial, double* __restrict__ force) {
+    const int i = a_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a_hi) return;
+    double th = 0.0, tk = 0.0, tl = 0.0;
+    for (int s = 0; s < nsplit; s++) {
+        const double* p = partial + ((size_t)s * (a_hi - a_lo) + (i - a_lo)) * 3;
+        th += p[0];
+        tk += p[1];
+        tl += p[2];
+    }
+    const double scale = charge[i] / FOUR_PI_EPSILON_0;
+    force[3 * i] += scale * (th * basis.b[0] + tk * basis.b[3] + tl * basis.b[6]);
+    force[3 * i + 1] += scale * (th * basis.b[1] + tk * basis.b[4] + tl * basis.b[7]);
+    force[3 * i + 2] += scale * (th * basis.b[2] + tk * basis.b[5] + tl * basis.b[8]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------------
@@ -429,8 +835,54 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
         return 0;
     }
 
+    // ---- which kernels -----------------------------------------------------------------------------
+    // tiled (GEMM-like) kernels for large N x Nk, direct ones for the small systems and the molecular virial
+    const int lq = (kmax + 1 + TK_TL - 1) / TK_TL;
+    const size_t rho_tables = (size_t)3 * (lq * TK_TL) * TK_ATOMS * sizeof(double2);
+    const int row_groups = TK_THREADS / lq;
+    const size_t rho_smem = rho_tables + (size_t)row_groups * TK_TR * TK_ATOMS * sizeof(double2);
+    const size_t force_tables64 = (size_t)3 * (kmax + 1) * 64 * sizeof(double2), gtile = (size_t)TF_ROWS * ((kmax + 1) * 8 + 4) * sizeof(double);
+    const bool tiled_possible = ctx->krows_regular && kmax >= 8 && kmax <= 255 && rho_smem <= 200 * 1024 &&
+                                force_tables64 / 2 + gtile <= 200 * 1024;
+    bool tiled = tiled_possible && (ctx->kspace_algorithm == 1 || (ctx->kspace_algorithm < 0 && (int64_t)owned * nk >= (int64_t)1 << 24));
+    const bool tiled_forces = tiled && !req.molecular_virial;
+
     // ---- rho(k) ---------------------------------------------------------------------------------
-    {
+    int nchunks = 1;
+    if (tiled) {
+        const int nrows = (int)ctx->nkrows;
+        const int rows_per_block = row_groups * TK_TR;
+        const int row_tiles = (nrows + rows_per_block - 1) / rows_per_block;
+        nchunks = (2 * ctx->sm_count + row_tiles - 1) / row_tiles;
+        const int max_chunks = (owned + TK_ATOMS - 1) / TK_ATOMS;
+        if (nchunks > max_chunks) nchunks = max_chunks;
+        if (nchunks < 1) nchunks = 1;
+        if (nchunks > 65535) nchunks = 65535;
+        LUMOL_CUDA_CHECK(ctx, ctx->rho_partial.reserve((size_t)nchunks * nk));
+        TiledRhoArgs a;
+        a.pos = ctx->position.ptr;
+        a.charge = ctx->charge.ptr;
+        a.a_lo = (int)lo;
+        a.a_hi = (int)hi;
+        a.nchunks = nchunks;
+        a.kmax = kmax;
+        a.nk = nk;
+        a.nrows = nrows;
+        a.lq = lq;
+        a.row_groups = row_groups;
+        a.basis = basis;
+        a.rows = reinterpret_cast<const KRow*>(ctx->krows.ptr);
+        a.rho_partial = ctx->rho_partial.ptr;
+        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute((const void*)ewald_rho_tiled_kernel,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rho_smem));
+        {
+            ScopedClock clock(ctx, &ctx->clk_kspace);
+            ewald_rho_tiled_kernel<<<dim3(row_tiles, nchunks), TK_THREADS, rho_smem, ctx->stream>>>(a);
+            ctx->launches++;
+            ctx->clk_kspace.launches++;
+            LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+        }
+    } else {
         const int kblocks = (nk + RHO_THREADS - 1) / RHO_THREADS;
         // shared-memory tile: as many atoms as fit in ~96 KB, capped at 256
         const size_t per_atom = (size_t)3 * (kmax + 1) * sizeof(double2) + sizeof(double);
@@ -440,7 +892,7 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
             return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "kmax = %d needs more shared memory than one atom tile", kmax);
         }
         // enough chunks to fill the GPU a few times over, never more than one chunk per tile
-        int nchunks = (4 * ctx->sm_count + kblocks - 1) / kblocks;
+        nchunks = (4 * ctx->sm_count + kblocks - 1) / kblocks;
         const int max_chunks = (owned + tile - 1) / tile;
         if (nchunks > max_chunks) nchunks = max_chunks;
         if (nchunks < 1) nchunks = 1;
@@ -469,6 +921,8 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
             ctx->clk_kspace.launches++;
             LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
         }
+    }
+    {
         RhoReduceArgs r;
         r.nk = nk;
         r.nchunks = nchunks;
@@ -498,7 +952,58 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
     }
 
     // ---- forces -------------------------------------------------------------------------------------
-    if ((req.forces || req.molecular_virial) && owned > 0) {
+    if (tiled_forces && req.forces && owned > 0) {
+        const int nrows = (int)ctx->nkrows;
+        const int lp = kmax + 1;
+        LUMOL_CUDA_CHECK(ctx, ctx->kgmat.reserve((size_t)nrows * lp * 8 + 8));
+        ewald_gmat_kernel<<<(nrows * lp + 255) / 256, 256, 0, ctx->stream>>>(nrows, kmax, reinterpret_cast<const KRow*>(ctx->krows.ptr),
+                                                                           ctx->rho.ptr, ctx->kenergy.ptr, ctx->kgmat.ptr);
+        ctx->launches++;
+        LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+        // 64 atoms per block when two blocks fit on an SM, 32 atoms for large kmax
+        const bool wide = force_tables64 + gtile <= 110 * 1024;
+        const int atoms = wide ? 64 : 32;
+        const size_t smem = force_tables64 / (wide ? 1 : 2) + gtile;
+        const int ablocks = (owned + atoms - 1) / atoms;
+        int nsplit = (2 * ctx->sm_count + ablocks - 1) / ablocks;
+        const int max_split = (nrows + TF_ROWS - 1) / TF_ROWS;
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit > 64) nsplit = 64;
+        if (nsplit < 1) nsplit = 1;
+        TiledForceArgs a;
+        a.pos = ctx->position.ptr;
+        a.charge = ctx->charge.ptr;
+        a.a_lo = (int)lo;
+        a.a_hi = (int)hi;
+        a.kmax = kmax;
+        a.nrows = nrows;
+        a.nsplit = nsplit;
+        a.basis = basis;
+        a.rows = reinterpret_cast<const KRow*>(ctx->krows.ptr);
+        a.gmat = ctx->kgmat.ptr;
+        a.force = ctx->force.ptr;
+        a.partial = nullptr;
+        if (nsplit > 1) {
+            LUMOL_CUDA_CHECK(ctx, ctx->kforce_partial.reserve((size_t)nsplit * owned * 3));
+            a.partial = ctx->kforce_partial.ptr;
+        }
+        const void* kernel = wide ? (const void*)ewald_force_tiled_kernel<64> : (const void*)ewald_force_tiled_kernel<32>;
+        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            ScopedClock clock(ctx, &ctx->clk_kspace);
+            void* params[] = {&a};
+            LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(ablocks, nsplit), dim3(atoms / TF_TA * TF_ROW_GROUPS), params, smem,
+                                                   ctx->stream));
+            ctx->launches++;
+            ctx->clk_kspace.launches++;
+        }
+        if (nsplit > 1) {
+            ewald_force_combine_kernel<<<(owned + 255) / 256, 256, 0, ctx->stream>>>((int)lo, (int)hi, nsplit, basis, ctx->charge.ptr,
+                                                                                    ctx->kforce_partial.ptr, ctx->force.ptr);
+            ctx->launches++;
+            LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+        }
+    } else if ((req.forces || req.molecular_virial) && owned > 0) {
         if (req.molecular_virial) {
             status = launch_molecule_com(ctx);
             if (status != 0) return status;

@@ -264,6 +264,9 @@ class DeviceSystem:
     def set_neighbor_path(self, path):
         self._check(self.lib.lumol_cuda_set_neighbor_path(self.ctx, path))
 
+    def set_kspace_algorithm(self, algorithm):
+        self._check(self.lib.lumol_cuda_set_kspace_algorithm(self.ctx, algorithm))
+
 
 def device_for(system, coulomb="system", velocities=False):
     """The ``DeviceSystem`` of ``system``, created on first use and synchronised with the host arrays."""

@@ -100,6 +100,7 @@ extern "C" {
     pub fn lumol_cuda_comm_init(ctx: *mut lumol_cuda_context, nranks: i32, rank: i32, id: *const u8) -> i32;
     pub fn lumol_cuda_set_neighbor_skin(ctx: *mut lumol_cuda_context, skin: f64) -> i32;
     pub fn lumol_cuda_set_neighbor_path(ctx: *mut lumol_cuda_context, path: i32) -> i32;
+    pub fn lumol_cuda_set_kspace_algorithm(ctx: *mut lumol_cuda_context, algorithm: i32) -> i32;
     pub fn lumol_cuda_stream(ctx: *mut lumol_cuda_context) -> *mut c_void;
     pub fn lumol_cuda_synchronize(ctx: *mut lumol_cuda_context) -> i32;
 }

@@ -538,6 +538,31 @@ def test_ewald_structure_factor():
     check_system(system)
 
 
+def test_tiled_kspace_kernels_vs_oracle_and_direct():
+    """The register-tiled reciprocal-space kernels (sharing the +l / -l products) against the oracle and against the
+    direct kernels: 5184-atom SPC/E box, kmax 10 and an odd kmax with fewer |l| values than a thread tile, and a
+    triclinic cell whose rows of the k list are not symmetric in l."""
+    for kmax, alpha in ((10, 0.32), (13, 0.36)):
+        system = systems.spce_box(12)
+        ewald = lumol.SharedEwald(lumol.Ewald(9.0, kmax, alpha))
+        ewald.set_restriction(lumol.PairRestriction.InterMolecular)
+        system.set_coulomb_potential(ewald)
+        device = device_for(system)
+        device.set_kspace_algorithm(1)
+        device = check_system(system, molecular=False, path=1)
+        tiled = device.compute(forces=True, energy=True, virial=True, parts=_ffi.PART_COULOMB)
+        device.set_kspace_algorithm(0)
+        direct = device.compute(forces=True, energy=True, virial=True, parts=_ffi.PART_COULOMB)
+        assert np.abs(tiled.forces - direct.forces).max() < 1e-11 * np.abs(direct.forces).max()
+        assert abs(tiled.energy.coulomb_kspace - direct.energy.coulomb_kspace) < 1e-11 * abs(direct.energy.coulomb_kspace)
+        assert np.abs(tiled.virial - direct.virial).max() < 1e-10 * np.abs(direct.virial).max()
+    cell = lumol.UnitCell.triclinic(22.0, 23.0, 24.0, 80.0, 95.0, 105.0)
+    system = random_molecular_system(seed=8, cell=cell, natoms=480)
+    system.set_coulomb_potential(lumol.SharedEwald(lumol.Ewald(6.0, 12, 0.5)))
+    device_for(system).set_kspace_algorithm(1)
+    check_system(system)
+
+
 # ---- kinetic estimators ----------------------------------------------------------------------------------------------
 
 def test_kinetic_estimators():

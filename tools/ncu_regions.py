@@ -12,7 +12,7 @@ def main():
     col = {name: header.index(name) for name in ("Source", "# Samples", "stall_long_sb", "stall_short_sb", "stall_barrier",
                                                   "stall_wait", "stall_math", "stall_mio", "stall_not_selected", "stall_selected",
                                                   "Instructions Executed")}
-    data = rows[2:]
+    data = [r for r in rows[2:] if len(r) == len(header)]
     total = sum(int(r[col["# Samples"]]) for r in data)
     bars = [k for k, r in enumerate(data) if "BAR" in r[col["Source"]]]
     print("total samples", total, "barriers at", bars)
