@@ -35,7 +35,7 @@ FLOP_PER_LJ_PAIR_FORCE = 36.0
 FLOP_PER_COULOMB_PAIR = 75.0
 FLOP_PER_ATOM_K_RHO = 16.0
 FLOP_PER_ATOM_K_FORCE = 21.0
-BYTES_PER_ATOM_VV = 208.0
+BYTES_PER_ATOM_VV = 128.0  # merged second-half + first-half kick and drift (SURVEY 8d counts 208 B for the two separate passes)
 BYTES_PER_ATOM_SORT = 100.0
 
 
@@ -50,6 +50,9 @@ def parse_args():
     parser.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-e2e", action="store_true")
+    parser.add_argument("--no-spce", action="store_true", help="skip the SPC/E + Ewald companion run of the default (lj) bench")
+    parser.add_argument("--spce-lattice", default="32", help="molecules per axis of the SPC/E companion run")
+    parser.add_argument("--spce-steps", type=int, default=40)
     return parser.parse_args()
 
 
@@ -60,17 +63,19 @@ def lattice_of(text):
     return tuple(parts)
 
 
-def build_workload(args):
+def build_workload(args, workload=None, lattice_text=None):
     """The synthetic boxes of SURVEY section 8d, through the host-side API."""
     from lumol_b200 import synthetic
     import lumol_b200 as lumol
 
-    lattice = lattice_of(args.lattice)
-    if args.workload == "lj":
+    workload = workload or args.workload
+    lattice_text = lattice_text or args.lattice
+    lattice = lattice_of(lattice_text)
+    if workload == "lj":
         system = synthetic.lj_box(lattice, seed=20240 + 20)
         synthetic.maxwell_boltzmann(system, 120.0, seed=7)
         description = {
-            "workload": f"synthetic LJ argon box, {system.size()} atoms, lattice {args.lattice}, rho=0.0213/A^3, "
+            "workload": f"synthetic LJ argon box, {system.size()} atoms, lattice {lattice_text}, rho=0.0213/A^3, "
                         "sigma=3.4 A, eps=1 kJ/mol, rc=10 A, tail corrections, NVE velocity-Verlet dt=1 fs, 120 K",
             "atoms": system.size(),
             "cell_A": [round(float(v), 3) for v in system.cell.lengths()],
@@ -166,11 +171,13 @@ def cpu_sample_rows(system, target_seconds):
         lib.orc_pair_forces_sample(reference.ref, len(rows), oracle.iptr(rows), ctypes.byref(checksum))
         return time.perf_counter() - start
 
-    probe_rows = max(threads * 2, 16)
-    probe = run(probe_rows)
-    rows = int(min(n, max(probe_rows, probe_rows * target_seconds / max(probe, 1e-6))))
-    rows = max(threads, rows // threads * threads)
+    rows = max(threads * 2, 16)
     seconds = run(rows)
+    # grow the sample until it runs for about the target (the first probes are dominated by thread start-up)
+    while seconds < 0.6 * target_seconds and rows < n:
+        rows = int(min(n, max(rows * 2, rows * target_seconds / max(seconds, 1e-3))))
+        rows = max(threads, rows // threads * threads)
+        seconds = run(rows)
     return rows / seconds, rows, seconds, threads
 
 
@@ -203,36 +210,31 @@ def run_reference(args):
 
 # ---- GPU arm ---------------------------------------------------------------------------------------------------
 
-def main():
-    args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+def load_json(name):
+    try:
+        with open(os.path.join(ROOT, name)) as fd:
+            return json.load(fd)
+    except (OSError, ValueError):
+        return {}
 
+
+def measure(args, env, workload, lattice_text, steps, warmup, with_e2e, with_cpu):
+    """One workload on this rank's GPU: device-resident MD (value), e2e through the C ABI with host buffers, and a
+    profiled pass for the rooflines.  Returns the result dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
 
     from lumol_b200 import _ffi, md, parallel
     from lumol_b200.device import device_for
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: lumol_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    system, description = build_workload(args)
+    rank, world, local_rank = env
+    system, description = build_workload(args, workload, lattice_text)
     system.device_ordinal = local_rank
     n = system.size()
     device = device_for(system, velocities=True)
     lib, ctx = device.lib, device.ctx
-
     if world > 1:
         parallel.init_communicator(device, rank, world)
-
     stream = torch.cuda.ExternalStream(lib.lumol_cuda_stream(ctx))
 
     def barrier():
@@ -248,7 +250,7 @@ def main():
     propagator.setup(system)
 
     # ---- device-resident MD: warm-up, then exactly K timed steps --------------------------------------------
-    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, args.warmup))
+    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, warmup))
     barrier()
     _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
     rebuilds_before_timed = int(device.stats().neighbor_rebuilds)
@@ -258,7 +260,7 @@ def main():
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record(stream)
-    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, args.steps))
+    _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, steps))
     stop.record(stream)
     barrier()
     elapsed_ms = max_over_ranks(start.elapsed_time(stop))
@@ -266,11 +268,11 @@ def main():
     stats = device.stats()
     launches = int(stats.kernel_launches)
     rebuilds_timed = int(stats.neighbor_rebuilds) - rebuilds_before_timed
-    value = n * args.steps / (elapsed_ms * 1e-3)
+    value = n * steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         host_positions = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
         host_forces = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
         positions = np.zeros((n, 3))
@@ -278,7 +280,7 @@ def main():
         host_positions.copy_(torch.from_numpy(positions))
         p_in = ctypes.cast(host_positions.data_ptr(), ctypes.POINTER(ctypes.c_double))
         p_out = ctypes.cast(host_forces.data_ptr(), ctypes.POINTER(ctypes.c_double))
-        e2e_steps = max(3, min(args.steps, 50))
+        e2e_steps = max(3, min(steps, 50))
 
         def e2e_step():
             # what lumol's VelocityVerlet::integrate does around system.forces() (integrators.rs:44-69) when the
@@ -310,7 +312,7 @@ def main():
     pair_count, coulomb_pairs, nk = counts.pair_count, counts.coulomb_pair_count, int(counts.nkvectors)
     fp64_peak = ctypes.c_double()
     _ffi.check(ctx, lib.lumol_cuda_measure_fp64_peak(ctx, ctypes.byref(fp64_peak)))
-    profile_steps = max(3, min(args.steps, 20))
+    profile_steps = max(3, min(steps, 20))
     propagator.setup(system)
     _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, 2))
     _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
@@ -320,24 +322,23 @@ def main():
     _ffi.check(ctx, lib.lumol_cuda_set_profiling(ctx, 0))
     profile = device.stats()
     barrier()
+    device.close()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fd:
-            peaks = json.load(fd)
-    except OSError:
-        pass
+    peaks = load_json("MEASURED_PEAKS.json")
+    traffic = load_json(os.path.join("profiles", "traffic.json"))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    fp64_source = ("measured live: dependent-free DFMA chains on every SM (lumol_cuda_measure_fp64_peak); "
+                   "MEASURED_PEAKS.json has no FP64 entry")
 
     def per_launch(clock_ms, clock_launches):
         return clock_ms / clock_launches if clock_launches else None
 
+    staged = counts.neighbor_path == 1 and workload == "lj"
+    pair_kernel = "lj_force_kernel" if staged else ("list_force_kernel" if counts.neighbor_path == 1 else "allpairs_kernel")
     pair_ms = per_launch(profile.pair_ms, profile.pair_launches)
     pair_flops = (pair_count * FLOP_PER_LJ_PAIR_FORCE + coulomb_pairs * FLOP_PER_COULOMB_PAIR) / world
     kspace_ms = per_launch(profile.kspace_ms, profile.kspace_launches)
@@ -345,12 +346,12 @@ def main():
     if pair_ms:
         achieved = pair_flops / (pair_ms * 1e-3) / 1e12
         roofline_pair = {
-            "kernel": "list_force_kernel" if counts.neighbor_path == 1 else "allpairs_kernel", "bound": "fp64",
-            "achieved": achieved, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value,
-            "peak_source": "measured live: dependent-free DFMA chains on every SM (lumol_cuda_measure_fp64_peak); "
-                           "MEASURED_PEAKS.json has no FP64 entry",
+            "kernel": pair_kernel, "bound": "fp64", "achieved": achieved, "peak": fp64_peak.value, "unit": "TFLOP/s",
+            "frac": achieved / fp64_peak.value, "peak_source": fp64_source,
             "algorithmic_flop_per_launch": pair_flops, "pairs_in_cutoff": pair_count, "coulomb_pairs_in_cutoff": coulomb_pairs,
-            "avg_launch_ms": pair_ms, "launches_timed": int(profile.pair_launches), "traffic": None,
+            "avg_launch_ms": pair_ms, "launches_timed": int(profile.pair_launches),
+            "traffic": (traffic.get(f"{pair_kernel}:{workload}:{n}") or {}).get("bytes"),
+            "traffic_source": (traffic.get(f"{pair_kernel}:{workload}:{n}") or {}).get("source"),
         }
     roofline_extra = {}
     if kspace_ms and nk:
@@ -359,33 +360,38 @@ def main():
         total_ms = profile.kspace_ms / (profile.kspace_launches / 2.0)
         achieved = flops / (total_ms * 1e-3) / 1e12
         roofline_extra["ewald_kspace"] = {
-            "bound": "fp64", "achieved": achieved, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value,
-            "nkvectors": nk, "rho_plus_force_ms": total_ms,
+            "kernel": "ewald_rho_tiled_kernel + ewald_force_tiled_kernel", "bound": "fp64", "achieved": achieved,
+            "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value, "peak_source": fp64_source,
+            "nkvectors": nk, "rho_plus_force_ms": total_ms, "algorithmic_flop_per_evaluation": flops,
+            "traffic": (traffic.get(f"ewald_kspace:{workload}:{n}") or {}).get("bytes"),
+            "traffic_source": (traffic.get(f"ewald_kspace:{workload}:{n}") or {}).get("source"),
         }
+    if pair_ms and roofline_pair is not None and "ewald_kspace" in roofline_extra:
+        roofline_extra["pair_kernel"] = roofline_pair
     if profile.integrate_launches:
-        steps_profiled = profile_steps
-        total_ms = profile.integrate_ms / steps_profiled
+        total_ms = profile.integrate_ms / profile_steps
         achieved = BYTES_PER_ATOM_VV * n / world / (total_ms * 1e-3) / 1e9
         roofline_extra["velocity_verlet"] = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "peak_source": hbm_source, "ms_per_step": total_ms, "bytes_per_atom_step": BYTES_PER_ATOM_VV,
         }
     if profile.neighbor_launches:
-        # per step: refresh of the sorted positions (116 B/atom) plus the amortised rebuilds (flag-guarded kernels)
+        # per step: refresh of the sorted positions (cell-relative double4 + box-frame planes) plus the amortised
+        # rebuilds (one cooperative kernel, launched every step, that returns at once when no rebuild is due)
         total_ms = profile.neighbor_ms / profile_steps
-        achieved = 116.0 * n / (total_ms * 1e-3) / 1e9
+        achieved = 140.0 * n / (total_ms * 1e-3) / 1e9
         roofline_extra["neighbor_list"] = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "peak_source": hbm_source, "ms_per_step": total_ms, "bytes_per_atom_step": 116.0,
+            "peak_source": hbm_source, "ms_per_step": total_ms, "bytes_per_atom_step": 140.0,
             "rebuilds_in_profiled_steps": int(profile.neighbor_rebuilds - rebuilds_before_profile),
             "skin_A": profile.neighbor_skin,
         }
     dominant = roofline_pair
     if "ewald_kspace" in roofline_extra and kspace_ms and pair_ms and profile.kspace_ms > profile.pair_ms:
-        dominant = dict(roofline_extra["ewald_kspace"], kernel="ewald_rho_kernel + ewald_force_kernel", traffic=None)
+        dominant = roofline_extra["ewald_kspace"]
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and with_cpu:
         rate, rows, seconds, threads = cpu_sample_rows(system, args.cpu_seconds)
         cpu_baseline = {
             "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -393,23 +399,58 @@ def main():
                       "loop of sys/compute.rs:37-55 restated in oracle/lumol_oracle.c (OpenMP)",
         }
 
-    bytes_resident = n * (24 * 3 + 8 * 2 + 4 + 4 * 3 + 32 + 16 + 4 * 4)
+    bytes_resident = n * (24 * 3 + 8 * 2 + 4 + 4 * 3 + 32 + 24 + 16 + 4 * 4)
     description.update({
         "parallelism": f"{world} x B200, atoms in contiguous blocks per rank, replicated positions" if world > 1 else "1 x B200",
         "neighbor_path": "cell list" if counts.neighbor_path == 1 else "all-pairs",
         "cells": [int(c) for c in counts.ncells],
         "neighbor_list": {"skin_A": counts.neighbor_skin, "rebuilds_in_timed_steps": rebuilds_timed},
-        "l2": f"working set {bytes_resident / 1e6:.0f} MB per rank is larger than the 126 MB L2; no explicit flush",
+        "l2": f"working set ({bytes_resident / 1e6:.0f} MB of particle state plus the neighbour list, "
+              f"{(pair_count * 2 * 1.33 * 2) / 1e6:.0f} MB) against the 126 MB L2; no explicit flush",
     })
-    result = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    return {
+        "metric": METRIC if workload == "lj" else METRIC.replace("LJ argon NVE", "SPC/E water Ewald NVE"),
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": description,
-        "ns_per_day": args.steps / (elapsed_ms * 1e-3) * TIMESTEP_FS * 86400.0 * 1e-6,
+        "ns_per_day": steps / (elapsed_ms * 1e-3) * TIMESTEP_FS * 86400.0 * 1e-6,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": dominant, "roofline_extra": roofline_extra,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(result))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lumol_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = (rank, world, local_rank)
+
+    result = measure(args, env, args.workload, args.lattice, args.steps, args.warmup, not args.no_e2e,
+                     not args.no_cpu_baseline)
+    companion = None
+    if args.workload == "lj" and not args.no_spce:
+        # the other half of the headline metric: SPC/E water with Ewald (alpha, kmax from Ewald::with_accuracy)
+        companion = measure(args, env, "spce", args.spce_lattice, args.spce_steps, max(3, min(args.warmup, 5)), not args.no_e2e,
+                            False)
+    if rank == 0:
+        if companion is not None:
+            keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "ns_per_day", "config", "e2e", "gpu_launches",
+                    "roofline", "roofline_extra")
+            result["spce"] = {key: companion[key] for key in keep}
+        print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 

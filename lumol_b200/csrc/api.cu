@@ -632,9 +632,11 @@ int evaluate_forces_device(Context* c, const ComputeRequest& req) {
         LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_E_BONDS, 0, 9 * sizeof(double), c->stream));
     }
 
-    LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_E_KSPACE, 0, 7 * sizeof(double), c->stream));
-    LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_W_KSPACE_CORRECTION, 0, 9 * sizeof(double), c->stream));
-    LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_CHARGE2, 0, sizeof(double), c->stream));
+    if (req.energy || req.virial || req.molecular_virial) {  // the host reads no sums after a forces-only evaluation
+        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_E_KSPACE, 0, 7 * sizeof(double), c->stream));
+        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_W_KSPACE_CORRECTION, 0, 9 * sizeof(double), c->stream));
+        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_CHARGE2, 0, sizeof(double), c->stream));
+    }
     if (do_coulomb) {
         if (req.energy) {
             status = launch_coulomb_self(c);
@@ -917,7 +919,7 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
     if (c->integrator < 0) return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_setup was not called");
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
     for (int64_t s = 0; s < nsteps; s++) {
-        int status = md_step(c);
+        int status = md_step(c, s == 0, s + 1 == nsteps);
         if (status) return status;
     }
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));

@@ -180,10 +180,12 @@ __global__ void zero_results_kernel(double* results, int first, int count) {
 
 int launch_bonded(Context* ctx, const ComputeRequest& req) {
     const bool sums = req.energy || req.virial;
-    // energies/virial default to zero when a list is empty
-    zero_results_kernel<<<1, 32, 0, ctx->stream>>>(ctx->results.ptr, RES_E_BONDS, 9);
-    ctx->launches++;
-    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    // energies/virial default to zero when a list is empty (nobody reads them after a forces-only evaluation)
+    if (sums) {
+        zero_results_kernel<<<1, 32, 0, ctx->stream>>>(ctx->results.ptr, RES_E_BONDS, 9);
+        ctx->launches++;
+        LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    }
     if (!req.forces && !sums) return 0;
 
     BondedArgs a;

@@ -278,7 +278,7 @@ int ewald_prepare(Context* ctx);                                                
 int launch_ewald_kspace(Context* ctx, const ComputeRequest& req);                                // ewald.cu
 int launch_kinetic(Context* ctx, bool tensor);                                                   // integrate.cu
 int md_setup(Context* ctx);                                                                      // integrate.cu
-int md_step(Context* ctx);                                                                       // integrate.cu
+int md_step(Context* ctx, bool first, bool last);                                                                     // integrate.cu
 int launch_scale_velocities(Context* ctx, double factor, bool from_device);                      // integrate.cu
 int launch_remove_translation(Context* ctx);                                                     // integrate.cu
 int evaluate_forces_device(Context* ctx, const ComputeRequest& req);                             // api.cu

@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_default2.json 2> gpurun_out/bench_default2.err; tail -3 gpurun_out/bench_default2.err
