@@ -210,6 +210,34 @@ def run_reference(args):
 
 # ---- GPU arm ---------------------------------------------------------------------------------------------------
 
+def bench_system_latencies(repeats=30):
+    """Per-call latency (microseconds, host API, host buffers in and out) of forces / potential energy / atomic
+    virial on the reference's four criterion bench systems (benches/{argon,nacl,water,propane}.rs; 128-300 atoms,
+    SURVEY section 6), for continuity with the reference's own harness."""
+    tests = os.path.join(ROOT, "tests")
+    if tests not in sys.path:
+        sys.path.insert(0, tests)
+    import systems
+    from lumol_b200.compute import AtomicVirial, Forces, PotentialEnergy
+
+    out = {}
+    for name, builder in (("argon", systems.argon), ("nacl_ewald", lambda: systems.nacl("ewald")),
+                          ("nacl_wolf", lambda: systems.nacl("wolf")), ("water_ewald", lambda: systems.water("ewald")),
+                          ("propane", systems.propane)):
+        system = builder()
+        row = {"atoms": system.size()}
+        for label, estimator in (("forces", Forces()), ("energy", PotentialEnergy()), ("virial", AtomicVirial())):
+            for _ in range(3):
+                estimator.compute(system)
+            start = time.perf_counter()
+            for _ in range(repeats):
+                estimator.compute(system)
+            row[label] = (time.perf_counter() - start) / repeats * 1e6
+        system._device.close()
+        out[name] = row
+    return out
+
+
 def load_json(name):
     try:
         with open(os.path.join(ROOT, name)) as fd:
@@ -446,6 +474,8 @@ def main():
         companion = measure(args, env, "spce", args.spce_lattice, args.spce_steps, max(3, min(args.warmup, 5)), not args.no_e2e,
                             False)
     if rank == 0:
+        if world == 1 and args.workload == "lj" and not args.no_spce:
+            result["criterion_us_per_call"] = bench_system_latencies()
         if companion is not None:
             keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "ns_per_day", "config", "e2e", "gpu_launches",
                     "roofline", "roofline_extra")

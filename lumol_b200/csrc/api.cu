@@ -710,6 +710,9 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
         int rebuilds = 0, overflow = 0;
         status = neighbor_list_status(c, &rebuilds, &overflow);
         if (status) return status;
+        if (overflow == 2) {
+            return c->fail(LUMOL_CUDA_ERROR_NOT_FINITE, "a particle position is not finite: the neighbour list cannot be built");
+        }
         if (overflow) {
             return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list capacity exceeded (strongly inhomogeneous density)");
         }
@@ -927,6 +930,9 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
         int rebuilds = 0, overflow = 0;
         int status = neighbor_list_status(c, &rebuilds, &overflow);
         if (status) return status;
+        if (overflow == 2) {
+            return c->fail(LUMOL_CUDA_ERROR_NOT_FINITE, "a particle position is not finite: the neighbour list cannot be built");
+        }
         if (overflow) {
             return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list capacity exceeded (strongly inhomogeneous density)");
         }

@@ -73,6 +73,8 @@ int choose_neighbor_path(Context* ctx, double cutoff) {
 
 // flags[0]: rebuild requested, flags[1]: a list column overflowed, flags[2]: number of rebuilds so far
 constexpr int FLAG_REBUILD = 0, FLAG_OVERFLOW = 1, FLAG_COUNT = 2;
+// flags[3]: blocks that could not be staged (FLAG_UNSTAGED); flags[4]: a position was not finite at the last rebuild
+constexpr int FLAG_NONFINITE = 4;
 
 // ------------------------------------------------------------------------------------------------
 // counting sort (every kernel returns immediately when no rebuild is requested)
@@ -106,15 +108,20 @@ constexpr int REBUILD_THREADS = 256;
 constexpr int REBUILD_WARPS = REBUILD_THREADS / 32;
 
 __device__ __forceinline__ void cell_zero_phase(int count, int* __restrict__ cell_count, int* __restrict__ flags) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_phase
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_phase
+        flags[FLAG_NONFINITE] = 0;
+    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) cell_count[k] = 0;
 }
 
 __device__ __forceinline__ void cell_assign_phase(int vb, int n, const GridView& g, const double* __restrict__ pos,
                                                   int* __restrict__ cell_of, int* __restrict__ slot_of,
-                                                  int* __restrict__ cell_count) {
+                                                  int* __restrict__ cell_count, int* __restrict__ flags) {
     const int i = vb * REBUILD_THREADS + threadIdx.x;
     if (i >= n) return;
+    // an exploded simulation must not turn the sort into a quadratic loop over one cell: the rebuild stops here
+    if (!(isfinite(pos[3 * i]) && isfinite(pos[3 * i + 1]) && isfinite(pos[3 * i + 2]))) flags[FLAG_NONFINITE] = 1;
     const int cx = cell_coordinate(wrap_coordinate(pos[3 * i], g.length[0]), g.length[0], g.nc[0]);
     const int cy = cell_coordinate(wrap_coordinate(pos[3 * i + 1], g.length[1]), g.length[1], g.nc[1]);
     const int cz = cell_coordinate(wrap_coordinate(pos[3 * i + 2], g.length[2]), g.length[2], g.nc[2]);
@@ -702,9 +709,10 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild_kernel(RebuildArgs r)
     cell_zero_phase(r.ncells + 1, r.cell_count, r.flags);
     grid.sync();
     for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
-        cell_assign_phase(vb, r.n, r.g, r.position, r.cell_of, r.slot_of, r.cell_count);
+        cell_assign_phase(vb, r.n, r.g, r.position, r.cell_of, r.slot_of, r.cell_count, r.flags);
     }
     grid.sync();
+    if (r.flags[FLAG_NONFINITE] != 0) return;  // every block reads the same value: the force kernels return as well
     for (int vb = blockIdx.x; vb < r.scan_blocks; vb += gridDim.x) {
         scan_blocks_phase(vb, r.ncells, r.cell_count, r.cell_start, r.scan_scratch, scan_shared);
     }
@@ -769,6 +777,7 @@ struct ForceArgs {
     int write_forces;            // energy-only queries must not clobber the forces the integrator holds
     double* __restrict__ force;  // original order, n x 3
     double* __restrict__ partials;
+    const int* __restrict__ flags;  // FLAG_NONFINITE: the list is not valid, nothing is evaluated
 };
 
 // 1 / x to full FP64 precision without the slow-path branch of the compiler's division: the hardware seed
@@ -950,6 +959,7 @@ __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
     PairParams* sp = reinterpret_cast<PairParams*>(smem_raw);
     __shared__ double offset64[27][3];  // (a, b, c) * edge for the 27 neighbour-cell offsets
     __shared__ double scratch[32 * NL_NV];
+    if (a.flags[FLAG_NONFINITE] != 0) return;
 
     {
         const int words = (int)(sizeof(PairParams) / sizeof(double)) * a.nkinds * a.nkinds;
@@ -1083,6 +1093,7 @@ __global__ void __launch_bounds__(LJ_THREADS, 2) lj_force_kernel(ForceArgs a) {
     __shared__ int4 images[STAGE_MAX_ENTRIES];  // runs seen through a periodic boundary: first slot, end, image code
     __shared__ int nimages;
 
+    if (a.flags[FLAG_NONFINITE] != 0) return;
     double acc[NL_NV];
 #pragma unroll
     for (int k = 0; k < NL_NV; k++) acc[k] = 0.0;
@@ -1450,6 +1461,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.cutoff2 = active_cutoff * active_cutoff;
     a.force = ctx->force.ptr;
     a.write_forces = req.forces;
+    a.flags = flags;
 
     // the staged kernel needs lists built for it (lj_system); a system with charges whose coulomb part is
     // not requested still takes the general kernel
@@ -1510,10 +1522,11 @@ int neighbor_list_status(Context* ctx, int* rebuilds, int* overflow) {
     *rebuilds = 0;
     *overflow = 0;
     if (ctx->nl_flags.ptr == nullptr || !ctx->flags_initialised) return 0;
-    int host[3] = {0, 0, 0};
+    int host[5] = {0, 0, 0, 0, 0};
     LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(host, ctx->nl_flags.ptr, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    *overflow = host[FLAG_OVERFLOW];
+    *overflow = host[FLAG_NONFINITE] != 0 ? 2 : host[FLAG_OVERFLOW];
+    if (host[FLAG_NONFINITE] != 0) ctx->list_valid = false;  // the next evaluation rebuilds from scratch
     *rebuilds = host[FLAG_COUNT];
     return 0;
 }

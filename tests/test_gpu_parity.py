@@ -473,6 +473,20 @@ def test_staged_lj_kernel_full_size():
     assert np.abs(staged.virial - plain.virial).max() < 1e-11 * np.abs(plain.virial).max()
 
 
+def test_non_finite_positions_on_the_cell_path():
+    """An exploded simulation must give an error, not a hang: the rebuild stops when a position is not finite, the
+    force kernels return, and the context works again once the positions are sane."""
+    system = systems.lj_box(16, seed=3)
+    good = system.positions.copy()
+    expected = device_for(system).compute(forces=True).forces
+    system.positions[17, 1] = np.nan
+    with pytest.raises(lumol.LumolCudaError, match="not finite"):
+        device_for(system).compute(forces=True)
+    system.positions[:] = good
+    again = device_for(system).compute(forces=True).forces
+    assert np.abs(again - expected).max() <= 1e-12 * np.abs(expected).max()
+
+
 def test_water_box_cell_list_vs_oracle():
     """5184-atom synthetic SPC/E box: LJ + Ewald real space with intra-molecular exclusions on the cell path."""
     system = systems.spce_box(12)
