@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(KFORCE_THREADS) ewald_force_kernel(KForceArgs 
 
 constexpr int TK_THREADS = 256;
 constexpr int TK_ATOMS = 32;  // atoms per shared-memory tile of the rho kernel
-constexpr int TK_TR = 2;      // rows per thread
+constexpr int TK_TR = 4;      // rows per thread: 4 x 4 complex tile = 64 DFMA per 8 LDS.128 (the shared-memory pipe moves
+                              // four wavefronts per 128-bit load whatever the broadcast, so 2 x 4 tiles were bound by it)
 constexpr int TK_TL = 4;      // |l| values per thread
 
 __device__ __forceinline__ int row_index(const KRow& row, int l) {
@@ -485,13 +486,13 @@ struct TiledRhoArgs {
 // (TK_ATOMS x rows per block): in the main loop every thread of a warp reads the same atom, so rows and |l|
 // values must be the fastest index for the reads to be conflict-free.
 // grid: (row tiles, atom chunks)
-__global__ void __launch_bounds__(TK_THREADS) ewald_rho_tiled_kernel(TiledRhoArgs a) {
+__global__ void __launch_bounds__(TK_THREADS, 1) ewald_rho_tiled_kernel(TiledRhoArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lpad = a.lq * TK_TL;
     double2* table = reinterpret_cast<double2*>(smem_raw);
     double2* amat = table + (size_t)TK_ATOMS * 3 * lpad;
     const int rows_per_block = a.row_groups * TK_TR;
-    __shared__ KRow s_rows[TK_THREADS];  // rows_per_block <= TK_THREADS (checked on the host)
+    __shared__ KRow s_rows[TK_THREADS * 2];  // rows_per_block <= 2 * TK_THREADS (kmax >= 8: at most 85 row groups)
 
     const int t = threadIdx.x;
     const int row0 = blockIdx.x * rows_per_block;
@@ -543,8 +544,9 @@ __global__ void __launch_bounds__(TK_THREADS) ewald_rho_tiled_kernel(TiledRhoArg
         }
         __syncthreads();
         // A[atom][row] = q e_x(h) e_y(k); h >= 0 in the half space, e_y(-k) = conj e_y(k)
+        int atom = t / rows_per_block, r = t - atom * rows_per_block;
+        const int atom_step = TK_THREADS / rows_per_block, r_step = TK_THREADS - atom_step * rows_per_block;
         for (int w = t; w < rows_per_block * TK_ATOMS; w += TK_THREADS) {
-            const int atom = w / rows_per_block, r = w - atom * rows_per_block;
             const KRow row = s_rows[r];
             const double2* tables = table + (size_t)atom * 3 * lpad;
             const double2 ex = tables[row.h];
@@ -553,6 +555,12 @@ __global__ void __launch_bounds__(TK_THREADS) ewald_rho_tiled_kernel(TiledRhoArg
             const double q = atom < count ? a.charge[base + atom] : 0.0;
             const double2 e = cmul(ex, ey);
             amat[w] = make_double2(q * e.x, q * e.y);
+            atom += atom_step;
+            r += r_step;
+            if (r >= rows_per_block) {
+                r -= rows_per_block;
+                atom++;
+            }
         }
         __syncthreads();
         if (worker) {
@@ -597,9 +605,9 @@ __global__ void __launch_bounds__(TK_THREADS) ewald_rho_tiled_kernel(TiledRhoArg
     }
 }
 
-// G matrix of the force kernel: per (row, |l|) eight doubles
-//   S = g+ + g-, D = g+ - g-, g = 2 e_k conj(rho_k) (0 outside the list; for l = 0 only g+):
-//   {S.re, D.im, S.im, D.re, l D.re, l S.im, l D.im, l S.re}
+// G matrix of the force kernel: per (row, |l|) four doubles
+//   S = g+ + g-, D = g+ - g-, g = 2 e_k conj(rho_k) (0 outside the list; for l = 0 only g+): {S.re, S.im, D.re, D.im}
+// (the l-weighted sum W1 uses the same numbers with l e_z(l) instead of e_z(l))
 __global__ void __launch_bounds__(256)
     ewald_gmat_kernel(int nrows, int kmax, const KRow* __restrict__ rows, const double2* __restrict__ rho,
                       const double* __restrict__ kenergy, double* __restrict__ gmat) {
@@ -622,22 +630,17 @@ __global__ void __launch_bounds__(256)
         gm = make_double2(f * v.x, -f * v.y);
     }
     const double sr = gp.x + gm.x, si = gp.y + gm.y, dr = gp.x - gm.x, di = gp.y - gm.y;
-    const double l = (double)m;
-    double* g = gmat + (size_t)w * 8;
+    double* g = gmat + (size_t)w * 4;
     g[0] = sr;
-    g[1] = di;
-    g[2] = si;
-    g[3] = dr;
-    g[4] = l * dr;
-    g[5] = l * si;
-    g[6] = l * di;
-    g[7] = l * sr;
+    g[1] = si;
+    g[2] = dr;
+    g[3] = di;
 }
 
 constexpr int TF_TA = 4;          // atoms per thread
-constexpr int TF_TR = 2;          // rows per thread
+constexpr int TF_TR = 4;          // rows per thread: 12 LDS.128 per 136 FP64 instructions and |l| step
 constexpr int TF_ROW_GROUPS = 8;  // thread rows
-constexpr int TF_ROWS = TF_ROW_GROUPS * TF_TR;  // rows per staged tile: 16
+constexpr int TF_ROWS = TF_ROW_GROUPS * TF_TR;  // rows per staged tile: 32
 
 struct TiledForceArgs {
     const double* __restrict__ pos;
@@ -653,7 +656,7 @@ struct TiledForceArgs {
     double* __restrict__ partial;  // nsplit > 1: [split][owned atom][3] (sum_h, sum_k, sum_l), reduced afterwards
 };
 
-// Shared: tables [axis][m][atom] (3 x (kmax + 1) x TF_ATOMS complex) + G tile (TF_ROWS x (kmax + 1) x 8 doubles).
+// Shared: tables [axis][m][atom] (3 x (kmax + 1) x TF_ATOMS complex) + G tile (TF_ROWS x (kmax + 1) x 4 doubles).
 // TF_ATOMS atoms per block (64, or 32 when kmax is large), TF_ATOMS / TF_TA x TF_ROW_GROUPS threads.
 template <int TF_ATOMS>
 __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_tiled_kernel(TiledForceArgs a) {
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
     const int lp = a.kmax + 1;
     double2* table = reinterpret_cast<double2*>(smem_raw);
     double* gtile = reinterpret_cast<double*>(table + (size_t)3 * lp * TF_ATOMS);
-    const int gstride = lp * 8 + 4;  // doubles per row of the staged G tile: neighbouring rows in different banks
+    const int gstride = lp * 4 + 4;  // doubles per row of the staged G tile: neighbouring rows in different banks
     __shared__ KRow s_rows[TF_ROWS];
 
     const int t = threadIdx.x;
@@ -706,9 +709,9 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
         __syncthreads();
         const int nrows = min(TF_ROWS, row_hi - tile);
         {
-            const double* src = a.gmat + (size_t)tile * lp * 8;
-            for (int w = t; w < TF_ROWS * lp * 8; w += TF_THREADS) {
-                const int r = w / (lp * 8), c = w - r * (lp * 8);
+            const double* src = a.gmat + (size_t)tile * lp * 4;
+            for (int w = t; w < TF_ROWS * lp * 4; w += TF_THREADS) {
+                const int r = w / (lp * 4), c = w - r * (lp * 4);
                 gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
             }
             if (t < TF_ROWS) {
@@ -727,19 +730,23 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
             for (int x = 0; x < TF_TA; x++) w0[r][x][0] = w0[r][x][1] = w1[r][x][0] = w1[r][x][1] = 0.0;
         const double* g0 = gtile + (size_t)rg * gstride;
         for (int m = 0; m < lp; m++) {
-            double2 z[TF_TA];
+            double2 z[TF_TA], zl[TF_TA];
+            const double weight = (double)m;
 #pragma unroll
-            for (int x = 0; x < TF_TA; x++) z[x] = ez[(size_t)m * TF_ATOMS + x * AG];
+            for (int x = 0; x < TF_TA; x++) {
+                z[x] = ez[(size_t)m * TF_ATOMS + x * AG];
+                zl[x] = make_double2(weight * z[x].x, weight * z[x].y);
+            }
 #pragma unroll
             for (int r = 0; r < TF_TR; r++) {
-                const double4 ga = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 8);
-                const double4 gb = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 8 + 4);
+                // S.re, S.im, D.re, D.im
+                const double4 g = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 4);
 #pragma unroll
                 for (int x = 0; x < TF_TA; x++) {
-                    w0[r][x][0] = fma(z[x].x, ga.x, fma(-z[x].y, ga.y, w0[r][x][0]));
-                    w0[r][x][1] = fma(z[x].x, ga.z, fma(z[x].y, ga.w, w0[r][x][1]));
-                    w1[r][x][0] = fma(z[x].x, gb.x, fma(-z[x].y, gb.y, w1[r][x][0]));
-                    w1[r][x][1] = fma(z[x].x, gb.z, fma(z[x].y, gb.w, w1[r][x][1]));
+                    w0[r][x][0] = fma(z[x].x, g.x, fma(-z[x].y, g.w, w0[r][x][0]));
+                    w0[r][x][1] = fma(z[x].x, g.y, fma(z[x].y, g.z, w0[r][x][1]));
+                    w1[r][x][0] = fma(zl[x].x, g.z, fma(-zl[x].y, g.y, w1[r][x][0]));
+                    w1[r][x][1] = fma(zl[x].x, g.w, fma(zl[x].y, g.x, w1[r][x][1]));
                 }
             }
         }
@@ -841,7 +848,7 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
     const size_t rho_tables = (size_t)3 * (lq * TK_TL) * TK_ATOMS * sizeof(double2);
     const int row_groups = TK_THREADS / lq;
     const size_t rho_smem = rho_tables + (size_t)row_groups * TK_TR * TK_ATOMS * sizeof(double2);
-    const size_t force_tables64 = (size_t)3 * (kmax + 1) * 64 * sizeof(double2), gtile = (size_t)TF_ROWS * ((kmax + 1) * 8 + 4) * sizeof(double);
+    const size_t force_tables64 = (size_t)3 * (kmax + 1) * 64 * sizeof(double2), gtile = (size_t)TF_ROWS * ((kmax + 1) * 4 + 4) * sizeof(double);
     const bool tiled_possible = ctx->krows_regular && kmax >= 8 && kmax <= 255 && rho_smem <= 200 * 1024 &&
                                 force_tables64 / 2 + gtile <= 200 * 1024;
     bool tiled = tiled_possible && (ctx->kspace_algorithm == 1 || (ctx->kspace_algorithm < 0 && (int64_t)owned * nk >= (int64_t)1 << 24));
@@ -853,7 +860,8 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
         const int nrows = (int)ctx->nkrows;
         const int rows_per_block = row_groups * TK_TR;
         const int row_tiles = (nrows + rows_per_block - 1) / rows_per_block;
-        nchunks = (2 * ctx->sm_count + row_tiles - 1) / row_tiles;
+        // one block per SM: a whole number of waves (four) so that no wave runs with a handful of blocks
+        nchunks = 4 * ctx->sm_count / row_tiles;
         const int max_chunks = (owned + TK_ATOMS - 1) / TK_ATOMS;
         if (nchunks > max_chunks) nchunks = max_chunks;
         if (nchunks < 1) nchunks = 1;
@@ -955,7 +963,7 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
     if (tiled_forces && req.forces && owned > 0) {
         const int nrows = (int)ctx->nkrows;
         const int lp = kmax + 1;
-        LUMOL_CUDA_CHECK(ctx, ctx->kgmat.reserve((size_t)nrows * lp * 8 + 8));
+        LUMOL_CUDA_CHECK(ctx, ctx->kgmat.reserve((size_t)nrows * lp * 4 + 8));
         ewald_gmat_kernel<<<(nrows * lp + 255) / 256, 256, 0, ctx->stream>>>(nrows, kmax, reinterpret_cast<const KRow*>(ctx->krows.ptr),
                                                                            ctx->rho.ptr, ctx->kenergy.ptr, ctx->kgmat.ptr);
         ctx->launches++;

@@ -12,7 +12,13 @@ def main():
     col = {name: header.index(name) for name in ("Source", "# Samples", "stall_long_sb", "stall_short_sb", "stall_barrier",
                                                   "stall_wait", "stall_math", "stall_mio", "stall_not_selected", "stall_selected",
                                                   "Instructions Executed")}
-    data = [r for r in rows[2:] if len(r) == len(header)]
+    # a report with several kernels repeats the "Kernel Name" / header lines: keep the first kernel (or argv[3]-th)
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    starts = [k for k, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    begin = starts[which] + 2
+    end = starts[which + 1] if which + 1 < len(starts) else len(rows)
+    print("kernel:", rows[starts[which]][1])
+    data = [r for r in rows[begin:end] if len(r) == len(header)]
     total = sum(int(r[col["# Samples"]]) for r in data)
     bars = [k for k, r in enumerate(data) if "BAR" in r[col["Source"]]]
     print("total samples", total, "barriers at", bars)
