@@ -34,6 +34,7 @@
 
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <cstring>
 
 namespace lumol {
@@ -477,11 +478,12 @@ __device__ __forceinline__ void block_table_phase(int vb, const TableArgs& a) {
 
 constexpr unsigned LIST_INDEX_MASK = (1u << 26) - 1u;
 constexpr int BUILD_WARPS = REBUILD_WARPS;
+constexpr int BUILD_CHUNKS = 8;  // work items per cell of the list build
 
 struct BuildArgs {
     GridView g;
     int ncells;
-    int cells_per_warp;
+    int cells_per_warp;  // work items (cell, chunk) per warp
     int o_lo, o_hi;  // original-index range of the atoms this rank owns (lists are built for those)
     int capacity;    // 32-bit entries per atom (a staged column holds as many 16-bit ones in half the space)
     float radius2;   // (cut-off + skin)^2, enlarged by 1e-4 relative
@@ -500,16 +502,21 @@ struct BuildArgs {
 __device__ __forceinline__ void list_build_phase(int vb, const BuildArgs& a, const float (*offset32)[3]) {
     const int lane = threadIdx.x & 31;
     const int global_warp = vb * BUILD_WARPS + (threadIdx.x >> 5);
-    const int cell_lo = global_warp * a.cells_per_warp;
-    const int cell_hi = min(a.ncells, cell_lo + a.cells_per_warp);
+    // work items: (k, cell) for k < BUILD_CHUNKS; item (k, c) takes the 32-atom chunks k, k + BUILD_CHUNKS, ... of
+    // cell c, so that dense cells (100 atoms at water density, few cells) still spread over every SM
+    const int item_lo = global_warp * a.cells_per_warp;
+    const int item_hi = min(a.ncells * BUILD_CHUNKS, item_lo + a.cells_per_warp);
 
-    for (int c = cell_lo; c < cell_hi; c++) {
+    for (int item = item_lo; item < item_hi; item++) {
+        // chunk-major order: the consecutive items of a warp are different cells (at liquid-argon density only chunk 0
+        // of a cell holds atoms)
+        const int first_chunk = item / a.ncells, c = item - first_chunk * a.ncells;
         const int hs = a.cell_start[c], he = a.cell_start[c + 1];
-        if (hs == he) continue;
+        if (hs + 32 * first_chunk >= he) continue;
         const int cx = c % a.g.nc[0];
         const int cy = (c / a.g.nc[0]) % a.g.nc[1];
         const int cz = c / (a.g.nc[0] * a.g.nc[1]);
-        for (int base = hs; base < he; base += 32) {
+        for (int base = hs + 32 * first_chunk; base < he; base += 32 * BUILD_CHUNKS) {
             const int s_i = base + lane;
             bool active = s_i < he;
             float xf = 1.0e18f, yf = 0.0f, zf = 0.0f;  // lanes without an owned atom sit far away
@@ -571,21 +578,28 @@ __device__ __forceinline__ void list_build_phase(int vb, const BuildArgs& a, con
                     // what is stored for neighbour s_j: tag + s_j
                     unsigned tag = (unsigned)code << 26;
                     if (staged) tag = (unsigned)((entries[entry_first + row * entry_width + dx].y & 0xffff) - s0);
-#pragma unroll 4
-                    for (int s_j = s0; s_j < s1; s_j++) {
-                        const float4 f = __ldg(a.sorted_f32 + s_j);  // same address in every lane: one broadcast
-                        const float ddx = xr - f.x, ddy = yr - f.y, ddz = zr - f.z;
-                        const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                        if (r2 < a.radius2 && s_j != s_i) {
-                            if (count < a.capacity) {
-                                const unsigned value = tag + (unsigned)s_j;
-                                if (staged) {
-                                    column16[(count >> 3) * 256 + (count & 7)] = (unsigned short)value;
-                                } else {
-                                    column[(count >> 2) * 128 + (count & 3)] = value;
+                    // eight candidates per round, loaded before the first one is tested (uniform addresses: one
+                    // broadcast each); the compiler does not hoist these loads over the divergent stores by itself
+                    for (int first = s0; first < s1; first += 8) {
+                        float4 f[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) f[u] = __ldg(a.sorted_f32 + min(first + u, s1 - 1));
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int s_j = first + u;
+                            const float ddx = xr - f[u].x, ddy = yr - f[u].y, ddz = zr - f[u].z;
+                            const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                            if (r2 < a.radius2 && s_j != s_i && s_j < s1) {
+                                if (count < a.capacity) {
+                                    const unsigned value = tag + (unsigned)s_j;
+                                    if (staged) {
+                                        column16[(count >> 3) * 256 + (count & 7)] = (unsigned short)value;
+                                    } else {
+                                        column[(count >> 2) * 128 + (count & 3)] = value;
+                                    }
                                 }
+                                count++;
                             }
-                            count++;
                         }
                     }
                 }
@@ -624,51 +638,76 @@ __device__ __forceinline__ void list_build_phase(int vb, const BuildArgs& a, con
 
 constexpr int REORDER_THREADS = 32;
 
+// one warp per slab of 32 columns; shared: the slab's entries grouped by bucket, [position][lane]
 __global__ void __launch_bounds__(REORDER_THREADS)
     list_reorder_kernel(int n, int capacity, const int4* __restrict__ blk_header, const int* __restrict__ ncount,
                         unsigned* __restrict__ nlist, int epoch, const int* __restrict__ flags) {
     if (flags[FLAG_REBUILD] != epoch) return;
-    extern __shared__ unsigned short sorted[];  // entry p of thread t at [p * REORDER_THREADS + t]
+    extern __shared__ unsigned short reorder_smem[];
+    unsigned short* sorted = reorder_smem;  // entry p of thread t at [p * 32 + t], grouped by bucket
     __shared__ unsigned short cursor[16][REORDER_THREADS], last[16][REORDER_THREADS];
     const int t = threadIdx.x;
     for (int slab = blockIdx.x; slab * REORDER_THREADS < n; slab += gridDim.x) {
-    const int s_i = slab * REORDER_THREADS + t;
-    if (s_i >= n) continue;
-    if (blk_header[s_i / TB].z < 0) continue;  // global format: no shared-memory gathers
-    const int count = ncount[s_i];
-    unsigned short* column16 =
-        reinterpret_cast<unsigned short*>(nlist + ((size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31)) * 4);
+        const int s_i = slab * REORDER_THREADS + t;
+        if (s_i >= n) continue;
+        if (blk_header[s_i / TB].z < 0) continue;  // global format: no shared-memory gathers
+        const int count = ncount[s_i];
+        uint4* words = reinterpret_cast<uint4*>(nlist) + (size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31);
+        const int nwords = (count + 7) >> 3;
 #pragma unroll
-    for (int b = 0; b < 16; b++) last[b][t] = 0;
-    for (int k = 0; k < count; k++) last[column16[(k >> 3) * 256 + (k & 7)] & 15][t]++;
-    int running = 0;
+        for (int b = 0; b < 16; b++) last[b][t] = 0;
+        // whole 16-byte words in, eight entries each (the tail of the last word is padding and is not counted)
+        for (int w = 0; w < nwords; w++) {
+            const uint4 word = words[w * 32];
+            const unsigned pairs[4] = {word.x, word.y, word.z, word.w};
 #pragma unroll
-    for (int b = 0; b < 16; b++) {
-        cursor[b][t] = (unsigned short)running;
-        running += last[b][t];
-        last[b][t] = (unsigned short)running;
-    }
-    // stable scatter into the buckets
-    for (int k = 0; k < count; k++) {
-        const unsigned short e = column16[(k >> 3) * 256 + (k & 7)];
-        const int position = cursor[e & 15][t]++;
-        sorted[position * REORDER_THREADS + t] = e;
-    }
-    // rewind, then emit round robin
-    running = 0;
+            for (int q = 0; q < 8; q++) {
+                const unsigned short e = (unsigned short)(q & 1 ? pairs[q >> 1] >> 16 : pairs[q >> 1] & 0xffffu);
+                if (8 * w + q < count) last[e & 15][t]++;
+            }
+        }
+        int running = 0;
 #pragma unroll
-    for (int b = 0; b < 16; b++) {
-        cursor[b][t] = (unsigned short)running;
-        running = last[b][t];
-    }
-    int bucket = s_i & 15;
-    for (int k = 0; k < count; k++) {
-        int b = bucket;
-        while (cursor[b][t] == last[b][t]) b = (b + 1) & 15;  // some bucket is non-empty: k < count
-        const int position = cursor[b][t]++;
-        column16[(k >> 3) * 256 + (k & 7)] = sorted[position * REORDER_THREADS + t];
-        bucket = (bucket + 1) & 15;
-    }
+        for (int b = 0; b < 16; b++) {
+            cursor[b][t] = (unsigned short)running;
+            running += last[b][t];
+            last[b][t] = (unsigned short)running;
+        }
+        // stable scatter into the buckets (second pass over the words: they are in L1 / L2 now)
+        for (int w = 0; w < nwords; w++) {
+            const uint4 word = words[w * 32];
+            const unsigned pairs[4] = {word.x, word.y, word.z, word.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const unsigned short e = (unsigned short)(q & 1 ? pairs[q >> 1] >> 16 : pairs[q >> 1] & 0xffffu);
+                if (8 * w + q < count) {
+                    const int position = cursor[e & 15][t]++;
+                    sorted[position * REORDER_THREADS + t] = e;
+                }
+            }
+        }
+        // rewind, then emit round robin, whole words out
+        running = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            cursor[b][t] = (unsigned short)running;
+            running = last[b][t];
+        }
+        int bucket = s_i & 15;
+        for (int w = 0; w < nwords; w++) {
+            unsigned pairs[4] = {0u, 0u, 0u, 0u};  // padding entries point at the dummy slot 0
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (8 * w + q < count) {
+                    int b = bucket;
+                    while (cursor[b][t] == last[b][t]) b = (b + 1) & 15;  // some bucket is non-empty
+                    const int position = cursor[b][t]++;
+                    pairs[q >> 1] |= (unsigned)sorted[position * REORDER_THREADS + t] << (16 * (q & 1));
+                    bucket = (bucket + 1) & 15;
+                }
+            }
+            words[w * 32] = make_uint4(pairs[0], pairs[1], pairs[2], pairs[3]);
+        }
     }
 }
 
@@ -731,7 +770,7 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild_kernel(RebuildArgs r)
     grid.sync();
     for (int vb = blockIdx.x; vb * REBUILD_WARPS < r.nblocks; vb += gridDim.x) block_table_phase(vb, r.table);
     grid.sync();
-    for (int vb = blockIdx.x; vb * BUILD_WARPS * r.build.cells_per_warp < r.ncells; vb += gridDim.x) {
+    for (int vb = blockIdx.x; vb * BUILD_WARPS * r.build.cells_per_warp < r.ncells * BUILD_CHUNKS; vb += gridDim.x) {
         list_build_phase(vb, r.build, offset32);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) r.flags[FLAG_COUNT] += 1;
@@ -1370,7 +1409,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         b.g = g;
         b.ncells = ncells;
         // one warp per `cells_per_warp` consecutive cells: about sixteen work items per resident warp
-        b.cells_per_warp = ncells / (ctx->sm_count * 8 * BUILD_WARPS * 16) + 1;
+        b.cells_per_warp = ncells * BUILD_CHUNKS / (ctx->sm_count * 8 * BUILD_WARPS * 16) + 1;
         b.o_lo = (int)o_lo;
         b.o_hi = (int)o_hi;
         b.capacity = capacity;
@@ -1416,7 +1455,8 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         ctx->launches++;
         ctx->clk_neighbor.launches++;
         const size_t reorder_smem = (size_t)capacity * REORDER_THREADS * sizeof(unsigned short);
-        if (allow_staging && reorder_smem <= 200 * 1024) {
+        static const bool reorder_disabled = std::getenv("LUMOL_CUDA_NO_REORDER") != nullptr;  // profiling switch
+        if (allow_staging && reorder_smem <= 200 * 1024 && !reorder_disabled) {
             if (reorder_smem > 40 * 1024) {
                 LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                            (int)reorder_smem));

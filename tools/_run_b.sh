@@ -1,1 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "non_finite" 2>&1 | grep -v "^$" | tail -30
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 600 python bench.py > gpurun_out/bench_default4.json 2> gpurun_out/bench_default4.err; tail -3 gpurun_out/bench_default4.err

@@ -1,2 +1,5 @@
-timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tiled_kspace or structure_factor or water" 2>&1 | tail -3
-timeout 200 ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:ewald -c 4 --csv --log-file gpurun_out/r1n_ewald_launches.csv python tools/profile_step.py --workload spce --lattice 32 --steps 1 2>&1 | tail -1
+for v in 0 1; do
+if [ $v = 1 ]; then export LUMOL_CUDA_NO_REORDER=1; fi
+timeout 300 python bench.py --steps 1000 --warmup 50 --no-e2e --no-cpu-baseline --no-spce > gpurun_out/bench_reorder_$v.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_reorder_$v.json')); print('noreorder=$v', d['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['config']['neighbor_list'])"
+done
