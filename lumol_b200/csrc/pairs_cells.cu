@@ -237,6 +237,7 @@ struct ScatterArgs {
     int* __restrict__ sorted_cell;
     double* __restrict__ frame;  // x, y, z planes of `frame_stride` doubles: positions in the frame of the box
     size_t frame_stride;
+    double frame_scale;  // 1 / sigma for a Lennard-Jones system: the staged kernel works in reduced lengths
     double* __restrict__ xref;
 };
 
@@ -267,9 +268,9 @@ __device__ __forceinline__ void cell_scatter_phase(int vb, const ScatterArgs& a)
     a.sorted_cell[dst] = c;
     // the same position in the frame of the box (cell centre + relative part), read by the staged kernel
     const int f = frame_start(c, lo) + rank;
-    a.frame[f] = x + ((double)cx + 0.5) * a.g.edge[0];
-    a.frame[a.frame_stride + f] = y + ((double)cy + 0.5) * a.g.edge[1];
-    a.frame[2 * a.frame_stride + f] = z + ((double)cz + 0.5) * a.g.edge[2];
+    a.frame[f] = (x + ((double)cx + 0.5) * a.g.edge[0]) * a.frame_scale;
+    a.frame[a.frame_stride + f] = (y + ((double)cy + 0.5) * a.g.edge[1]) * a.frame_scale;
+    a.frame[2 * a.frame_stride + f] = (z + ((double)cz + 0.5) * a.g.edge[2]) * a.frame_scale;
     a.xref[3 * i] = px;
     a.xref[3 * i + 1] = py;
     a.xref[3 * i + 2] = pz;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(256)
                        const double* __restrict__ xref, const double4* __restrict__ rel0,
                        const int* __restrict__ sorted_cell, const int* __restrict__ cell_start,
                        double4* __restrict__ sorted_pos,
-                       double* __restrict__ frame, size_t frame_stride, double threshold2, int epoch,
+                       double* __restrict__ frame, size_t frame_stride, double frame_scale, double threshold2, int epoch,
                        int* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -299,9 +300,9 @@ __global__ void __launch_bounds__(256)
         const int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
         const int first = cell_start[c];
         const int f = frame_start(c, first) + (s - first);
-        frame[f] = x + ((double)cx + 0.5) * g.edge[0];
-        frame[frame_stride + f] = y + ((double)cy + 0.5) * g.edge[1];
-        frame[2 * frame_stride + f] = z + ((double)cz + 0.5) * g.edge[2];
+        frame[f] = (x + ((double)cx + 0.5) * g.edge[0]) * frame_scale;
+        frame[frame_stride + f] = (y + ((double)cy + 0.5) * g.edge[1]) * frame_scale;
+        frame[2 * frame_stride + f] = (z + ((double)cz + 0.5) * g.edge[2]) * frame_scale;
     }
 }
 
@@ -805,6 +806,8 @@ struct ForceArgs {
     double cutoff2;  // (largest cut-off)^2: early-out of the general path
     // LJ fast path
     double lj_sigma2, lj_epsilon24, lj_epsilon48, lj_epsilon4, lj_cutoff2, lj_shift;
+    double lj_inv_sigma;                  // staged blocks: lengths in units of sigma
+    long long lj_reduced_cutoff2_bits;    // (cut-off / sigma)^2 as an integer: squared distances compare like integers
     const int4* __restrict__ blk_header;
     const int4* __restrict__ blk_entries;
     const int2* __restrict__ blk_runs;
@@ -1053,7 +1056,7 @@ __device__ __forceinline__ double reciprocal3(double x) {
     return fma(y, fma(e, e, e), y);
 }
 
-// One staged neighbour of the Lennard-Jones kernel: 19 FP64 instructions, no branch.  A padding entry points
+// One staged neighbour of the Lennard-Jones kernel: 17 FP64 instructions, no branch.  A padding entry points
 // at the dummy slot, far outside any cut-off.
 template <int MODE>
 __device__ __forceinline__ void staged_lj(const ForceArgs& a, const double* __restrict__ stage, unsigned index,
@@ -1061,13 +1064,14 @@ __device__ __forceinline__ void staged_lj(const ForceArgs& a, const double* __re
                                           double (&acc)[NL_NV]) {
     const double* pj = stage + index;
     const double dx = xi - pj[0], dy = yi - pj[STAGE_SLOTS], dz = zi - pj[2 * STAGE_SLOTS];
+    // reduced lengths (x / sigma): 1 / r^2 is s2 directly; the comparison runs on the integer pipe (r2 >= 0, so the
+    // bit patterns order like the values; NaN compares as outside)
     const double r2 = dx * dx + dy * dy + dz * dz;
-    const bool inside = r2 < a.lj_cutoff2;
-    const double rinv2 = reciprocal3(r2);
-    const double s2 = a.lj_sigma2 * rinv2;
+    const bool inside = __double_as_longlong(r2) < a.lj_reduced_cutoff2_bits;
+    const double s2 = reciprocal3(r2);
     const double s6 = s2 * s2 * s2;
-    // force(r) / r = -24 eps (s6 - 2 s6^2) / r^2 (functions.rs:85-88)
-    double fr = (s6 * rinv2) * fma(a.lj_epsilon48, s6, -a.lj_epsilon24);
+    // sigma^2 * force(r) / r = -24 eps (s6 - 2 s6^2) s2 (functions.rs:85-88); the thread rescales its sum at the end
+    double fr = (s6 * s2) * fma(a.lj_epsilon48, s6, -a.lj_epsilon24);
     fr = inside ? fr : 0.0;
     fx = fma(fr, dx, fx);
     fy = fma(fr, dy, fy);
@@ -1241,6 +1245,9 @@ __global__ void __launch_bounds__(LJ_THREADS, 2) lj_force_kernel(ForceArgs a) {
                 wcur = wnext;
                 wnext = wafter;
             }
+            fx *= a.lj_inv_sigma;
+            fy *= a.lj_inv_sigma;
+            fz *= a.lj_inv_sigma;
         }
     }
     if (mine && header.y > 0 && a.write_forces) {
@@ -1323,6 +1330,8 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     // Lennard-Jones fast path (one LJ interaction, no restriction, no charges in play): staged blocks
     const bool lj_system = ctx->any_pair && ctx->single_lj && ctx->coulomb.kind == 0;
     const bool allow_staging = lj_system && ctx->forced_path != 2;
+    // the staged kernel works in units of sigma (one multiplication less per pair)
+    const double frame_scale = lj_system ? 1.0 / ctx->host_pairs[0].p[0] : 1.0;
     const int stage_bytes = STAGE_BYTES;
     const int stage_atoms_max = STAGE_ATOMS_MAX;
     const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -1362,7 +1371,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
             list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
                                                                 ctx->sorted_cell.ptr, ctx->cell_start.ptr, ctx->sorted_pos.ptr,
                                                                 allow_staging ? ctx->frame_pos.ptr : nullptr, frame_stride,
-                                                                half * half, epoch, flags);
+                                                                frame_scale, half * half, epoch, flags);
         }
         ctx->launches++;
         ctx->clk_neighbor.launches++;
@@ -1387,6 +1396,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         s.sorted_cell = ctx->sorted_cell.ptr;
         s.frame = ctx->frame_pos.ptr;
         s.frame_stride = frame_stride;
+        s.frame_scale = frame_scale;
         s.xref = ctx->xref.ptr;
 
         TableArgs t;
@@ -1507,6 +1517,8 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     // not requested still takes the general kernel
     const bool lj_only = do_pairs && !do_coulomb && lj_system;
     a.lj_sigma2 = a.lj_epsilon24 = a.lj_epsilon48 = a.lj_epsilon4 = a.lj_cutoff2 = a.lj_shift = 0.0;
+    a.lj_inv_sigma = 1.0;
+    a.lj_reduced_cutoff2_bits = 0;
     if (lj_only) {
         const lumol_cuda_pair& p = ctx->host_pairs[0];
         a.lj_sigma2 = p.p[0] * p.p[0];
@@ -1514,6 +1526,10 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         a.lj_epsilon48 = 48.0 * p.p[1];
         a.lj_epsilon4 = 4.0 * p.p[1];
         a.lj_cutoff2 = p.cutoff * p.cutoff;
+        a.lj_inv_sigma = frame_scale;
+        const double reduced_cutoff = p.cutoff * frame_scale;
+        const double reduced_cutoff2 = reduced_cutoff * reduced_cutoff;
+        std::memcpy(&a.lj_reduced_cutoff2_bits, &reduced_cutoff2, sizeof(double));
         a.lj_shift = p.shift;
     }
     a.blk_header = ctx->blk_header.ptr;
@@ -1523,7 +1539,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     a.frame = ctx->frame_pos.ptr;
     a.frame_stride = frame_stride;
     a.ntiles = nblocks;
-    for (int d = 0; d < 3; d++) a.length[d] = g.length[d];
+    for (int d = 0; d < 3; d++) a.length[d] = g.length[d] * frame_scale;  // image vectors of the staged copies
     const size_t smem = lj_only ? (size_t)stage_bytes : sizeof(PairParams) * (size_t)ctx->nkinds * ctx->nkinds;
     if (!lj_only && smem > 100 * 1024) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many particle kinds (%d) for the shared pair table", ctx->nkinds);
