@@ -946,13 +946,16 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
 template <bool LJ_ONLY, int MODE>
 __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const PairParams* sp, const double (*offset64)[3],
                                                    int s_i, const int4& info_i, double& fx, double& fy, double& fz,
-                                                   double (&acc)[NL_NV]) {
+                                                   double (&acc)[NL_NV], int part = 0, int nparts = 1) {
+    // thread `part` of the `nparts` threads sharing the atom takes the words part, part + nparts, ...
     const double4 pi = a.sorted_pos[s_i];
     const int count = a.ncount[s_i];
-    const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
-    const int nwords = (count + 3) >> 2;
+    const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31) +
+                         (size_t)part * 32;
+    const int stride = 32 * nparts;
+    const int nwords = (((count + 3) >> 2) - part + nparts - 1) / nparts;
     uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
-    uint4 wnext = nwords > 1 ? words[32] : make_uint4(0, 0, 0, 0);
+    uint4 wnext = nwords > 1 ? words[stride] : make_uint4(0, 0, 0, 0);
     double4 pcur[4], pnext[4];
     {
         const unsigned e[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
@@ -964,7 +967,7 @@ __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const Pai
     const unsigned offset_base = (unsigned)__cvta_generic_to_shared(&offset64[0][0]);
     for (int w = 0; w < nwords; w++) {
         uint4 wafter = make_uint4(0, 0, 0, 0);
-        if (w + 2 < nwords) wafter = words[(w + 2) * 32];
+        if (w + 2 < nwords) wafter = words[(size_t)(w + 2) * stride];
         {
             const unsigned e[4] = {wnext.x, wnext.y, wnext.z, wnext.w};
 #pragma unroll
@@ -973,7 +976,7 @@ __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const Pai
         const unsigned entries[4] = {wcur.x, wcur.y, wcur.z, wcur.w};
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-            const bool listed = 4 * w + t < count;  // the last word is padded
+            const bool listed = 4 * (w * nparts + part) + t < count;  // the last word is padded
             const unsigned address = offset_base + (entries[t] >> 26) * 24u;
             double ox, oy, oz;
             asm("ld.shared.f64 %0, [%1];" : "=d"(ox) : "r"(address));
@@ -995,7 +998,9 @@ __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const Pai
 }
 
 // General kernel (any potential, restrictions, Ewald real space / Wolf): every block uses the global format.
-template <int MODE>
+// SPLIT threads (neighbouring lanes) share an atom and take every SPLIT-th word of its column: a 100k-atom water box
+// has only 3072 warps of one thread per atom, too few to hide the latency of the erfc / exp chains.
+template <int MODE, int SPLIT>
 __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairParams* sp = reinterpret_cast<PairParams*>(smem_raw);
@@ -1021,21 +1026,26 @@ __global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
 #pragma unroll
     for (int k = 0; k < NL_NV; k++) acc[k] = 0.0;
 
-    const int s_i = blockIdx.x * NL_THREADS + threadIdx.x;
+    const int s_i = (blockIdx.x * NL_THREADS + threadIdx.x) / SPLIT;
+    const int part = threadIdx.x % SPLIT;
     int4 info_i = make_int4(0, 0, 0, -1);
     bool active = s_i < a.n;
     if (active) {
         info_i = a.sorted_info[s_i];
         active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
     }
-    if (active) {
-        double fx = 0.0, fy = 0.0, fz = 0.0;
-        walk_global_column<false, MODE>(a, sp, offset64, s_i, info_i, fx, fy, fz, acc);
-        if (a.write_forces) {
-            a.force[3 * info_i.w] = fx;
-            a.force[3 * info_i.w + 1] = fy;
-            a.force[3 * info_i.w + 2] = fz;
-        }
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (active) walk_global_column<false, MODE>(a, sp, offset64, s_i, info_i, fx, fy, fz, acc, part, SPLIT);
+#pragma unroll
+    for (int o = 1; o < SPLIT; o <<= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (active && part == 0 && a.write_forces) {
+        a.force[3 * info_i.w] = fx;
+        a.force[3 * info_i.w + 1] = fy;
+        a.force[3 * info_i.w + 2] = fz;
     }
 
     if (MODE == NL_MODE_FULL) {
@@ -1546,7 +1556,12 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     }
     const bool full = req.energy || req.virial;
     const int threads = lj_only ? LJ_THREADS : NL_THREADS;
-    const int force_blocks = (n + threads - 1) / threads;
+    // general kernel: up to four threads per atom while that does not exceed about a dozen warps per SM slot
+    int split = 1;
+    if (!lj_only) {
+        while (split < 4 && (int64_t)n * split * 2 <= (int64_t)ctx->sm_count * 2048 * 4) split *= 2;
+    }
+    const int force_blocks = lj_only ? (n + threads - 1) / threads : (int)(((int64_t)n * split + threads - 1) / threads);
     LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)force_blocks * NL_NV));
     a.partials = ctx->partials.ptr;
 
@@ -1554,7 +1569,13 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     if (lj_only) {
         kernel = full ? (const void*)lj_force_kernel<NL_MODE_FULL> : (const void*)lj_force_kernel<NL_MODE_FORCES>;
     } else {
-        kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL> : (const void*)list_force_kernel<NL_MODE_FORCES>;
+        if (split == 4) {
+            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 4> : (const void*)list_force_kernel<NL_MODE_FORCES, 4>;
+        } else if (split == 2) {
+            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 2> : (const void*)list_force_kernel<NL_MODE_FORCES, 2>;
+        } else {
+            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 1> : (const void*)list_force_kernel<NL_MODE_FORCES, 1>;
+        }
     }
     if (smem > 40 * 1024) {
         LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,1 +1,3 @@
-timeout 120 ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum --clock-control none -k regex:lj_force -c 1 --csv --log-file gpurun_out/exp_launches.csv python tools/profile_step.py --steps 1 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_md.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python bench.py --workload spce --lattice 32 --steps 50 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/bench_spce32_k4.json 2> gpurun_out/bench_spce32_k4.err; tail -3 gpurun_out/bench_spce32_k4.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_spce32_k4.json').read().splitlines()[-1]); print(d['value'], d['ms_per_step'], {k:v.get('ms_per_step', v.get('rho_plus_force_ms', v.get('avg_launch_ms'))) for k,v in d['roofline_extra'].items()})"
