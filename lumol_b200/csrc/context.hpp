@@ -170,6 +170,7 @@ struct Context {
     DeviceBuffer<float4> sorted_f32;   // the same position in FP32
     DeviceBuffer<int4> sorted_info;    // kind, mol_first, bd_row, original index
     DeviceBuffer<int> scan_scratch;
+    DeviceBuffer<unsigned char> cell_needed;   // sharded runs: cells this rank's lists refer to
     DeviceBuffer<int> sorted_cell;             // linear cell index, sorted order
     DeviceBuffer<int2> blk_runs;               // runs of consecutive cells: one bulk copy each
     DeviceBuffer<int4> blk_header, blk_entries;  // staging tables of the Lennard-Jones kernel (pairs_cells.cu)

@@ -108,12 +108,16 @@ __device__ __forceinline__ int cell_coordinate(double wrapped, double length, in
 constexpr int REBUILD_THREADS = 256;
 constexpr int REBUILD_WARPS = REBUILD_THREADS / 32;
 
-__device__ __forceinline__ void cell_zero_phase(int count, int* __restrict__ cell_count, int* __restrict__ flags) {
+__device__ __forceinline__ void cell_zero_phase(int count, int* __restrict__ cell_count, unsigned char* __restrict__ cell_needed,
+                                                int* __restrict__ flags) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_phase
         flags[FLAG_NONFINITE] = 0;
     }
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) cell_count[k] = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        cell_count[k] = 0;
+        cell_needed[k] = 0;
+    }
 }
 
 __device__ __forceinline__ void cell_assign_phase(int vb, int n, const GridView& g, const double* __restrict__ pos,
@@ -284,9 +288,11 @@ __global__ void __launch_bounds__(256)
                        const int* __restrict__ sorted_cell, const int* __restrict__ cell_start,
                        double4* __restrict__ sorted_pos,
                        double* __restrict__ frame, size_t frame_stride, double frame_scale, double threshold2, int epoch,
-                       int* __restrict__ flags) {
+                       const unsigned char* __restrict__ cell_needed, int* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    // sharded runs: a rank refreshes (and watches the displacement of) only the cells its own lists reach
+    if (cell_needed != nullptr && cell_needed[sorted_cell[s]] == 0) return;
     const int i = order[s];
     const double dx = pos[3 * i] - xref[3 * i];
     const double dy = pos[3 * i + 1] - xref[3 * i + 1];
@@ -496,6 +502,7 @@ struct BuildArgs {
     unsigned short* __restrict__ self_local;
     unsigned* __restrict__ nlist;
     int* __restrict__ ncount;
+    unsigned char* __restrict__ cell_needed;  // cells whose atoms this rank's lists refer to
     int* __restrict__ flags;
 };
 
@@ -552,6 +559,13 @@ __device__ __forceinline__ void list_build_phase(int vb, const BuildArgs& a, con
             if (!__any_sync(0xffffffffu, active)) {
                 if (s_i < he) a.ncount[s_i] = 0;
                 continue;
+            }
+            if (lane < 27) {
+                int mx = cx + (lane % 3) - 1, my = cy + ((lane / 3) % 3) - 1, mz = cz + (lane / 9) - 1;
+                mx += mx < 0 ? a.g.nc[0] : (mx >= a.g.nc[0] ? -a.g.nc[0] : 0);
+                my += my < 0 ? a.g.nc[1] : (my >= a.g.nc[1] ? -a.g.nc[1] : 0);
+                mz += mz < 0 ? a.g.nc[2] : (mz >= a.g.nc[2] ? -a.g.nc[2] : 0);
+                a.cell_needed[(mz * a.g.nc[1] + my) * a.g.nc[0] + mx] = 1;
             }
             // The columns of 32 consecutive atoms form one contiguous slab of (capacity / 4) x 32 16-byte words,
             // interleaved word by word: word w of atom i is word (w * 32 + i % 32) of slab i / 32, so that a
@@ -746,7 +760,7 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild_kernel(RebuildArgs r)
     }
     const int atom_blocks = (r.n + REBUILD_THREADS - 1) / REBUILD_THREADS;
 
-    cell_zero_phase(r.ncells + 1, r.cell_count, r.flags);
+    cell_zero_phase(r.ncells + 1, r.cell_count, r.build.cell_needed, r.flags);
     grid.sync();
     for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
         cell_assign_phase(vb, r.n, r.g, r.position, r.cell_of, r.slot_of, r.cell_count, r.flags);
@@ -1325,6 +1339,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     LUMOL_CUDA_CHECK(ctx, ctx->cell_of.reserve((size_t)2 * n));  // cell_of + slot_of
     LUMOL_CUDA_CHECK(ctx, ctx->cell_count.reserve((size_t)ncells + 1));
     LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_needed.reserve((size_t)ncells + 1));
     LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));  // order + grouped
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_pos.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
@@ -1381,7 +1396,8 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
             list_update_kernel<<<blocks, 256, 0, ctx->stream>>>(n, g, order, ctx->position.ptr, ctx->xref.ptr, ctx->rel0.ptr,
                                                                 ctx->sorted_cell.ptr, ctx->cell_start.ptr, ctx->sorted_pos.ptr,
                                                                 allow_staging ? ctx->frame_pos.ptr : nullptr, frame_stride,
-                                                                frame_scale, half * half, epoch, flags);
+                                                                frame_scale, half * half, epoch,
+                                                                ctx->nranks > 1 ? ctx->cell_needed.ptr : nullptr, flags);
         }
         ctx->launches++;
         ctx->clk_neighbor.launches++;
@@ -1442,6 +1458,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         b.sorted_info = ctx->sorted_info.ptr;
         b.nlist = ctx->nlist.ptr;
         b.ncount = ctx->ncount.ptr;
+        b.cell_needed = ctx->cell_needed.ptr;
         b.flags = flags;
         RebuildArgs r;
         r.n = n;
