@@ -926,6 +926,13 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
         if (status) return status;
     }
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->nranks > 1) {
+        double timed_out = 0.0;
+        LUMOL_CUDA_CHECK(c, cudaMemcpy(&timed_out, c->results.ptr + RES_FLAGS + 1, sizeof(double), cudaMemcpyDeviceToHost));
+        if (timed_out != 0.0) {
+            return c->fail(LUMOL_CUDA_ERROR_COMM, "the positions of another rank did not arrive (peer exchange timed out)");
+        }
+    }
     if (c->path == 1) {
         int rebuilds = 0, overflow = 0;
         int status = neighbor_list_status(c, &rebuilds, &overflow);

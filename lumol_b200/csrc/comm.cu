@@ -12,7 +12,9 @@
 
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace lumol {
 
@@ -29,6 +31,7 @@ typedef int (*fn_all_gather)(const void*, void*, size_t, int, NcclComm, cudaStre
 typedef const char* (*fn_get_error_string)(int);
 
 constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
+constexpr int NCCL_CHAR = 0;     // ncclChar
 constexpr int NCCL_SUM = 0;      // ncclSum
 
 struct NcclApi {
@@ -73,6 +76,22 @@ static bool load_nccl(std::string& error) {
 struct Comm {
     NcclComm comm = nullptr;
     DeviceBuffer<double> staging;
+    // ---- peer-memory position exchange --------------------------------------------------------------
+    // Instead of an NCCL all-gather after the drift, the drift kernel itself stores the new positions of the rank's
+    // atoms into an inbox on every other GPU (NVLink peer stores through CUDA IPC mappings) and raises a flag
+    // there; a gather kernel waits for the flags of all peers and copies their blocks out of the local inbox.
+    // Two inbox copies alternate with the parity of the push number: a rank that is one step ahead writes into
+    // the copy its peers are not reading.
+    int peer_state = 0;  // 0: not set up, 1: ready, -1: unavailable (NCCL all-gather is used)
+    int64_t peer_atoms = 0;
+    int push_epoch = 0;
+    DeviceBuffer<double> inbox;      // 2 x 3n
+    DeviceBuffer<int> inbox_flags;   // 2 x PEER_MAX_RANKS flags, then the block counter
+    DeviceBuffer<unsigned char> handle_staging;
+    double* peer_inbox[PEER_MAX_RANKS] = {};
+    int* peer_flags[PEER_MAX_RANKS] = {};
+    void* opened[2 * PEER_MAX_RANKS] = {};
+    int nopened = 0;
 };
 
 #define NCCL_CHECK(ctx, expr)                                                                               \
@@ -99,6 +118,159 @@ int comm_allgather_positions(Context* ctx) { return allgather_in_place(ctx, ctx-
 
 int comm_allgather_blocks(Context* ctx, double* data, int64_t total) { return allgather_in_place(ctx, data, total / 3, 3); }
 
+// ------------------------------------------------------------------------------------------------
+// peer-memory position exchange
+// ------------------------------------------------------------------------------------------------
+
+static void peer_close(Comm* comm) {
+    for (int k = 0; k < comm->nopened; k++) cudaIpcCloseMemHandle(comm->opened[k]);
+    comm->nopened = 0;
+    comm->peer_state = 0;
+}
+
+// Collective over the ranks: allocates the inboxes, exchanges their IPC handles through NCCL and maps the peers'.
+// Any failure on any rank (no peer access, IPC not permitted) makes every rank fall back to the NCCL all-gather.
+static int peer_setup(Context* ctx) {
+    Comm* comm = ctx->comm;
+    peer_close(comm);
+    comm->peer_atoms = ctx->n;
+    comm->push_epoch = 0;
+    const int nranks = ctx->nranks;
+    bool ok = nranks <= PEER_MAX_RANKS && std::getenv("LUMOL_CUDA_NO_PEER_PUSH") == nullptr;
+    const size_t n3 = (size_t)3 * ctx->n;
+    cudaIpcMemHandle_t mine[2];
+    std::memset(mine, 0, sizeof(mine));
+    if (ok) {
+        ok = comm->inbox.reserve(2 * n3) == cudaSuccess && comm->inbox_flags.reserve(2 * PEER_MAX_RANKS + 8) == cudaSuccess;
+        if (ok) {
+            ok = cudaMemsetAsync(comm->inbox_flags.ptr, 0, (2 * PEER_MAX_RANKS + 8) * sizeof(int), ctx->stream) == cudaSuccess &&
+                 cudaIpcGetMemHandle(&mine[0], comm->inbox.ptr) == cudaSuccess &&
+                 cudaIpcGetMemHandle(&mine[1], comm->inbox_flags.ptr) == cudaSuccess;
+        }
+        cudaGetLastError();
+    }
+    // exchange: [ok byte + padding | two handles] per rank
+    const size_t record = 16 + sizeof(mine);
+    std::vector<unsigned char> host(record * (size_t)nranks, 0);
+    LUMOL_CUDA_CHECK(ctx, comm->handle_staging.reserve(record * (size_t)nranks));
+    unsigned char* own = host.data() + record * (size_t)ctx->rank;
+    own[0] = ok ? 1 : 0;
+    std::memcpy(own + 16, mine, sizeof(mine));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(comm->handle_staging.ptr + record * (size_t)ctx->rank, own, record, cudaMemcpyHostToDevice,
+                                          ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.all_gather(comm->handle_staging.ptr + record * (size_t)ctx->rank, comm->handle_staging.ptr, record, NCCL_CHAR,
+                                      comm->comm, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(host.data(), comm->handle_staging.ptr, host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < nranks; p++) ok = ok && host[record * (size_t)p] == 1;
+    if (ok) {
+        for (int p = 0; p < nranks && ok; p++) {
+            if (p == ctx->rank) {
+                comm->peer_inbox[p] = comm->inbox.ptr;
+                comm->peer_flags[p] = comm->inbox_flags.ptr;
+                continue;
+            }
+            cudaIpcMemHandle_t theirs[2];
+            std::memcpy(theirs, host.data() + record * (size_t)p + 16, sizeof(theirs));
+            void* inbox = nullptr;
+            void* flags = nullptr;
+            ok = cudaIpcOpenMemHandle(&inbox, theirs[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) comm->opened[comm->nopened++] = inbox;
+            ok = ok && cudaIpcOpenMemHandle(&flags, theirs[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) comm->opened[comm->nopened++] = flags;
+            comm->peer_inbox[p] = (double*)inbox;
+            comm->peer_flags[p] = (int*)flags;
+        }
+        cudaGetLastError();
+    }
+    // every rank must take the same path: agree on the outcome
+    double verdict = ok ? 0.0 : 1.0;
+    LUMOL_CUDA_CHECK(ctx, comm->staging.reserve(8));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(comm->staging.ptr, &verdict, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.all_reduce(comm->staging.ptr, comm->staging.ptr, 1, NCCL_FLOAT64, NCCL_SUM, comm->comm, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(&verdict, comm->staging.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (verdict != 0.0) {
+        peer_close(comm);
+        comm->peer_state = -1;
+    } else {
+        comm->peer_state = 1;
+    }
+    return 0;
+}
+
+// Fills `push` for the next drift kernel (collective: every rank calls it at the same step).  push->nranks stays 0
+// when the peer path is unavailable and the caller must use comm_allgather_positions instead.
+int comm_peer_push_begin(Context* ctx, PeerPush* push) {
+    *push = PeerPush();
+    if (ctx->nranks <= 1 || ctx->comm == nullptr) return 0;
+    Comm* comm = ctx->comm;
+    if (comm->peer_state == 0 || comm->peer_atoms != ctx->n) {
+        int status = peer_setup(ctx);
+        if (status != 0) return status;
+    }
+    if (comm->peer_state != 1) return 0;
+    comm->push_epoch++;
+    const int parity = comm->push_epoch & 1;
+    push->nranks = ctx->nranks;
+    push->rank = ctx->rank;
+    push->epoch = comm->push_epoch;
+    for (int p = 0; p < ctx->nranks; p++) {
+        push->inbox[p] = comm->peer_inbox[p] + (size_t)parity * 3 * ctx->n;
+        push->flags[p] = comm->peer_flags[p] + parity * PEER_MAX_RANKS;
+    }
+    push->counter = comm->inbox_flags.ptr + 2 * PEER_MAX_RANKS;
+    return 0;
+}
+
+// Waits until every peer's block of this push has arrived in the local inbox, then copies the blocks into the
+// position array.  RES_FLAGS + 1 is raised (and the wait abandoned) after about twenty seconds.
+__global__ void __launch_bounds__(256)
+    peer_gather_kernel(int nranks, int rank, int epoch, const int* __restrict__ flags, const double* __restrict__ inbox,
+                       double* __restrict__ position, int64_t chunk3, int64_t n3, double* __restrict__ results) {
+    __shared__ int proceed;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        const long long start = clock64();
+        for (int p = 0; p < nranks; p++) {
+            if (p == rank) continue;
+            const volatile int* flag = flags + p;
+            while (*flag < epoch) {
+                if (clock64() - start > 40000000000ll) {
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        proceed = ok;
+    }
+    __syncthreads();
+    if (!proceed) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) results[RES_FLAGS + 1] = 1.0;
+        return;
+    }
+    const int64_t own_lo = chunk3 * rank, own_hi = min(n3, own_lo + chunk3);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n3; k += (int64_t)gridDim.x * blockDim.x) {
+        if (k < own_lo || k >= own_hi) position[k] = __ldcv(inbox + k);
+    }
+}
+
+int comm_peer_gather(Context* ctx, const PeerPush& push) {
+    if (push.nranks <= 1) return 0;
+    ScopedClock clock(ctx, &ctx->clk_comm);
+    const int64_t n3 = 3 * ctx->n;
+    const int64_t chunk3 = 3 * ((ctx->n + ctx->nranks - 1) / ctx->nranks);
+    int blocks = (int)((n3 + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;  // every block spins on the flags: all must be resident
+    peer_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(push.nranks, push.rank, push.epoch, push.flags[push.rank], push.inbox[push.rank],
+                                                        ctx->position.ptr, chunk3, n3, ctx->results.ptr);
+    ctx->launches++;
+    ctx->clk_comm.launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
 int comm_allreduce(Context* ctx, double* data, int64_t count) {
     if (ctx->nranks <= 1) return 0;
     ScopedClock clock(ctx, &ctx->clk_comm);
@@ -112,7 +284,11 @@ void comm_destroy(Context* ctx) {
         if (ctx->comm->comm != nullptr && g_nccl.comm_destroy != nullptr) {
             g_nccl.comm_destroy(ctx->comm->comm);
         }
+        peer_close(ctx->comm);
         ctx->comm->staging.release();
+        ctx->comm->inbox.release();
+        ctx->comm->inbox_flags.release();
+        ctx->comm->handle_staging.release();
         delete ctx->comm;
         ctx->comm = nullptr;
     }

@@ -85,6 +85,17 @@ struct KernelClock {
 
 struct Comm;  // comm.cu
 
+// Peer-memory position exchange (comm.cu): where the drift kernel of a sharded run stores the new positions of its
+// atoms on the other GPUs, and how their arrival is signalled.
+constexpr int PEER_MAX_RANKS = 8;
+struct PeerPush {
+    int nranks = 0, rank = 0;
+    int epoch = 0;                        // push number; its parity selects the inbox copy
+    double* inbox[PEER_MAX_RANKS] = {};   // rank p's inbox copy of this parity (3 n doubles), mapped here
+    int* flags[PEER_MAX_RANKS] = {};      // rank p's arrival flags of this parity: flags[source rank] = epoch
+    int* counter = nullptr;               // blocks of the pushing kernel that are done
+};
+
 struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -283,6 +294,8 @@ int md_step(Context* ctx, bool first, bool last);                               
 int launch_scale_velocities(Context* ctx, double factor, bool from_device);                      // integrate.cu
 int launch_remove_translation(Context* ctx);                                                     // integrate.cu
 int evaluate_forces_device(Context* ctx, const ComputeRequest& req);                             // api.cu
+int comm_peer_push_begin(Context* ctx, PeerPush* push);                                          // comm.cu
+int comm_peer_gather(Context* ctx, const PeerPush& push);                                        // comm.cu
 int comm_allgather_positions(Context* ctx);                                                      // comm.cu
 int comm_allreduce(Context* ctx, double* data, int64_t count);                                   // comm.cu
 int comm_allgather_blocks(Context* ctx, double* data, int64_t total);                            // comm.cu

@@ -23,31 +23,73 @@ static inline int grid_for(int64_t count, int sm_count) {
     return (int)blocks;
 }
 
-// VelocityVerlet first half (integrators.rs:47-53): a = f / m; v += (0.5 dt) a; x += v dt.
-// The reference stores accelerations; a = force / mass is recomputed here from the resident forces,
-// which gives the identical value and saves one n x 3 array (208 B/atom/step in total).
-__global__ void __launch_bounds__(INT_THREADS)
-    vv_kick_drift_kernel(int64_t lo3, int64_t hi3, double half_dt, double dt, const double* __restrict__ force,
-                         const double* __restrict__ mass, double* __restrict__ velocity, double* __restrict__ position) {
-    for (int64_t k = lo3 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < hi3; k += (int64_t)gridDim.x * blockDim.x) {
-        const double a = __ddiv_rn(force[k], mass[k / 3]);
-        const double v = __dadd_rn(velocity[k], __dmul_rn(half_dt, a));
-        velocity[k] = v;
-        position[k] = __dadd_rn(position[k], __dmul_rn(v, dt));
+// Sharded runs: the drift kernel is also the position exchange.  Every new position is stored into the inbox of every
+// other GPU (peer stores over NVLink, comm.cu); the last block to finish raises this rank's arrival flag on the peers.
+__device__ __forceinline__ void peer_store(const PeerPush& push, int64_t k, double x) {
+    for (int p = 0; p < push.nranks; p++) {
+        if (p != push.rank) push.inbox[p][k] = x;
     }
 }
 
-// Second half of one step and first half of the next in one pass (no thermostat or control runs between them):
-// the same three roundings as the two kernels, 128 instead of 208 bytes per atom.
-__global__ void __launch_bounds__(INT_THREADS)
-    vv_kick_kick_drift_kernel(int64_t lo3, int64_t hi3, double half_dt, double dt, const double* __restrict__ force,
-                              const double* __restrict__ mass, double* __restrict__ velocity, double* __restrict__ position) {
-    for (int64_t k = lo3 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < hi3; k += (int64_t)gridDim.x * blockDim.x) {
-        const double kick = __dmul_rn(half_dt, __ddiv_rn(force[k], mass[k / 3]));
-        const double v = __dadd_rn(__dadd_rn(velocity[k], kick), kick);
-        velocity[k] = v;
-        position[k] = __dadd_rn(position[k], __dmul_rn(v, dt));
+__device__ __forceinline__ void peer_publish(const PeerPush& push) {
+    if (push.nranks <= 1) return;
+    __shared__ bool last;
+    __threadfence_system();  // this thread's peer stores are visible before the block's ticket is taken
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(push.counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *push.counter = 0;
+        if (threadIdx.x < push.nranks && (int)threadIdx.x != push.rank) {
+            __threadfence_system();
+            *(reinterpret_cast<volatile int*>(push.flags[threadIdx.x]) + push.rank) = push.epoch;
+        }
     }
+}
+
+// VelocityVerlet first half (integrators.rs:47-53): a = f / m; v += (0.5 dt) a; x += v dt.
+// The reference stores accelerations; a = force / mass is recomputed here from the resident forces,
+// which gives the identical value and saves one n x 3 array (208 B/atom/step in total).
+// MERGED: the second half of the previous step and the first half of this one in one pass (no thermostat or control
+// runs between them): the same three roundings as the two kernels, 128 instead of 208 bytes per atom.
+template <bool MERGED>
+__device__ __forceinline__ double vv_advance(double half_dt, double dt, double f, double m, double& v, double x) {
+    const double kick = __dmul_rn(half_dt, __ddiv_rn(f, m));
+    v = __dadd_rn(v, kick);
+    if (MERGED) v = __dadd_rn(v, kick);
+    return __dadd_rn(x, __dmul_rn(v, dt));
+}
+
+// Two consecutive components per thread: 16-byte loads and stores, also towards the peers' inboxes.
+template <bool MERGED>
+__global__ void __launch_bounds__(INT_THREADS)
+    vv_kick_drift_kernel(int64_t lo3, int64_t hi3, double half_dt, double dt, const double* __restrict__ force,
+                         const double* __restrict__ mass, double* __restrict__ velocity, double* __restrict__ position,
+                         PeerPush push) {
+    const int64_t first = lo3 & ~(int64_t)1;
+    for (int64_t k = first + 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); k < hi3; k += 2 * (int64_t)gridDim.x * blockDim.x) {
+        if (k >= lo3 && k + 1 < hi3) {
+            const double2 f = *reinterpret_cast<const double2*>(force + k);
+            double2 v = *reinterpret_cast<const double2*>(velocity + k);
+            double2 x = *reinterpret_cast<const double2*>(position + k);
+            x.x = vv_advance<MERGED>(half_dt, dt, f.x, mass[k / 3], v.x, x.x);
+            x.y = vv_advance<MERGED>(half_dt, dt, f.y, mass[(k + 1) / 3], v.y, x.y);
+            *reinterpret_cast<double2*>(velocity + k) = v;
+            *reinterpret_cast<double2*>(position + k) = x;
+            for (int p = 0; p < push.nranks; p++) {
+                if (p != push.rank) *reinterpret_cast<double2*>(push.inbox[p] + k) = x;
+            }
+        } else {
+            for (int64_t e = max(k, lo3); e < min(k + 2, hi3); e++) {
+                double v = velocity[e];
+                const double x = vv_advance<MERGED>(half_dt, dt, force[e], mass[e / 3], v, position[e]);
+                velocity[e] = v;
+                position[e] = x;
+                peer_store(push, e, x);
+            }
+        }
+    }
+    peer_publish(push);
 }
 
 // VelocityVerlet second half (integrators.rs:55-68): a = f / m; v += (0.5 dt) a.
@@ -293,22 +335,30 @@ int md_step(Context* ctx, bool first, bool last) {
 
     if (ctx->integrator == LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET) {
         const bool merged = ctx->thermostat == LUMOL_CUDA_THERMOSTAT_NONE && ctx->controls == 0;
+        // sharded: the drift stores the new positions straight into the other GPUs' inboxes (nranks stays 0 when
+        // peer memory is not available: NCCL all-gather below)
+        PeerPush push;
+        if ((status = comm_peer_push_begin(ctx, &push)) != 0) return status;
         {
             ScopedClock clock(ctx, &ctx->clk_integrate);
             if (merged && !first) {
-                vv_kick_kick_drift_kernel<<<grid, INT_THREADS, 0, ctx->stream>>>(lo3, hi3, 0.5 * ctx->dt, ctx->dt, ctx->force.ptr,
-                                                                                 ctx->mass.ptr, ctx->velocity.ptr,
-                                                                                 ctx->position.ptr);
+                vv_kick_drift_kernel<true><<<grid, INT_THREADS, 0, ctx->stream>>>(lo3, hi3, 0.5 * ctx->dt, ctx->dt, ctx->force.ptr,
+                                                                                  ctx->mass.ptr, ctx->velocity.ptr,
+                                                                                  ctx->position.ptr, push);
             } else {
-                vv_kick_drift_kernel<<<grid, INT_THREADS, 0, ctx->stream>>>(lo3, hi3, 0.5 * ctx->dt, ctx->dt, ctx->force.ptr,
-                                                                            ctx->mass.ptr, ctx->velocity.ptr,
-                                                                            ctx->position.ptr);
+                vv_kick_drift_kernel<false><<<grid, INT_THREADS, 0, ctx->stream>>>(lo3, hi3, 0.5 * ctx->dt, ctx->dt, ctx->force.ptr,
+                                                                                   ctx->mass.ptr, ctx->velocity.ptr,
+                                                                                   ctx->position.ptr, push);
             }
             ctx->launches++;
             ctx->clk_integrate.launches++;
             LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
         }
-        if (ctx->nranks > 1 && (status = comm_allgather_positions(ctx)) != 0) return status;
+        if (push.nranks > 1) {
+            if ((status = comm_peer_gather(ctx, push)) != 0) return status;
+        } else if (ctx->nranks > 1 && (status = comm_allgather_positions(ctx)) != 0) {
+            return status;
+        }
         if ((status = evaluate_forces_device(ctx, req)) != 0) return status;
         if (!merged || last) {
             ScopedClock clock(ctx, &ctx->clk_integrate);
