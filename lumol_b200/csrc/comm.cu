@@ -136,7 +136,11 @@ static int peer_setup(Context* ctx) {
     comm->peer_atoms = ctx->n;
     comm->push_epoch = 0;
     const int nranks = ctx->nranks;
-    bool ok = nranks <= PEER_MAX_RANKS && std::getenv("LUMOL_CUDA_NO_PEER_PUSH") == nullptr;
+    // Measured on 8 x B200 (1M-atom box): pushing from the drift kernel beats the NCCL all-gather with two ranks
+    // (22 + 35 us against 58 + 19 us) but not with four or eight, where one kernel storing to three or seven peers
+    // reaches only ~400 GB/s; LUMOL_CUDA_PEER_PUSH=1 / =0 forces the choice.
+    const char* forced = std::getenv("LUMOL_CUDA_PEER_PUSH");
+    bool ok = nranks <= PEER_MAX_RANKS && (forced != nullptr ? forced[0] == '1' : nranks == 2);
     const size_t n3 = (size_t)3 * ctx->n;
     cudaIpcMemHandle_t mine[2];
     std::memset(mine, 0, sizeof(mine));
