@@ -75,6 +75,7 @@ int choose_neighbor_path(Context* ctx, double cutoff) {
 // flags[0]: rebuild requested, flags[1]: a list column overflowed, flags[2]: number of rebuilds so far
 constexpr int FLAG_REBUILD = 0, FLAG_OVERFLOW = 1, FLAG_COUNT = 2;
 // flags[3]: blocks that could not be staged (FLAG_UNSTAGED); flags[4]: a position was not finite at the last rebuild
+constexpr int FLAG_UNSTAGED = 3;
 constexpr int FLAG_NONFINITE = 4;
 
 // ------------------------------------------------------------------------------------------------
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(256)
     if (!(dx * dx + dy * dy + dz * dz <= threshold2)) flags[FLAG_REBUILD] = epoch;  // also catches NaN
     const double4 r = rel0[s];
     const double x = r.x + dx, y = r.y + dy, z = r.z + dz;
-    sorted_pos[s] = make_double4(x, y, z, r.w);
+    // the cell-relative copy is read by the general kernel and by blocks that could not be staged only
+    if (frame == nullptr || flags[FLAG_UNSTAGED] != 0) sorted_pos[s] = make_double4(x, y, z, r.w);
     if (frame != nullptr) {
         const int c = sorted_cell[s];
         const int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
@@ -336,7 +338,6 @@ constexpr int STAGE_MAX_SEGMENTS = 6;
 constexpr int STAGE_SLOTS = 4528;                   // atoms of the staged copy, dummy slot 0 included (a multiple of 16)
 constexpr int STAGE_BYTES = 3 * STAGE_SLOTS * 8;    // x | y | z planes: 106 KiB, two blocks per SM
 constexpr int STAGE_ATOMS_MAX = STAGE_SLOTS;
-constexpr int FLAG_UNSTAGED = 3;                    // flags[3]: blocks of the last rebuild that were not staged
 
 struct BlockRows {
     int c0, K, nx, r0, xa0, len0, nseg, nentries;
