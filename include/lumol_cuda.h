@@ -143,7 +143,9 @@ enum {
 typedef enum {
     LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET = 0, /* integrators.rs:39-70 */
     LUMOL_CUDA_INTEGRATOR_VERLET = 1,          /* integrators.rs:92-123 */
-    LUMOL_CUDA_INTEGRATOR_LEAP_FROG = 2        /* integrators.rs:145-169 */
+    LUMOL_CUDA_INTEGRATOR_LEAP_FROG = 2,       /* integrators.rs:145-169 */
+    LUMOL_CUDA_INTEGRATOR_BERENDSEN_BAROSTAT = 3,       /* integrators.rs:176-255 */
+    LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT = 4  /* integrators.rs:260-341 */
 } lumol_cuda_integrator;
 
 /* Thermostats, lumol-sim/src/md/thermostats.rs */
@@ -156,7 +158,9 @@ typedef enum {
 
 /* Controls, lumol-sim/src/md/controls.rs (bit mask) */
 enum {
-    LUMOL_CUDA_CONTROL_REMOVE_TRANSLATION = 1 /* controls.rs:30-41 */
+    LUMOL_CUDA_CONTROL_REMOVE_TRANSLATION = 1, /* controls.rs:30-41 */
+    LUMOL_CUDA_CONTROL_REMOVE_ROTATION = 2,    /* controls.rs:47-73 */
+    LUMOL_CUDA_CONTROL_REWRAP = 4              /* controls.rs:80-87 */
 };
 
 /* DegreesOfFreedom, sys/system.rs:249-255 */
@@ -266,6 +270,17 @@ int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps);
 /* velocities::scale / thermostat scaling (velocities.rs:16-22), RemoveTranslation (controls.rs:30-41) */
 int32_t lumol_cuda_scale_velocities(lumol_cuda_context* ctx, double factor);
 int32_t lumol_cuda_remove_translation(lumol_cuda_context* ctx);
+/* RemoveRotation::control and Rewrap::control (controls.rs:47-87) on the resident state. */
+int32_t lumol_cuda_remove_rotation(lumol_cuda_context* ctx);
+int32_t lumol_cuda_rewrap(lumol_cuda_context* ctx);
+/* BerendsenBarostat / AnisoBerendsenBarostat (integrators.rs:176-342), selected by lumol_cuda_md_setup: target is
+ * the stress matrix (row-major; the isotropic barostat reads target[0] as its pressure), tau the time scale in units
+ * of the timestep.  Every step scales positions and cell by eta, evaluates pressure (or stress) and forces in one
+ * pass at the new positions, and updates eta; positions and velocities stay on the device, the host sees nine sums per
+ * step.  lumol_cuda_md_run fails with the reference's message when the cell shrinks below twice the cut-off. */
+int32_t lumol_cuda_md_set_barostat(lumol_cuda_context* ctx, const double target[9], double tau);
+/* The cell matrix as it is now (the barostats change it). */
+int32_t lumol_cuda_get_cell(lumol_cuda_context* ctx, double cell[9]);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) ----------------------------------------------- */
 /* Rank 0 creates the id, the host launcher broadcasts it, every rank calls comm_init.  Afterwards each

@@ -20,8 +20,9 @@ CELL_INFINITE, CELL_ORTHORHOMBIC, CELL_TRICLINIC = 0, 1, 2
 FORCES, ENERGY, ATOMIC_VIRIAL, MOLECULAR_VIRIAL = 1, 2, 4, 8
 PART_PAIRS, PART_BONDED, PART_COULOMB, PART_ALL = 1, 2, 4, 7
 INTEGRATOR_VELOCITY_VERLET, INTEGRATOR_VERLET, INTEGRATOR_LEAP_FROG = 0, 1, 2
+INTEGRATOR_BERENDSEN_BAROSTAT, INTEGRATOR_ANISO_BERENDSEN_BAROSTAT = 3, 4
 THERMOSTAT_NONE, THERMOSTAT_RESCALE, THERMOSTAT_BERENDSEN, THERMOSTAT_CSVR = 0, 1, 2, 3
-CONTROL_REMOVE_TRANSLATION = 1
+CONTROL_REMOVE_TRANSLATION, CONTROL_REMOVE_ROTATION, CONTROL_REWRAP = 1, 2, 4
 DOF_PARTICLES, DOF_MOLECULES = 0, 1
 
 SUCCESS = 0
@@ -149,6 +150,10 @@ SIGNATURES = {
     "lumol_cuda_md_run": (_c.c_int32, [_ctx, _c.c_int64]),
     "lumol_cuda_scale_velocities": (_c.c_int32, [_ctx, _c.c_double]),
     "lumol_cuda_remove_translation": (_c.c_int32, [_ctx]),
+    "lumol_cuda_remove_rotation": (_c.c_int32, [_ctx]),
+    "lumol_cuda_rewrap": (_c.c_int32, [_ctx]),
+    "lumol_cuda_md_set_barostat": (_c.c_int32, [_ctx, _dp, _c.c_double]),
+    "lumol_cuda_get_cell": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_comm_unique_id": (_c.c_int32, [_c.POINTER(_c.c_uint8)]),
     "lumol_cuda_comm_init": (_c.c_int32, [_ctx, _c.c_int32, _c.c_int32, _c.POINTER(_c.c_uint8)]),
     "lumol_cuda_set_profiling": (_c.c_int32, [_ctx, _c.c_int32]),

@@ -855,11 +855,12 @@ extern "C" int32_t lumol_cuda_ewald_kvectors(lumol_cuda_context* ctx, int64_t ca
 
 extern "C" int32_t lumol_cuda_md_setup(lumol_cuda_context* ctx, int32_t integrator, double timestep) {
     CTX_OR_FAIL(ctx);
-    if (integrator < LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET || integrator > LUMOL_CUDA_INTEGRATOR_LEAP_FROG) {
+    if (integrator < LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET || integrator > LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown integrator %d", integrator);
     }
     c->integrator = integrator;
     c->dt = timestep;
+    for (int k = 0; k < 9; k++) c->barostat_eta[k] = (k % 4 == 0) ? 1.0 : 0.0;  // eta starts at one (integrators.rs:196, 276)
     int status = md_setup(c);
     if (status) return status;
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -912,10 +913,145 @@ extern "C" int32_t lumol_cuda_md_set_csvr_noise(lumol_cuda_context* ctx, int64_t
 
 extern "C" int32_t lumol_cuda_md_set_controls(lumol_cuda_context* ctx, uint32_t controls) {
     CTX_OR_FAIL(ctx);
-    if (controls & ~1u) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown control bits");
+    if (controls & ~7u) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown control bits");
     c->controls = controls;
     return LUMOL_CUDA_SUCCESS;
 }
+
+extern "C" int32_t lumol_cuda_md_set_barostat(lumol_cuda_context* ctx, const double target[9], double tau) {
+    CTX_OR_FAIL(ctx);
+    if (target == nullptr || !(tau > 0.0)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_md_set_barostat: bad arguments");
+    for (int k = 0; k < 9; k++) c->barostat_target[k] = target[k];
+    c->barostat_tau = tau;
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_get_cell(lumol_cuda_context* ctx, double cell[9]) {
+    CTX_OR_FAIL(ctx);
+    if (cell == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
+    for (int k = 0; k < 9; k++) cell[k] = c->cell.h[k];
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_remove_rotation(lumol_cuda_context* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (c->n == 0) return LUMOL_CUDA_SUCCESS;
+    int status = launch_remove_rotation(c);
+    if (status) return status;
+    LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_rewrap(lumol_cuda_context* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (c->n == 0) return LUMOL_CUDA_SUCCESS;
+    int status = launch_rewrap(c);
+    if (status) return status;
+    LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LUMOL_CUDA_SUCCESS;
+}
+
+namespace lumol {
+
+// UnitCell::lengths (cells.rs:134-146): distances between opposite faces
+static void cell_lengths(const CellView& cell, double out[3]) {
+    const double a[3] = {cell.h[0], cell.h[3], cell.h[6]}, b[3] = {cell.h[1], cell.h[4], cell.h[7]}, cc[3] = {cell.h[2], cell.h[5], cell.h[8]};
+    auto cross = [](const double* u, const double* v, double* w) {
+        w[0] = u[1] * v[2] - u[2] * v[1];
+        w[1] = u[2] * v[0] - u[0] * v[2];
+        w[2] = u[0] * v[1] - u[1] * v[0];
+    };
+    auto project = [](const double* normal, const double* v) {
+        const double norm = std::sqrt(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
+        return std::fabs((normal[0] / norm) * v[0] + (normal[1] / norm) * v[1] + (normal[2] / norm) * v[2]);
+    };
+    double na[3], nb[3], nc[3];
+    cross(b, cc, na);
+    cross(cc, a, nb);
+    cross(a, b, nc);
+    out[0] = project(na, a);
+    out[1] = project(nb, b);
+    out[2] = project(nc, cc);
+}
+
+// One step of BerendsenBarostat::integrate / AnisoBerendsenBarostat::integrate (integrators.rs:211-255, 295-341).
+// Positions, velocities and forces stay on the device; the host sees the virial and the kinetic sums.
+int barostat_step(Context* c) {
+    lumol_cuda_context* handle = reinterpret_cast<lumol_cuda_context*>(c);
+    const bool isotropic = c->integrator == LUMOL_CUDA_INTEGRATOR_BERENDSEN_BAROSTAT;
+    if (c->nranks > 1) return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the barostats are not available in sharded runs");
+    if (c->cell.shape == LUMOL_CUDA_CELL_INFINITE) return c->fail(LUMOL_CUDA_ERROR_INFINITE_CELL, "can not scale infinite cells");  // cells.rs:204
+    if (!(c->barostat_tau > 0.0)) return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_set_barostat was not called");
+    double* eta = c->barostat_eta;
+    int status = launch_barostat_drift(c, eta, isotropic);
+    if (status) return status;
+    // system.cell.scale_mut(factor): self.cell *= factor (cells.rs:203-207)
+    double factor[9] = {0};
+    if (isotropic) {
+        factor[0] = factor[4] = factor[8] = eta[0] * eta[0] * eta[0] * 1.0;
+    } else {
+        for (int k = 0; k < 9; k++) factor[k] = eta[k];
+    }
+    double scaled[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            scaled[3 * i + j] = c->cell.h[3 * i] * factor[j] + c->cell.h[3 * i + 1] * factor[3 + j] + c->cell.h[3 * i + 2] * factor[6 + j];
+    // UnitCell::scale_mut multiplies the matrix and keeps the shape (cells.rs:203-207): an orthorhombic cell scaled by a
+    // matrix with off-diagonal terms still takes the orthorhombic branches (diagonal lengths) everywhere, as in lumol
+    const int shape = c->cell.shape;
+    status = lumol_cuda_set_cell(handle, scaled, shape);
+    if (status) return status;
+    double maximum_cutoff = -1.0;
+    if (c->any_pair) maximum_cutoff = c->max_pair_cutoff;
+    if (c->coulomb.kind != 0 && c->coulomb.rc > maximum_cutoff) maximum_cutoff = c->coulomb.rc;
+    if (maximum_cutoff > 0.0) {
+        double lengths[3];
+        cell_lengths(c->cell, lengths);
+        for (int d = 0; d < 3; d++) {
+            if (0.5 * lengths[d] <= maximum_cutoff) {
+                return c->fail(LUMOL_CUDA_ERROR_STATE,
+                               "Tried to decrease the cell size in %sBerendesen barostat but the new size is smaller than the "
+                               "interactions cut off radius. You can try to increase the cell size or the number of particles.",
+                               isotropic ? "" : "anisotropic ");
+            }
+        }
+    }
+    // system.pressure() / system.stress() and system.forces() at the new positions: one device pass
+    double virial[9];
+    status = lumol_cuda_compute(handle, LUMOL_CUDA_FORCES | LUMOL_CUDA_ATOMIC_VIRIAL, LUMOL_CUDA_PART_PAIRS | LUMOL_CUDA_PART_BONDED | LUMOL_CUDA_PART_COULOMB,
+                                nullptr, nullptr, virial);
+    if (status) return status;
+    const double volume = volume_of(c->cell);
+    if (isotropic) {
+        double kinetic = 0.0;
+        status = lumol_cuda_kinetic_energy(handle, &kinetic);
+        if (status) return status;
+        // compute.rs:134-171, 393-413: T = 2 K / (dof kB); P = (dof kB T + tr W) / (3 V)
+        const double dof = c->dof_mode == LUMOL_CUDA_DOF_MOLECULES ? 3.0 * (double)c->nmol : (double)(3 * c->n - c->dof_frozen);
+        const double temperature = 1.0 / (dof * K_BOLTZMANN) * 2.0 * kinetic;
+        const double pressure = (dof * K_BOLTZMANN * temperature + (virial[0] + virial[4] + virial[8])) / (3.0 * volume);
+        const double eta3 = 1.0 - 7372.0 / c->barostat_tau * (c->barostat_target[0] - pressure);
+        eta[0] = eta[4] = eta[8] = std::cbrt(eta3);
+    } else {
+        double kinetic[9];
+        status = lumol_cuda_kinetic_tensor(handle, kinetic);
+        if (status) return status;
+        const double scale = c->dt * 7372.0 / c->barostat_tau;
+        for (int k = 0; k < 9; k++) {
+            const double stress = (kinetic[k] + virial[k]) / volume;  // compute.rs:452-480
+            eta[k] = ((k % 4 == 0) ? 1.0 : 0.0) - scale * (c->barostat_target[k] - stress);
+        }
+        for (int i = 0; i < 3; i++) {
+            for (int j = 0; j < i; j++) {
+                eta[3 * i + j] = 0.5 * (eta[3 * i + j] + eta[3 * j + i]);
+                eta[3 * j + i] = eta[3 * i + j];
+            }
+        }
+    }
+    return launch_second_kick(c);
+}
+
+}  // namespace lumol
 
 extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
     CTX_OR_FAIL(ctx);

@@ -71,7 +71,9 @@ enum ResultSlot {
     RES_W_KSPACE_CORRECTION = 60,  // 9: sum_mol sum_i f_i (x) (x_i - com), ewald.rs:736-753
     RES_SCALE_FACTOR = 69,         // thermostat factor computed on the device
     RES_FLAGS = 70,
-    RES_COUNT = 72
+    RES_CENTER = 72,      // sum m x (3) and sum m (1): RemoveRotation
+    RES_ROTATION = 76,    // angular momentum (3), -sum m d (x) d (6: xx xy xz yy yz zz)
+    RES_COUNT = 88
 };
 
 struct Timer {
@@ -203,6 +205,8 @@ struct Context {
     DeviceBuffer<double> csvr_noise_dev;
     int64_t csvr_cursor = 0, csvr_count = 0;
     unsigned controls = 0;
+    // Berendsen barostats (integrators.rs:176-342): target pressure / stress, time scale, current scaling matrix
+    double barostat_target[9] = {0}, barostat_tau = 0.0, barostat_eta[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     int dof_mode = 0;
     int64_t dof_frozen = 0;
     int64_t md_step = 0;
@@ -290,8 +294,13 @@ int ewald_prepare(Context* ctx);                                                
 int launch_ewald_kspace(Context* ctx, const ComputeRequest& req);                                // ewald.cu
 int launch_kinetic(Context* ctx, bool tensor);                                                   // integrate.cu
 int md_setup(Context* ctx);                                                                      // integrate.cu
+int barostat_step(Context* ctx);                                                                // api.cu
 int md_step(Context* ctx, bool first, bool last);                                                                     // integrate.cu
 int launch_scale_velocities(Context* ctx, double factor, bool from_device);                      // integrate.cu
+int launch_remove_rotation(Context* ctx);                                                        // integrate.cu
+int launch_rewrap(Context* ctx);                                                                 // integrate.cu
+int launch_barostat_drift(Context* ctx, const double eta[9], bool isotropic);                    // integrate.cu
+int launch_second_kick(Context* ctx);                                                            // integrate.cu
 int launch_remove_translation(Context* ctx);                                                     // integrate.cu
 int evaluate_forces_device(Context* ctx, const ComputeRequest& req);                             // api.cu
 int comm_peer_push_begin(Context* ctx, PeerPush* push);                                          // comm.cu

@@ -296,6 +296,210 @@ int launch_remove_translation(Context* ctx) {
     return 0;
 }
 
+// RemoveRotation (controls.rs:47-73): center of mass, then angular momentum L and inertia I about it, then
+// v -= (x - com) ^ (I^-1 L).  Two reductions and one element-wise pass, nothing leaves the device.
+constexpr int ROT_NV = 9;
+
+__global__ void __launch_bounds__(INT_THREADS)
+    center_kernel(int n, const double* __restrict__ position, const double* __restrict__ mass, double* __restrict__ partials) {
+    __shared__ double scratch[32 * 4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double m = mass[i];
+        acc[0] += m * position[3 * i];
+        acc[1] += m * position[3 * i + 1];
+        acc[2] += m * position[3 * i + 2];
+        acc[3] += m;
+    }
+    block_sum<4>(acc, scratch);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 4; k++) partials[(size_t)blockIdx.x * 4 + k] = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(INT_THREADS)
+    rotation_kernel(int n, const double* __restrict__ position, const double* __restrict__ velocity,
+                    const double* __restrict__ mass, const double* __restrict__ results, double* __restrict__ partials) {
+    __shared__ double scratch[32 * ROT_NV];
+    const double total = results[RES_CENTER + 3];
+    const double cx = results[RES_CENTER] / total, cy = results[RES_CENTER + 1] / total, cz = results[RES_CENTER + 2] / total;
+    double acc[ROT_NV];
+#pragma unroll
+    for (int k = 0; k < ROT_NV; k++) acc[k] = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double m = mass[i];
+        const double dx = position[3 * i] - cx, dy = position[3 * i + 1] - cy, dz = position[3 * i + 2] - cz;
+        const double vx = velocity[3 * i], vy = velocity[3 * i + 1], vz = velocity[3 * i + 2];
+        acc[0] += m * (dy * vz - dz * vy);
+        acc[1] += m * (dz * vx - dx * vz);
+        acc[2] += m * (dx * vy - dy * vx);
+        acc[3] += -m * (dx * dx);
+        acc[4] += -m * (dx * dy);
+        acc[5] += -m * (dx * dz);
+        acc[6] += -m * (dy * dy);
+        acc[7] += -m * (dy * dz);
+        acc[8] += -m * (dz * dz);
+    }
+    block_sum<ROT_NV>(acc, scratch);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < ROT_NV; k++) partials[(size_t)blockIdx.x * ROT_NV + k] = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(INT_THREADS)
+    remove_rotation_kernel(int n, const double* __restrict__ position, const double* __restrict__ results,
+                           double* __restrict__ velocity) {
+    const double total = results[RES_CENTER + 3];
+    const double cx = results[RES_CENTER] / total, cy = results[RES_CENTER + 1] / total, cz = results[RES_CENTER + 2] / total;
+    const double* r = results + RES_ROTATION;
+    // inertia += trace on the diagonal (controls.rs:62-65), then the adjugate inverse of matrix.rs:212-227
+    const double trace = r[3] + r[6] + r[8];
+    const double m00 = r[3] + trace, m01 = r[4], m02 = r[5], m11 = r[6] + trace, m12 = r[7], m22 = r[8] + trace;
+    const double det = m00 * (m11 * m22 - m12 * m12) - m01 * (m01 * m22 - m12 * m02) + m02 * (m01 * m12 - m11 * m02);
+    const double i00 = (m11 * m22 - m12 * m12) / det, i01 = (m02 * m12 - m01 * m22) / det, i02 = (m01 * m12 - m02 * m11) / det;
+    const double i11 = (m00 * m22 - m02 * m02) / det, i12 = (m01 * m02 - m00 * m12) / det, i22 = (m00 * m11 - m01 * m01) / det;
+    const double wx = i00 * r[0] + i01 * r[1] + i02 * r[2];
+    const double wy = i01 * r[0] + i11 * r[1] + i12 * r[2];
+    const double wz = i02 * r[0] + i12 * r[1] + i22 * r[2];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double dx = position[3 * i] - cx, dy = position[3 * i + 1] - cy, dz = position[3 * i + 2] - cz;
+        velocity[3 * i] -= dy * wz - dz * wy;
+        velocity[3 * i + 1] -= dz * wx - dx * wz;
+        velocity[3 * i + 2] -= dx * wy - dy * wx;
+    }
+}
+
+int launch_remove_rotation(Context* ctx) {
+    if (ctx->nranks > 1) return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "RemoveRotation is not available in sharded runs");
+    const int n = (int)ctx->n;
+    int blocks = grid_for(n, ctx->sm_count);
+    if (blocks > 1024) blocks = 1024;
+    LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)blocks * ROT_NV));
+    ScopedClock clock(ctx, &ctx->clk_integrate);
+    center_kernel<<<blocks, INT_THREADS, 0, ctx->stream>>>(n, ctx->position.ptr, ctx->mass.ptr, ctx->partials.ptr);
+    int status = launch_reduce(ctx, blocks, 4, RES_CENTER);
+    if (status != 0) return status;
+    rotation_kernel<<<blocks, INT_THREADS, 0, ctx->stream>>>(n, ctx->position.ptr, ctx->velocity.ptr, ctx->mass.ptr,
+                                                            ctx->results.ptr, ctx->partials.ptr);
+    status = launch_reduce(ctx, blocks, ROT_NV, RES_ROTATION);
+    if (status != 0) return status;
+    remove_rotation_kernel<<<blocks, INT_THREADS, 0, ctx->stream>>>(n, ctx->position.ptr, ctx->results.ptr, ctx->velocity.ptr);
+    ctx->launches += 3;
+    ctx->clk_integrate.launches += 3;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Rewrap (controls.rs:80-87): every molecule is translated so that its center of mass lies in the cell
+// (Molecule::wrap, molecules.rs:287-296; UnitCell::wrap_vector, cells.rs:263-279).  One thread per molecule.
+__global__ void __launch_bounds__(INT_THREADS)
+    rewrap_kernel(int nmol, const int* __restrict__ mol_start, CellView cell, const double* __restrict__ mass,
+                  double* __restrict__ position) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmol || cell.shape == LUMOL_CUDA_CELL_INFINITE) return;
+    const int lo = mol_start[m], hi = mol_start[m + 1];
+    double total = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    // no FMA contraction: a center of mass that sits on a cell face must fall on the same side as in the reference
+    for (int i = lo; i < hi; i++) {
+        total = __dadd_rn(total, mass[i]);
+        cx = __dadd_rn(cx, __dmul_rn(mass[i], position[3 * i]));
+        cy = __dadd_rn(cy, __dmul_rn(mass[i], position[3 * i + 1]));
+        cz = __dadd_rn(cz, __dmul_rn(mass[i], position[3 * i + 2]));
+    }
+    cx = __ddiv_rn(cx, total);
+    cy = __ddiv_rn(cy, total);
+    cz = __ddiv_rn(cz, total);
+    double wx = cx, wy = cy, wz = cz;
+    if (cell.shape == LUMOL_CUDA_CELL_ORTHORHOMBIC) {
+        wx = __dadd_rn(wx, -__dmul_rn(floor(__ddiv_rn(wx, cell.h[0])), cell.h[0]));
+        wy = __dadd_rn(wy, -__dmul_rn(floor(__ddiv_rn(wy, cell.h[4])), cell.h[4]));
+        wz = __dadd_rn(wz, -__dmul_rn(floor(__ddiv_rn(wz, cell.h[8])), cell.h[8]));
+    } else {
+        double fx = cell.inv[0] * wx + cell.inv[1] * wy + cell.inv[2] * wz;
+        double fy = cell.inv[3] * wx + cell.inv[4] * wy + cell.inv[5] * wz;
+        double fz = cell.inv[6] * wx + cell.inv[7] * wy + cell.inv[8] * wz;
+        fx -= floor(fx);
+        fy -= floor(fy);
+        fz -= floor(fz);
+        wx = cell.h[0] * fx + cell.h[1] * fy + cell.h[2] * fz;
+        wy = cell.h[3] * fx + cell.h[4] * fy + cell.h[5] * fz;
+        wz = cell.h[6] * fx + cell.h[7] * fy + cell.h[8] * fz;
+    }
+    const double dx = wx - cx, dy = wy - cy, dz = wz - cz;
+    for (int i = lo; i < hi; i++) {
+        position[3 * i] += dx;
+        position[3 * i + 1] += dy;
+        position[3 * i + 2] += dz;
+    }
+}
+
+int launch_rewrap(Context* ctx) {
+    if (ctx->nranks > 1) return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "Rewrap is not available in sharded runs");
+    if (ctx->nmol == 0) return 0;  // without lumol_cuda_set_molecules every atom is its own molecule (nmol == n)
+    ScopedClock clock(ctx, &ctx->clk_integrate);
+    const int nmol = (int)ctx->nmol;
+    rewrap_kernel<<<(nmol + INT_THREADS - 1) / INT_THREADS, INT_THREADS, 0, ctx->stream>>>(nmol, ctx->mol_start.ptr, ctx->cell, ctx->mass.ptr,
+                                                                                          ctx->position.ptr);
+    ctx->launches++;
+    ctx->clk_integrate.launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// First half of the Berendsen barostat steps (integrators.rs:215-223, 299-307): v += (0.5 dt) a; x = eta x; x += v dt.
+__global__ void __launch_bounds__(INT_THREADS)
+    barostat_drift_kernel(int n, double half_dt, double dt, const double* __restrict__ force, const double* __restrict__ mass,
+                          double* __restrict__ velocity, double* __restrict__ position, const double e00, const double e01,
+                          const double e02, const double e10, const double e11, const double e12, const double e20, const double e21,
+                          const double e22, int isotropic) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double m = mass[i];
+        double v[3], x[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            v[c] = __dadd_rn(velocity[3 * i + c], __dmul_rn(half_dt, __ddiv_rn(force[3 * i + c], m)));
+            x[c] = position[3 * i + c];
+            velocity[3 * i + c] = v[c];
+        }
+        double s[3];
+        if (isotropic) {
+            s[0] = __dmul_rn(x[0], e00);
+            s[1] = __dmul_rn(x[1], e00);
+            s[2] = __dmul_rn(x[2], e00);
+        } else {
+            s[0] = __dadd_rn(__dadd_rn(__dmul_rn(e00, x[0]), __dmul_rn(e01, x[1])), __dmul_rn(e02, x[2]));
+            s[1] = __dadd_rn(__dadd_rn(__dmul_rn(e10, x[0]), __dmul_rn(e11, x[1])), __dmul_rn(e12, x[2]));
+            s[2] = __dadd_rn(__dadd_rn(__dmul_rn(e20, x[0]), __dmul_rn(e21, x[1])), __dmul_rn(e22, x[2]));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) position[3 * i + c] = __dadd_rn(s[c], __dmul_rn(v[c], dt));
+    }
+}
+
+int launch_barostat_drift(Context* ctx, const double eta[9], bool isotropic) {
+    const int n = (int)ctx->n;
+    ScopedClock clock(ctx, &ctx->clk_integrate);
+    barostat_drift_kernel<<<grid_for(n, ctx->sm_count), INT_THREADS, 0, ctx->stream>>>(
+        n, 0.5 * ctx->dt, ctx->dt, ctx->force.ptr, ctx->mass.ptr, ctx->velocity.ptr, ctx->position.ptr, eta[0], eta[1], eta[2], eta[3],
+        eta[4], eta[5], eta[6], eta[7], eta[8], isotropic ? 1 : 0);
+    ctx->launches++;
+    ctx->clk_integrate.launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int launch_second_kick(Context* ctx) {
+    int64_t lo, hi;
+    ctx->owned_range(ctx->n, lo, hi);
+    ScopedClock clock(ctx, &ctx->clk_integrate);
+    vv_kick_kernel<<<grid_for(3 * (hi - lo), ctx->sm_count), INT_THREADS, 0, ctx->stream>>>(3 * lo, 3 * hi, 0.5 * ctx->dt, ctx->force.ptr,
+                                                                                         ctx->mass.ptr, ctx->velocity.ptr);
+    ctx->launches++;
+    ctx->clk_integrate.launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // MD driver
 // ------------------------------------------------------------------------------------------------
@@ -303,7 +507,8 @@ int launch_remove_translation(Context* ctx) {
 int md_setup(Context* ctx) {
     const int64_t n3 = 3 * ctx->n;
     LUMOL_CUDA_CHECK(ctx, ctx->force.reserve((size_t)n3));
-    if (ctx->integrator == LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET) {
+    if (ctx->integrator == LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET || ctx->integrator == LUMOL_CUDA_INTEGRATOR_BERENDSEN_BAROSTAT ||
+        ctx->integrator == LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT) {
         // VelocityVerlet::setup zeroes the accelerations (integrators.rs:40-42): the first half kick
         // of the first step is a no-op whatever the forces are.
         LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->force.ptr, 0, (size_t)n3 * sizeof(double), ctx->stream));
@@ -398,6 +603,9 @@ int md_step(Context* ctx, bool first, bool last) {
             ctx->clk_integrate.launches++;
             LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
         }
+    } else if (ctx->integrator == LUMOL_CUDA_INTEGRATOR_BERENDSEN_BAROSTAT ||
+               ctx->integrator == LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT) {
+        if ((status = barostat_step(ctx)) != 0) return status;
     } else {
         return ctx->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_setup was not called");
     }
@@ -427,6 +635,12 @@ int md_step(Context* ctx, bool first, bool last) {
     // controls (molecular_dynamics.rs:72-74)
     if (ctx->controls & LUMOL_CUDA_CONTROL_REMOVE_TRANSLATION) {
         if ((status = launch_remove_translation(ctx)) != 0) return status;
+    }
+    if (ctx->controls & LUMOL_CUDA_CONTROL_REMOVE_ROTATION) {
+        if ((status = launch_remove_rotation(ctx)) != 0) return status;
+    }
+    if (ctx->controls & LUMOL_CUDA_CONTROL_REWRAP) {
+        if ((status = launch_rewrap(ctx)) != 0) return status;
     }
     ctx->md_step++;
     return 0;

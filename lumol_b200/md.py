@@ -43,6 +43,35 @@ class LeapFrog(Integrator):
     KIND = _ffi.INTEGRATOR_LEAP_FROG
 
 
+class BerendsenBarostat(Integrator):
+    """integrators.rs:176-255: velocity-Verlet with isotropic Berendsen scaling of positions and cell.  ``tau`` is the
+    barostat time scale in units of the timestep."""
+
+    KIND = _ffi.INTEGRATOR_BERENDSEN_BAROSTAT
+
+    def __init__(self, timestep, pressure, tau):
+        super().__init__(timestep)
+        self.tau = float(tau)
+        self.target = np.zeros((3, 3))
+        self.target[0, 0] = float(pressure)
+
+
+class AnisoBerendsenBarostat(Integrator):
+    """integrators.rs:260-341: the same with a target stress matrix and a scaling matrix."""
+
+    KIND = _ffi.INTEGRATOR_ANISO_BERENDSEN_BAROSTAT
+
+    def __init__(self, timestep, stress, tau):
+        super().__init__(timestep)
+        self.tau = float(tau)
+        self.target = np.ascontiguousarray(np.array(stress, dtype=np.float64).reshape(3, 3))
+
+    @classmethod
+    def hydrostatic(cls, timestep, pressure, tau):
+        """integrators.rs:288-290"""
+        return cls(timestep, float(pressure) * np.eye(3), tau)
+
+
 class Thermostat:
     """``Thermostat`` trait (thermostats.rs:13-24)."""
 
@@ -130,6 +159,28 @@ class RemoveTranslation(Control):
         device.download(system, positions=False)
 
 
+class RemoveRotation(Control):
+    """controls.rs:44-73"""
+
+    FLAG = _ffi.CONTROL_REMOVE_ROTATION
+
+    def control(self, system):
+        device = device_for(system, velocities=True)
+        _ffi.check(device.ctx, device.lib.lumol_cuda_remove_rotation(device.ctx))
+        device.download(system, positions=False)
+
+
+class Rewrap(Control):
+    """controls.rs:76-87"""
+
+    FLAG = _ffi.CONTROL_REWRAP
+
+    def control(self, system):
+        device = device_for(system, velocities=True)
+        _ffi.check(device.ctx, device.lib.lumol_cuda_rewrap(device.ctx))
+        device.download(system, velocities=False)
+
+
 def scale(system, temperature):
     """``velocities::scale`` (velocities.rs:16-22)."""
     instant = system.temperature()
@@ -166,6 +217,9 @@ class MolecularDynamics:
         device = device_for(system, velocities=True)
         lib, ctx = device.lib, device.ctx
         _ffi.check(ctx, lib.lumol_cuda_md_setup(ctx, self.integrator.KIND, self.integrator.timestep))
+        if isinstance(self.integrator, (BerendsenBarostat, AnisoBerendsenBarostat)):
+            target = np.ascontiguousarray(self.integrator.target, dtype=np.float64)
+            _ffi.check(ctx, lib.lumol_cuda_md_set_barostat(ctx, _ffi.as_double_pointer(target), self.integrator.tau))
         thermostat = self.thermostat if self.thermostat is not None else Thermostat()
         _ffi.check(ctx, lib.lumol_cuda_md_set_thermostat(ctx, thermostat.KIND, thermostat.temperature, thermostat.parameter))
         flags = 0
@@ -187,6 +241,12 @@ class MolecularDynamics:
             _ffi.check(ctx, lib.lumol_cuda_md_set_csvr_noise(ctx, nsteps, _ffi.as_double_pointer(noise)))
         _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, nsteps))
         system.step += nsteps
+        if isinstance(self.integrator, (BerendsenBarostat, AnisoBerendsenBarostat)):
+            # the barostat scaled the cell on the device: bring it back (system.cell.scale_mut, integrators.rs:225, 309)
+            matrix = np.zeros((3, 3))
+            _ffi.check(ctx, lib.lumol_cuda_get_cell(ctx, _ffi.as_double_pointer(matrix)))
+            system.cell = type(system.cell)(matrix, system.cell.shape())  # scale_mut keeps the shape (cells.rs:203-207)
+            device._synced_cell = (system.cell.shape(), system.cell.matrix().tobytes())
         if download:
             device.download(system)
             # the host arrays now equal the device state: keep the device copy authoritative
@@ -212,5 +272,5 @@ def forces_to_host(device, n):
 
 __all__ = [
     "VelocityVerlet", "Verlet", "LeapFrog", "RescaleThermostat", "BerendsenThermostat", "CSVRThermostat",
-    "RemoveTranslation", "MolecularDynamics", "Simulation", "scale", "K_BOLTZMANN",
+    "RemoveTranslation", "RemoveRotation", "Rewrap", "BerendsenBarostat", "AnisoBerendsenBarostat", "MolecularDynamics", "Simulation", "scale", "K_BOLTZMANN",
 ]

@@ -2188,3 +2188,155 @@ void orc_remove_translation(int64_t n, const double* mass, double* velocity) {
         }
     }
 }
+
+/* ---- barostats and the remaining controls -------------------------------------------------------- */
+
+static const double ORC_WATER_COMPRESSIBILITY = 7372.0; /* integrators.rs:172 */
+
+static void mat3_mul(const double a[9], const double b[9], double out[9]) {
+    double r[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+    memcpy(out, r, sizeof(r));
+}
+
+/* Second half of both barostat steps: forces, accelerations, half kick (integrators.rs:246-254, 332-340). */
+static void barostat_finish(orc_system* s, double* velocity, double* accelerations, double dt) {
+    int64_t n = s->n;
+    double* forces = (double*)malloc((size_t)(3 * n > 0 ? 3 * n : 1) * sizeof(double));
+    orc_forces(s, forces);
+    for (int64_t i = 0; i < n; i++) {
+        for (int c = 0; c < 3; c++) {
+            accelerations[3 * i + c] = forces[3 * i + c] / s->mass[i];
+        }
+    }
+    for (int64_t k = 0; k < 3 * n; k++) {
+        velocity[k] += 0.5 * dt * accelerations[k];
+    }
+    free(forces);
+}
+
+/* BerendsenBarostat::integrate (integrators.rs:211-255).  Returns 1 when the reference would panic because the
+ * scaled cell is smaller than twice `maximum_cutoff` (pass 0 when the system has no cut-off). */
+int orc_berendsen_barostat_step(orc_system* s, double* position, double* velocity, double* accelerations, double dt,
+                                double pressure, double tau, double* eta, double maximum_cutoff) {
+    int64_t n = s->n;
+    for (int64_t k = 0; k < 3 * n; k++) {
+        velocity[k] += 0.5 * dt * accelerations[k];
+        position[k] *= *eta;
+        position[k] += velocity[k] * dt;
+    }
+    s->position = position;
+    s->velocity = velocity;
+    /* cell.scale_mut(eta * eta * eta * Matrix3::one()): self.cell *= factor (cells.rs:203-207) */
+    double factor[9] = {0};
+    factor[0] = factor[4] = factor[8] = (*eta) * (*eta) * (*eta) * 1.0;
+    mat3_mul(s->cell, factor, s->cell);
+    if (maximum_cutoff > 0.0) {
+        double lengths[3];
+        orc_cell_lengths(s->cell, s->shape, lengths);
+        for (int c = 0; c < 3; c++) {
+            if (0.5 * lengths[c] <= maximum_cutoff) return 1;
+        }
+    }
+    double eta3 = 1.0 - ORC_WATER_COMPRESSIBILITY / tau * (pressure - orc_pressure(s));
+    *eta = cbrt(eta3);
+    barostat_finish(s, velocity, accelerations, dt);
+    return 0;
+}
+
+/* AnisoBerendsenBarostat::integrate (integrators.rs:295-341); eta and stress are row-major Matrix3. */
+int orc_aniso_berendsen_barostat_step(orc_system* s, double* position, double* velocity, double* accelerations, double dt,
+                                      const double stress[9], double tau, double eta[9], double maximum_cutoff) {
+    int64_t n = s->n;
+    for (int64_t i = 0; i < n; i++) {
+        double* x = position + 3 * i;
+        double* v = velocity + 3 * i;
+        for (int c = 0; c < 3; c++) v[c] += 0.5 * dt * accelerations[3 * i + c];
+        double scaled[3];
+        for (int c = 0; c < 3; c++) scaled[c] = eta[3 * c] * x[0] + eta[3 * c + 1] * x[1] + eta[3 * c + 2] * x[2];
+        for (int c = 0; c < 3; c++) x[c] = scaled[c] + v[c] * dt;
+    }
+    s->position = position;
+    s->velocity = velocity;
+    mat3_mul(s->cell, eta, s->cell); /* cell.scale_mut(eta) */
+    if (maximum_cutoff > 0.0) {
+        double lengths[3];
+        orc_cell_lengths(s->cell, s->shape, lengths);
+        for (int c = 0; c < 3; c++) {
+            if (0.5 * lengths[c] <= maximum_cutoff) return 1;
+        }
+    }
+    double factor = dt * ORC_WATER_COMPRESSIBILITY / tau;
+    double current[9];
+    orc_stress(s, current);
+    for (int k = 0; k < 9; k++) {
+        double one = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0;
+        eta[k] = one - factor * (stress[k] - current[k]);
+    }
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < i; j++) {
+            eta[3 * i + j] = 0.5 * (eta[3 * i + j] + eta[3 * j + i]);
+            eta[3 * j + i] = eta[3 * i + j];
+        }
+    }
+    barostat_finish(s, velocity, accelerations, dt);
+    return 0;
+}
+
+/* RemoveRotation::control (controls.rs:47-73) */
+void orc_remove_rotation(int64_t n, const double* mass, const double* position, double* velocity) {
+    double total_mass = 0.0, com[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = 0; i < n; i++) {
+        total_mass += mass[i];
+        for (int c = 0; c < 3; c++) com[c] += mass[i] * position[3 * i + c];
+    }
+    for (int c = 0; c < 3; c++) com[c] /= total_mass;
+    double moment[3] = {0.0, 0.0, 0.0}, inertia[9] = {0};
+    for (int64_t i = 0; i < n; i++) {
+        double d[3], v[3];
+        for (int c = 0; c < 3; c++) {
+            d[c] = position[3 * i + c] - com[c];
+            v[c] = velocity[3 * i + c];
+        }
+        const double cross[3] = {d[1] * v[2] - d[2] * v[1], d[2] * v[0] - d[0] * v[2], d[0] * v[1] - d[1] * v[0]};
+        for (int c = 0; c < 3; c++) moment[c] += mass[i] * cross[c];
+        for (int p = 0; p < 3; p++)
+            for (int q = 0; q < 3; q++) inertia[3 * p + q] += -mass[i] * (d[p] * d[q]);
+    }
+    double trace = inertia[0] + inertia[4] + inertia[8];
+    inertia[0] += trace;
+    inertia[4] += trace;
+    inertia[8] += trace;
+    double inverse[9];
+    orc_matrix_inverse(inertia, inverse);
+    double angular[3];
+    for (int c = 0; c < 3; c++) angular[c] = inverse[3 * c] * moment[0] + inverse[3 * c + 1] * moment[1] + inverse[3 * c + 2] * moment[2];
+    for (int64_t i = 0; i < n; i++) {
+        double d[3];
+        for (int c = 0; c < 3; c++) d[c] = position[3 * i + c] - com[c];
+        velocity[3 * i] -= d[1] * angular[2] - d[2] * angular[1];
+        velocity[3 * i + 1] -= d[2] * angular[0] - d[0] * angular[2];
+        velocity[3 * i + 2] -= d[0] * angular[1] - d[1] * angular[0];
+    }
+}
+
+/* Rewrap::control (controls.rs:80-87) with Molecule::wrap (molecules.rs:287-296) */
+void orc_rewrap(const orc_system* s, double* position) {
+    for (int64_t m = 0; m < s->nmol; m++) {
+        double total_mass = 0.0, com[3] = {0.0, 0.0, 0.0};
+        for (int64_t i = s->mol_start[m]; i < s->mol_start[m + 1]; i++) {
+            total_mass += s->mass[i];
+            for (int c = 0; c < 3; c++) com[c] += s->mass[i] * position[3 * i + c];
+        }
+        double wrapped[3];
+        for (int c = 0; c < 3; c++) {
+            com[c] /= total_mass;
+            wrapped[c] = com[c];
+        }
+        orc_wrap_vector(s->cell, s->shape, wrapped);
+        for (int64_t i = s->mol_start[m]; i < s->mol_start[m + 1]; i++) {
+            for (int c = 0; c < 3; c++) position[3 * i + c] += wrapped[c] - com[c];
+        }
+    }
+}

@@ -241,6 +241,14 @@ void orc_scale_velocities(int64_t n, double* velocity, double factor);
 double orc_berendsen_thermostat_factor(double temperature, double instant, double tau);
 double orc_rescale_thermostat_factor(double temperature, double instant);
 void orc_remove_translation(int64_t n, const double* mass, double* velocity);
+/* controls.rs:47-87 */
+void orc_remove_rotation(int64_t n, const double* mass, const double* position, double* velocity);
+void orc_rewrap(const orc_system* s, double* position);
+/* integrators.rs:211-255, 295-341: one step; return 1 where the reference panics (cell smaller than the cut-off) */
+int orc_berendsen_barostat_step(orc_system* s, double* position, double* velocity, double* accelerations, double dt,
+                                double pressure, double tau, double* eta, double maximum_cutoff);
+int orc_aniso_berendsen_barostat_step(orc_system* s, double* position, double* velocity, double* accelerations, double dt,
+                                      const double stress[9], double tau, double eta[9], double maximum_cutoff);
 
 #ifdef __cplusplus
 }

@@ -173,6 +173,10 @@ def library():
             "orc_berendsen_thermostat_factor": (d, [d, d, d]),
             "orc_rescale_thermostat_factor": (d, [d, d]),
             "orc_remove_translation": (None, [ctypes.c_int64, _dp, _dp]),
+            "orc_remove_rotation": (None, [ctypes.c_int64, _dp, _dp, _dp]),
+            "orc_rewrap": (None, [sp, _dp]),
+            "orc_berendsen_barostat_step": (ctypes.c_int, [sp, _dp, _dp, _dp, d, d, d, _dp, d]),
+            "orc_aniso_berendsen_barostat_step": (ctypes.c_int, [sp, _dp, _dp, _dp, d, _dp, d, _dp, d]),
         }
         for name, (restype, argtypes) in signatures.items():
             function = getattr(lib, name)

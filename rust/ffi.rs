@@ -96,6 +96,10 @@ extern "C" {
     pub fn lumol_cuda_md_run(ctx: *mut lumol_cuda_context, nsteps: i64) -> i32;
     pub fn lumol_cuda_scale_velocities(ctx: *mut lumol_cuda_context, factor: f64) -> i32;
     pub fn lumol_cuda_remove_translation(ctx: *mut lumol_cuda_context) -> i32;
+    pub fn lumol_cuda_remove_rotation(ctx: *mut lumol_cuda_context) -> i32;
+    pub fn lumol_cuda_rewrap(ctx: *mut lumol_cuda_context) -> i32;
+    pub fn lumol_cuda_md_set_barostat(ctx: *mut lumol_cuda_context, target: *const f64, tau: f64) -> i32;
+    pub fn lumol_cuda_get_cell(ctx: *mut lumol_cuda_context, cell: *mut f64) -> i32;
     pub fn lumol_cuda_comm_unique_id(id: *mut u8) -> i32;
     pub fn lumol_cuda_comm_init(ctx: *mut lumol_cuda_context, nranks: i32, rank: i32, id: *const u8) -> i32;
     pub fn lumol_cuda_set_neighbor_skin(ctx: *mut lumol_cuda_context, skin: f64) -> i32;

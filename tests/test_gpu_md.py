@@ -5,6 +5,8 @@ energy conservation / thermostat targets; the same criteria are applied to the C
 step-by-step comparison with the oracle restating lumol-sim/src/md/integrators.rs.
 """
 
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -208,3 +210,106 @@ def test_large_box_properties():
         assert np.abs(forces[i] - expected).max() < 1e-10 * np.abs(forces).max()
     systems.random_velocities(system, 120.0, seed=2)
     assert relative_drift(system, md.MolecularDynamics(1.0), 100, chunks=2) < 5e-4
+
+
+# ---- barostats and the remaining controls ------------------------------------------------------------------------------
+
+def oracle_barostat_trajectory(system, nsteps, dt, tau, pressure=None, stress=None):
+    orc = oracle.OracleSystem(system)
+    n = system.size()
+    acc = np.zeros((n, 3))
+    if stress is None:
+        eta = ctypes.c_double(1.0)
+        for _ in range(nsteps):
+            assert orc.lib.orc_berendsen_barostat_step(orc.ref, oracle.dptr(orc.position), oracle.dptr(orc.velocity), oracle.dptr(acc), dt,
+                                                       pressure, tau, ctypes.byref(eta), 0.0) == 0
+    else:
+        eta = np.eye(3).reshape(-1).copy()
+        target = np.ascontiguousarray(np.array(stress, dtype=np.float64).reshape(-1))
+        for _ in range(nsteps):
+            assert orc.lib.orc_aniso_berendsen_barostat_step(orc.ref, oracle.dptr(orc.position), oracle.dptr(orc.velocity), oracle.dptr(acc),
+                                                             dt, oracle.dptr(target), tau, oracle.dptr(eta), 0.0) == 0
+    return orc.position.copy(), orc.velocity.copy(), np.array(orc.s.cell[:]).reshape(3, 3)
+
+
+@pytest.mark.parametrize("builder", ["helium", "nacl"])
+def test_berendsen_barostats_follow_the_oracle(builder):
+    """BerendsenBarostat and AnisoBerendsenBarostat (integrators.rs:176-342): ten device steps against the oracle's
+    restatement, positions, velocities and the scaled cell."""
+    build = {"helium": systems.md_helium, "nacl": lambda: systems.md_nacl("wolf")}[builder]
+    pressure = lumol.units.from_(500.0, "bar")
+    for kind in ("isotropic", "anisotropic"):
+        system = build()
+        systems.random_velocities(system, 300.0, seed=5)
+        reference = build()
+        reference.velocities = system.velocities.copy()
+        if kind == "isotropic":
+            integrator = md.BerendsenBarostat(1.0, pressure, 100.0)
+            x, v, cell = oracle_barostat_trajectory(reference, 10, 1.0, 100.0, pressure=pressure)
+        else:
+            stress = pressure * np.eye(3)
+            stress[0, 1] = stress[1, 0] = 0.1 * pressure
+            integrator = md.AnisoBerendsenBarostat(1.0, stress, 100.0)
+            x, v, cell = oracle_barostat_trajectory(reference, 10, 1.0, 100.0, stress=stress)
+        md.MolecularDynamics(integrator).propagate(system, 10)
+        assert np.abs(system.positions - x).max() < 1e-9
+        assert np.abs(system.velocities - v).max() < 1e-10 * max(np.abs(v).max(), 1e-3)
+        assert np.abs(system.cell.matrix() - cell).max() < 1e-10 * np.abs(cell).max()
+        assert not np.allclose(cell, reference.cell.matrix(), rtol=1e-9, atol=0)  # the box did change
+
+
+def test_berendsen_barostat_reaches_the_target_pressure_and_refuses_small_cells():
+    # tests/md-helium.rs:96-111 (npt-berendsen-barostat.toml): pressure within 5e-2 relative after equilibration
+    system = systems.md_helium()
+    systems.random_velocities(system, 300.0, seed=3)
+    target = lumol.units.from_(5000.0, "bar")
+    propagator = md.MolecularDynamics(md.BerendsenBarostat(1.0, target, 1000.0))
+    propagator.set_thermostat(md.BerendsenThermostat(300.0, 100.0))
+    propagator.propagate(system, 3000)
+    pressures = []
+    for _ in range(20):
+        propagator.propagate(system, 50)
+        pressures.append(system.pressure())
+    assert abs(np.mean(pressures) - target) / target < 5e-2
+    # integrators.rs:227-236
+    small = systems.md_helium()
+    systems.random_velocities(small, 300.0, seed=3)
+    squeeze = md.MolecularDynamics(md.BerendsenBarostat(1.0, lumol.units.from_(1e7, "bar"), 10.0))
+    with pytest.raises(lumol.LumolCudaError, match="Tried to decrease the cell size in Berendesen barostat"):
+        squeeze.propagate(small, 2000)
+
+
+def test_remove_rotation_and_rewrap():
+    # controls.rs:108-131 on the device
+    system = lumol.System(lumol.UnitCell.cubic(10.0))
+    system.add_particles(["Ag", "Ag"], np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]), masses=np.array([107.8682, 107.8682]))
+    system.velocities = np.array([[0.0, 1.0, 0.0], [0.0, -1.0, 2.0]])
+    md.RemoveRotation().control(system)
+    np.testing.assert_allclose(system.velocities, [[0.0, 0.0, 1.0], [0.0, 0.0, 1.0]], rtol=0, atol=1e-15)
+    system.positions = np.array([[0.0, 0.0, 0.0], [15.0, 0.0, 0.0]])
+    md.Rewrap().control(system)
+    np.testing.assert_array_equal(system.positions, [[0.0, 0.0, 0.0], [5.0, 0.0, 0.0]])
+    # a molecular system against the oracle, then both controls inside the device loop
+    water = systems.md_water()
+    systems.random_velocities(water, 300.0, seed=6)
+    rng = np.random.Generator(np.random.PCG64(2))
+    water.positions += rng.integers(-2, 3, (water.size() // 3, 1, 3)).repeat(3, axis=1).reshape(-1, 3) * water.cell.a()
+    expected_v = water.velocities.copy()
+    oracle.library().orc_remove_rotation(water.size(), oracle.dptr(np.ascontiguousarray(water.masses)),
+                                         oracle.dptr(np.ascontiguousarray(water.positions)), oracle.dptr(expected_v))
+    reference = oracle.OracleSystem(water)
+    expected_x = water.positions.copy()
+    reference.lib.orc_rewrap(reference.ref, oracle.dptr(expected_x))
+    md.RemoveRotation().control(water)
+    np.testing.assert_allclose(water.velocities, expected_v, rtol=0, atol=1e-12 * np.abs(expected_v).max())
+    md.Rewrap().control(water)
+    np.testing.assert_allclose(water.positions, expected_x, rtol=0, atol=1e-12)
+    propagator = md.MolecularDynamics(1.0)
+    propagator.add_control(md.RemoveTranslation())
+    propagator.add_control(md.RemoveRotation())
+    propagator.add_control(md.Rewrap())
+    propagator.propagate(water, 5)
+    centers = water.positions.reshape(-1, 3, 3)
+    weights = water.masses.reshape(-1, 3, 1)
+    com = (centers * weights).sum(axis=1) / weights.sum(axis=1)
+    assert (com >= -1e-9).all() and (com < water.cell.a() + 1e-9).all()

@@ -546,3 +546,89 @@ def test_restriction_information():
             lib.orc_restriction_information(restriction, 0.8, path, ctypes.byref(excluded), ctypes.byref(scaling))
             assert excluded.value == expected
             assert scaling.value == (0.8 if restriction == 6 and path == 4 else 1.0)
+
+
+# ---- controls and barostats (lumol-sim/src/md/controls.rs, integrators.rs:176-342) ------------------------------------
+
+def two_silver_atoms(second):
+    system = lumol.System(lumol.UnitCell.cubic(10.0))
+    system.add_particles(["Ag", "Ag"], np.array([[0.0, 0.0, 0.0], second]), masses=np.array([107.8682, 107.8682]))
+    return system
+
+
+def test_remove_rotation_known_answer():
+    # controls.rs:108-120
+    system = two_silver_atoms([1.0, 0.0, 0.0])
+    velocity = np.array([[0.0, 1.0, 0.0], [0.0, -1.0, 2.0]])
+    oracle.library().orc_remove_rotation(2, oracle.dptr(np.ascontiguousarray(system.masses)), oracle.dptr(np.ascontiguousarray(system.positions)),
+                                         oracle.dptr(velocity))
+    np.testing.assert_array_equal(velocity, [[0.0, 0.0, 1.0], [0.0, 0.0, 1.0]])
+
+
+def test_rewrap_known_answers():
+    # controls.rs:122-131
+    system = two_silver_atoms([15.0, 0.0, 0.0])
+    reference = oracle.OracleSystem(system)
+    position = system.positions.copy()
+    reference.lib.orc_rewrap(reference.ref, oracle.dptr(position))
+    np.testing.assert_array_equal(position, [[0.0, 0.0, 0.0], [5.0, 0.0, 0.0]])
+    # molecules.rs:334-345: a two-atom molecule moves as a whole
+    molecule = lumol.System(lumol.UnitCell.cubic(5.0))
+    molecule.add_particles(["O", "O"], np.array([[-2.0, 0.0, 0.0], [0.0, 0.0, 0.0]]), masses=np.array([15.999, 15.999]))
+    molecule.add_bonds(np.array([[0, 1]]))
+    reference = oracle.OracleSystem(molecule)
+    position = molecule.positions.copy()
+    reference.lib.orc_rewrap(reference.ref, oracle.dptr(position))
+    np.testing.assert_array_equal(position, [[3.0, 0.0, 0.0], [5.0, 0.0, 0.0]])
+
+
+def test_berendsen_barostats_reduce_to_velocity_verlet_and_scale_the_cell():
+    """With eta = 1 and the target equal to the instantaneous pressure the barostat step IS a velocity-Verlet step
+    (integrators.rs:211-255 against :44-69); a lower target pressure makes the next eta larger than one, and the cell
+    is scaled by eta^3 (sic, integrators.rs:225) on the following step."""
+    system = systems.md_helium()
+    systems.random_velocities(system, 300.0, seed=3)
+    n = system.size()
+    plain = oracle.OracleSystem(system)
+    acc = np.zeros((n, 3))
+    plain.lib.orc_velocity_verlet_step(plain.ref, oracle.dptr(plain.position), oracle.dptr(plain.velocity), oracle.dptr(acc), 1.0)
+
+    npt = oracle.OracleSystem(system)
+    acc2 = np.zeros((n, 3))
+    eta = ctypes.c_double(1.0)
+    # pressure after the first half of the step is what the barostat compares with: take it from the plain run
+    target = plain.pressure()
+    status = npt.lib.orc_berendsen_barostat_step(npt.ref, oracle.dptr(npt.position), oracle.dptr(npt.velocity), oracle.dptr(acc2), 1.0,
+                                                 target, 1000.0, ctypes.byref(eta), 0.0)
+    assert status == 0
+    np.testing.assert_array_equal(npt.position, plain.position)
+    np.testing.assert_allclose(npt.velocity, plain.velocity, rtol=0, atol=1e-18)
+    before = np.array(npt.s.cell[:])
+    np.testing.assert_array_equal(before, system.cell.matrix().reshape(-1))
+    eta_after_first = eta.value  # close to one: the target was the pressure at the end of the plain step
+    assert abs(eta_after_first - 1.0) < 1e-4
+    # second step with a much lower target: the box must grow
+    status = npt.lib.orc_berendsen_barostat_step(npt.ref, oracle.dptr(npt.position), oracle.dptr(npt.velocity), oracle.dptr(acc2), 1.0,
+                                                 target - 1e-6, 1000.0, ctypes.byref(eta), 0.0)
+    assert status == 0 and eta.value > 1.0
+    first_eta = eta.value
+    status = npt.lib.orc_berendsen_barostat_step(npt.ref, oracle.dptr(npt.position), oracle.dptr(npt.velocity), oracle.dptr(acc2), 1.0,
+                                                 target - 1e-6, 1000.0, ctypes.byref(eta), 0.0)
+    after = np.array(npt.s.cell[:])
+    np.testing.assert_allclose(after[0], before[0] * eta_after_first ** 3 * first_eta ** 3, rtol=1e-14)
+    # the anisotropic barostat with a hydrostatic target and eta = 1 is velocity Verlet as well
+    aniso = oracle.OracleSystem(system)
+    acc3 = np.zeros((n, 3))
+    eta9 = np.eye(3).reshape(-1).copy()
+    stress = np.ascontiguousarray(plain.stress().reshape(-1))
+    status = aniso.lib.orc_aniso_berendsen_barostat_step(aniso.ref, oracle.dptr(aniso.position), oracle.dptr(aniso.velocity), oracle.dptr(acc3),
+                                                         1.0, oracle.dptr(stress), 1000.0, oracle.dptr(eta9), 0.0)
+    assert status == 0
+    np.testing.assert_array_equal(aniso.position, plain.position)
+    np.testing.assert_allclose(eta9.reshape(3, 3), eta9.reshape(3, 3).T, rtol=0, atol=0)
+    # the cell shrinking below twice the cut-off is the reference's panic (integrators.rs:227-236)
+    small = oracle.OracleSystem(system)
+    eta = ctypes.c_double(0.5)
+    status = small.lib.orc_berendsen_barostat_step(small.ref, oracle.dptr(small.position), oracle.dptr(small.velocity), oracle.dptr(np.zeros((n, 3))),
+                                                   1.0, target, 1000.0, ctypes.byref(eta), 12.0)
+    assert status == 1
