@@ -235,6 +235,17 @@ def bench_system_latencies(repeats=30):
             row[label] = (time.perf_counter() - start) / repeats * 1e6
         system._device.close()
         out[name] = row
+    # device-resident MD of the smallest system (300 atoms): launch-latency bound, replayed from a CUDA graph
+    from lumol_b200 import md
+
+    system = systems.lj_box(7, seed=3)  # 343 atoms, all-pairs path (argon.pdb holds overlapping atoms: not for MD)
+    systems.random_velocities(system, 120.0, seed=1)
+    propagator = md.MolecularDynamics(TIMESTEP_FS)
+    propagator.propagate(system, 100, download=False)
+    start = time.perf_counter()
+    propagator.propagate(system, 5000, download=False)
+    out["md_343_atoms_us_per_step"] = (time.perf_counter() - start) / 5000 * 1e6
+    system._device.close()
     return out
 
 

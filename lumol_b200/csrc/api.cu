@@ -3,6 +3,7 @@
 #include "context.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -1057,7 +1058,51 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
     CTX_OR_FAIL(ctx);
     if (c->integrator < 0) return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_setup was not called");
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
-    for (int64_t s = 0; s < nsteps; s++) {
+    // Small systems (all-pairs path: every system of the reference's tests and benches) are bound by launch latency:
+    // one step in the middle of the run is captured into a CUDA graph and replayed.  The first
+    // step runs eagerly (it allocates and settles the path), the last one as well (it ends with the half kick).
+    int64_t s = 0;
+    static const bool graphs_disabled = std::getenv("LUMOL_CUDA_NO_GRAPH") != nullptr;
+    const bool plain_integrator = c->integrator >= LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET && c->integrator <= LUMOL_CUDA_INTEGRATOR_LEAP_FROG;
+    if (!graphs_disabled && nsteps >= 8 && c->nranks == 1 && !c->profiling && plain_integrator && c->thermostat != LUMOL_CUDA_THERMOSTAT_CSVR) {
+        int status = md_step(c, true, false);
+        if (status) return status;
+        s = 1;
+        if (c->path == 0) {
+            const int64_t launches_before = c->launches, step_before = c->md_step;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool captured = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (captured) {
+                status = md_step(c, false, false);
+                captured = cudaStreamEndCapture(c->stream, &graph) == cudaSuccess && status == 0 && graph != nullptr;
+                // what the capture "ran" was only recorded
+                c->launches = launches_before;
+                c->md_step = step_before;
+                if (captured) captured = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            }
+            if (captured) {
+                const int64_t replays = nsteps - 2;
+                int64_t per_step = 0;  // kernel and memset nodes of one step
+                {
+                    size_t nodes = 0;
+                    if (cudaGraphGetNodes(graph, nullptr, &nodes) == cudaSuccess) per_step = (int64_t)nodes;
+                }
+                for (int64_t r = 0; r < replays; r++) {
+                    LUMOL_CUDA_CHECK(c, cudaGraphLaunch(exec, c->stream));
+                }
+                c->launches += per_step * replays;
+                c->md_step += replays;
+                s += replays;
+            } else {
+                cudaGetLastError();
+                if (status) return status;
+            }
+            if (exec != nullptr) cudaGraphExecDestroy(exec);
+            if (graph != nullptr) cudaGraphDestroy(graph);
+        }
+    }
+    for (; s < nsteps; s++) {
         int status = md_step(c, s == 0, s + 1 == nsteps);
         if (status) return status;
     }
