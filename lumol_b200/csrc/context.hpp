@@ -174,7 +174,7 @@ struct Context {
     uint64_t list_signature = 0;
     uint64_t structure_generation = 0;  // bumped by every change the list depends on besides positions
     DeviceBuffer<int> nl_flags;         // rebuild flag, overflow flag, rebuild counter
-    DeviceBuffer<unsigned> nlist;       // transposed neighbour list: entry k of atom i at [k * stride + i]
+    DeviceBuffer<unsigned> nlist;       // neighbour list: one slab per 32 atoms, columns interleaved by 16-byte words
     DeviceBuffer<int> ncount;
     DeviceBuffer<double> xref;          // positions at the last rebuild, original order
     DeviceBuffer<double4> rel0;         // cell-relative positions at the last rebuild, sorted order
@@ -188,7 +188,6 @@ struct Context {
     DeviceBuffer<int2> blk_runs;               // runs of consecutive cells: one bulk copy each
     DeviceBuffer<int4> blk_header, blk_entries;  // staging tables of the Lennard-Jones kernel (pairs_cells.cu)
     DeviceBuffer<double> frame_pos;            // x | y | z planes, sorted order, positions in the frame of the box
-    DeviceBuffer<unsigned char> blk_map;       // staged slot -> entry number, per block
     DeviceBuffer<unsigned short> self_local;   // staged slot of each atom inside its own block
 
     // ---- reductions ------------------------------------------------------------------------------

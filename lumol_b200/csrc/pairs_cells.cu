@@ -9,27 +9,34 @@
 // FP64 at every evaluation; the list only bounds which pairs can pass.
 //
 // Rebuild (only when some atom moved more than skin / 2 since the last one; decided on the device, no host
-// round trip: the rebuild kernels are launched every time and return at once when the flag is clear):
+// round trip: ONE cooperative kernel, launched at every evaluation, that returns at once unless the refresh kernel
+// wrote the evaluation's epoch into the rebuild flag):
 //   1. counting sort of the atoms into cells of edge >= cut-off + skin (z-major cells, atoms of a cell
 //      contiguous and ordered by original index, so every rank of a multi-GPU run derives the same order);
 //   2. per atom, in cell order ("sorted index"):
 //        sorted_pos  double4 (x, y, z, q): position RELATIVE TO THE CENTRE OF THE ATOM'S CELL + charge
-//        sorted_f32  float4: the same position in FP32 (pre-filter of the list build)
+//        frame       x | y | z planes: the same position in the frame of the box, in units of sigma, every cell
+//                    starting at an even index (bulk copies of the Lennard-Jones kernel)
+//        sorted_f32  float4: the cell-relative position in FP32 (pre-filter of the list build)
 //        sorted_info int4 (kind, first atom of the molecule, bond-distance row, original index)
 //      With cell-relative coordinates the separation of atom i in cell h and atom j in cell h + (a, b, c) is
-//      (x_i - (a, b, c) * edge) - x_j whatever the periodic wrap of the cell index: no image logic in the
-//      kernels, and full relative precision in arbitrarily large boxes;
-//   3. list build: one lane per atom, one warp per home cell; the warp streams the 27 neighbour cells, every
-//      lane tests the broadcast candidate against its own atom in FP32 with an enlarged radius and appends
-//      survivors to its column of the list, entries (offset code << 26) | j, the columns of 32 consecutive atoms
-//      interleaved in one contiguous slab.
+//      (x_i - (a, b, c) * edge) - x_j whatever the periodic wrap of the cell index;
+//   3. staging tables of the Lennard-Jones kernel: per block of TB consecutive atoms the cells of its neighbourhood,
+//      their slots in the block's shared-memory copy, the runs of consecutive cells (one bulk copy each);
+//   4. list build: one lane per atom, one warp per 32-atom chunk of a home cell; the warp streams the 27 neighbour
+//      cells, every lane tests the broadcast candidate against its own atom in FP32 with an enlarged radius and
+//      appends survivors to its column: (offset code << 26) | j in the general format, 16-bit slot numbers for a
+//      staged block; the columns of 32 consecutive atoms are interleaved in one contiguous slab;
+//   5. (separate kernel) bank-aware order of the staged columns.
 // Every evaluation:
 //   - positions in sorted order are refreshed as rel0 + (x - x_at_build), so an atom keeps the periodic image
 //     it had at build time, and the displacement is compared with skin / 2;
-//   - force kernel: one thread per atom walks its column (coalesced across the warp), gathers the FP64
-//     position of each neighbour (software-pipelined one entry ahead), applies the exact r < rc test and
-//     accumulates the force in registers: no atomics, no shuffles.  Each pair is evaluated from both sides;
-//     energies / virials are taken from the side with the larger sorted index.
+//   - general kernel (any potential, Ewald real space, Wolf): up to four threads per atom walk its column, gather the
+//     FP64 position of each neighbour (software-pipelined one entry ahead), apply the exact r < rc test and
+//     accumulate the force in registers; energies / virials are taken from the side with the larger sorted index;
+//   - Lennard-Jones kernel: one thread per atom, neighbourhood of the block staged in shared memory by TMA bulk copies,
+//     17 FP64 instructions per listed pair; half of the energy and virial from each side of a pair.
+// No atomics on the pair path: every pair is evaluated from both sides, sums are reduced in a fixed order.
 #include "context.hpp"
 
 #include <cooperative_groups.h>
