@@ -153,51 +153,67 @@ class ClockSampler:
 
 # ---- CPU arm -------------------------------------------------------------------------------------------------
 
-def cpu_sample_rows(system, target_seconds):
-    """Time the oracle (restatement of lumol's pair-force loop, sys/compute.rs:37-55) on uniformly spaced rows i of
-    the O(N^2) loop; returns (rows per second, rows, seconds, threads).  Test infrastructure used as the baseline."""
-    from oracle import oracle
+class CpuSampler:
+    """The oracle (restatement of lumol's pair-force loop, sys/compute.rs:37-55, OpenMP on every host core) timed on
+    uniformly spaced rows i of the O(N^2) loop.  Test infrastructure used as the baseline."""
 
-    reference = oracle.OracleSystem(system)
-    lib = reference.lib
-    threads = os.cpu_count() or 1
-    lib.orc_set_threads(threads)
-    n = system.size()
-    checksum = ctypes.c_double()
+    def __init__(self, system):
+        from oracle import oracle
 
-    def run(count):
-        rows = np.ascontiguousarray(np.linspace(0, n - 1, count).astype(np.int64))
+        self.oracle = oracle
+        self.reference = oracle.OracleSystem(system)
+        self.threads = os.cpu_count() or 1
+        self.reference.lib.orc_set_threads(self.threads)
+        self.n = system.size()
+        self.checksum = ctypes.c_double()
+
+    def run(self, count):
+        rows = np.ascontiguousarray(np.linspace(0, self.n - 1, count).astype(np.int64))
         start = time.perf_counter()
-        lib.orc_pair_forces_sample(reference.ref, len(rows), oracle.iptr(rows), ctypes.byref(checksum))
+        self.reference.lib.orc_pair_forces_sample(self.reference.ref, len(rows), self.oracle.iptr(rows), ctypes.byref(self.checksum))
         return time.perf_counter() - start
 
-    rows = max(threads * 2, 16)
-    seconds = run(rows)
-    # grow the sample until it runs for about the target (the first probes are dominated by thread start-up)
-    while seconds < 0.6 * target_seconds and rows < n:
-        rows = int(min(n, max(rows * 2, rows * target_seconds / max(seconds, 1e-3))))
-        rows = max(threads, rows // threads * threads)
-        seconds = run(rows)
-    return rows / seconds, rows, seconds, threads
+    def calibrate(self, target_seconds):
+        """Number of rows that runs for about ``target_seconds`` (the first probes are dominated by thread start-up)."""
+        rows = min(self.n, max(self.threads * 2, 16))
+        seconds = self.run(rows)
+        while seconds < 0.6 * target_seconds and rows < self.n:
+            rows = int(min(self.n, max(rows * 2, rows * target_seconds / max(seconds, 1e-3))))
+            rows = max(self.threads, rows // self.threads * self.threads)
+            seconds = self.run(rows)
+        return rows, seconds
+
+
+def cpu_sample_rows(system, target_seconds):
+    """One bounded sample: (rows per second, rows, seconds, threads)."""
+    sampler = CpuSampler(system)
+    rows, seconds = sampler.calibrate(target_seconds)
+    return rows / seconds, rows, seconds, sampler.threads
 
 
 def run_reference(args):
-    """``--impl reference``: the CPU path alone, same metric and config, K bounded samples after W warm-ups."""
+    """``--impl reference``: the CPU path alone, same metric and config: W + K bounded samples ("steps") of the same
+    size, sized once so that the whole run takes about a minute and a half whatever K and W are."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     system, description = build_workload(args)
     if args.workload != "lj":
         description["note"] = "CPU arm times the pair-force loop only"
-    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1)))
-    values, rows, threads = [], 0, 1
+    count = max(args.steps + args.warmup, 1)
+    per_step = min(args.cpu_seconds, 90.0 / count)
+    sampler = CpuSampler(system)
+    rows, _ = sampler.calibrate(per_step)
+    values = []
     for step in range(args.warmup + args.steps):
-        rate, rows, seconds, threads = cpu_sample_rows(system, per_step)
+        seconds = sampler.run(rows)
         if step >= args.warmup:
-            values.append(rate)
+            values.append(rows / seconds)
     value = float(np.mean(values)) if values else 0.0
     n = system.size()
-    sample = f"pair-force rows of {rows} of {n} atoms (uniform stride), all j > i, O(N^2) loop of sys/compute.rs:37-55"
+    threads = sampler.threads
+    sample = (f"per step: pair-force rows of {rows} of {n} atoms (uniform stride), all j > i, O(N^2) loop of "
+              "sys/compute.rs:37-55 restated in oracle/lumol_oracle.c (OpenMP)")
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n / value if value else None, "higher_is_better": True,

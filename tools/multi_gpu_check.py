@@ -19,18 +19,20 @@ from lumol_b200 import _ffi, md, parallel, synthetic
 from lumol_b200.device import DeviceSystem
 
 
-def evaluate(system, rank, world, local_rank, sharded):
+def evaluate(system, rank, world, local_rank, sharded, kspace=None):
     device = DeviceSystem(local_rank)
     if sharded:
         parallel.init_communicator(device, rank, world)
+    if kspace is not None:
+        device.set_kspace_algorithm(kspace)
     device.sync(system, velocities=True)
     result = device.compute(forces=True, energy=True, virial=True)
     return device, result
 
 
-def check(name, system, rank, world, local_rank):
-    single_device, single = evaluate(system, rank, world, local_rank, sharded=False)
-    sharded_device, sharded = evaluate(system, rank, world, local_rank, sharded=True)
+def check(name, system, rank, world, local_rank, kspace=None):
+    single_device, single = evaluate(system, rank, world, local_rank, sharded=False, kspace=kspace)
+    sharded_device, sharded = evaluate(system, rank, world, local_rank, sharded=True, kspace=kspace)
     scale = max(np.abs(single.forces).max(), 1e-300)
     force_error = np.abs(sharded.forces - single.forces).max() / scale
     terms = ("pairs", "pairs_tail", "bonds", "angles", "dihedrals", "coulomb_real", "coulomb_self", "coulomb_kspace")
@@ -81,6 +83,13 @@ def main():
     water.set_coulomb_potential(ewald)
     synthetic.maxwell_boltzmann(water, 300.0, seed=5)
     check("spce-3000 (list + Ewald + bonded)", water, rank, world, local_rank)
+    # the same with the register-tiled reciprocal-space kernels, atoms of rho and of the k-space forces sharded
+    tiled = synthetic.spce_box(10, flexible=True)
+    ewald = lumol.SharedEwald(lumol.Ewald(9.0, 11, 0.34))
+    ewald.set_restriction(lumol.PairRestriction.InterMolecular)
+    tiled.set_coulomb_potential(ewald)
+    synthetic.maxwell_boltzmann(tiled, 300.0, seed=5)
+    check("spce-3000 (tiled k-space kernels)", tiled, rank, world, local_rank, kspace=1)
 
     nacl = systems.md_nacl("wolf")
     nacl.positions += np.random.Generator(np.random.PCG64(9)).uniform(-0.2, 0.2, nacl.positions.shape)  # perfect lattice: zero forces
