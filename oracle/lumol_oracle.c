@@ -2340,3 +2340,248 @@ void orc_rewrap(const orc_system* s, double* position) {
         }
     }
 }
+
+/* ------------------------------------------------------------------------ */
+/* Monte Carlo energy cache (sys/cache.rs) and the GlobalCache of Ewald/Wolf  */
+/* ------------------------------------------------------------------------ */
+
+/* cells.rs:316-320 distance(u, v) = image(v - u).norm() */
+static inline double distance_points(const geom_t* g, const double* u, const double* v) {
+    double d[3] = {v[0] - u[0], v[1] - u[1], v[2] - u[2]};
+    geom_image(g, d);
+    return norm3(d);
+}
+
+/* energy.rs:32-45 EnergyEvaluator::pair */
+static double evaluator_pair(const orc_system* s, int32_t path, double r, int64_t i, int64_t j) {
+    const orc_pair* potential = pair_potential(s, i, j);
+    if (potential == NULL) {
+        return 0.0;
+    }
+    int32_t excluded;
+    double scaling;
+    orc_restriction_information(potential->restriction, potential->scale14, path, &excluded, &scaling);
+    if (!excluded) {
+        return scaling * orc_pair_energy(potential, r);
+    }
+    return 0.0;
+}
+
+/* The entry pairs_cache[(i, j)] as EnergyCache::init fills it (cache.rs:81-90): evaluated for i < j from
+ * nearest_image(i, j).norm() and mirrored. */
+static double cached_pair(const orc_system* s, const geom_t* g, int64_t a, int64_t b) {
+    int64_t i = imin(a, b), j = imax(a, b);
+    double d[3];
+    nearest_image(s, g, i, j, d);
+    return evaluator_pair(s, orc_bond_path(s, i, j), norm3(d), i, j);
+}
+
+/* cache.rs:145-172: pair part of EnergyCache::move_molecule_cost.  The reference reads the old pair
+ * energies from pairs_cache; they are re-evaluated here exactly as EnergyCache::init stored them. */
+double orc_move_molecule_pairs_cost(const orc_system* s, int64_t molecule, const double* new_positions) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    double pairs_delta = 0.0;
+    int64_t first = s->mol_start[molecule], last = s->mol_start[molecule + 1];
+    for (int64_t part_i = first; part_i < last; part_i++) {
+        int64_t i = part_i - first;
+        for (int64_t other = 0; other < s->nmol; other++) {
+            if (other == molecule) continue;
+            for (int64_t part_j = s->mol_start[other]; part_j < s->mol_start[other + 1]; part_j++) {
+                double r = distance_points(&g, s->position + 3 * part_j, new_positions + 3 * i);
+                int32_t path = orc_bond_path(s, part_i, part_j);
+                double energy = evaluator_pair(s, path, r, part_i, part_j);
+                pairs_delta += energy;
+                pairs_delta -= cached_pair(s, &g, part_i, part_j);
+            }
+        }
+    }
+    return pairs_delta;
+}
+
+/* ewald.rs:572-613 real_space_move_molecule_cost */
+double orc_ewald_real_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    double old_energy = 0.0, new_energy = 0.0;
+    int64_t first = s->mol_start[molecule], last = s->mol_start[molecule + 1];
+    for (int64_t part_i = first; part_i < last; part_i++) {
+        int64_t i = part_i - first;
+        double qi = s->charge[part_i];
+        if (qi == 0.0) continue;
+        for (int64_t other = 0; other < s->nmol; other++) {
+            if (other == molecule) continue;
+            for (int64_t part_j = s->mol_start[other]; part_j < s->mol_start[other + 1]; part_j++) {
+                double qj = s->charge[part_j];
+                if (qj == 0.0) continue;
+                double old_r = distance(s, &g, part_i, part_j);
+                double new_r = distance_points(&g, new_positions + 3 * i, s->position + 3 * part_j);
+                int32_t path = orc_bond_path(s, part_i, part_j);
+                int32_t excluded;
+                double scaling;
+                orc_restriction_information(s->coulomb_restriction, s->coulomb_scale14, path, &excluded, &scaling);
+                old_energy += ewald_real_energy_pair(s, excluded, qi * qj, old_r);
+                new_energy += ewald_real_energy_pair(s, excluded, qi * qj, new_r);
+            }
+        }
+    }
+    return new_energy - old_energy;
+}
+
+/* ewald.rs:758-839 delta_rho_move_rigid_molecules + k_space_move_molecule_cost.  The reference reads the old
+ * phases and rho(k) from the cache left by its last eik_dot_r; here that call is made on the spot, i.e. the cache
+ * is taken to be current (it is in the reference's own test, ewald.rs:1326-1327).  delta_rho (2 per k) may be NULL. */
+double orc_ewald_kspace_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions,
+                                           int64_t capacity, double* delta_rho) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    ewald_factors_t f;
+    ewald_factors_init(&f, s, &g);
+    ewald_kspace_t ks;
+    eik_dot_r(&ks, s, &g, &f);
+
+    double old_energy = 0.0;
+    for (int64_t ik = 0; ik < f.nk; ik++) {
+        old_energy += f.energy[ik] * (ks.rho[ik].re * ks.rho[ik].re + ks.rho[ik].im * ks.rho[ik].im);
+    }
+    old_energy /= ORC_FOUR_PI_EPSILON_0;
+
+    int64_t first = s->mol_start[molecule], size = s->mol_start[molecule + 1] - first;
+    int64_t kmax = s->kmax;
+    ewald_kspace_t fresh;
+    fresh.kmax = kmax;
+    fresh.n = size;
+    fresh.eikr = (cplx*)malloc((size_t)((2 * kmax + 1) * 3 * (size > 0 ? size : 1)) * sizeof(cplx));
+    fresh.rho = NULL;
+    for (int spatial = 0; spatial < 3; spatial++) {
+        double k_idx[3] = {0.0, 0.0, 0.0};
+        k_idx[spatial] = 1.0;
+        double k_vector[3];
+        geom_k_vector(&g, k_idx, k_vector);
+        for (int64_t i = 0; i < size; i++) {
+            double phi = dot3(k_vector, new_positions + 3 * i);
+            cplx one = {1.0, 0.0};
+            cplx e1 = {1.0 * cos(phi), 1.0 * sin(phi)};
+            cplx em1 = {e1.re, -e1.im};
+            *eikr_at(&fresh, 0, spatial, i) = one;
+            *eikr_at(&fresh, 1, spatial, i) = e1;
+            *eikr_at(&fresh, -1, spatial, i) = em1;
+        }
+    }
+    for (int spatial = 0; spatial < 3; spatial++) {
+        for (int64_t k = 2; k < kmax + 1; k++) {
+            for (int64_t i = 0; i < size; i++) {
+                cplx v = cmul(*eikr_at(&fresh, k - 1, spatial, i), *eikr_at(&fresh, 1, spatial, i));
+                cplx c = {v.re, -v.im};
+                *eikr_at(&fresh, k, spatial, i) = v;
+                *eikr_at(&fresh, -k, spatial, i) = c;
+            }
+        }
+    }
+
+    double new_energy = 0.0;
+    for (int64_t ik = 0; ik < f.nk; ik++) {
+        int64_t ikx = f.index[3 * ik], iky = f.index[3 * ik + 1], ikz = f.index[3 * ik + 2];
+        cplx partial = {0.0, 0.0};
+        for (int64_t i = 0; i < size; i++) {
+            int64_t part_i = first + i;
+            cplx old_phi = cmul(cmul(*eikr_at(&ks, ikx, 0, part_i), *eikr_at(&ks, iky, 1, part_i)), *eikr_at(&ks, ikz, 2, part_i));
+            cplx new_phi = cmul(cmul(*eikr_at(&fresh, ikx, 0, i), *eikr_at(&fresh, iky, 1, i)), *eikr_at(&fresh, ikz, 2, i));
+            partial.re += s->charge[part_i] * (new_phi.re - old_phi.re);
+            partial.im += s->charge[part_i] * (new_phi.im - old_phi.im);
+        }
+        if (delta_rho != NULL && ik < capacity) {
+            delta_rho[2 * ik] = partial.re;
+            delta_rho[2 * ik + 1] = partial.im;
+        }
+        double re = ks.rho[ik].re + partial.re, im = ks.rho[ik].im + partial.im;
+        new_energy += f.energy[ik] * (re * re + im * im);
+    }
+    new_energy /= ORC_FOUR_PI_EPSILON_0;
+
+    free(fresh.eikr);
+    kspace_free(&ks);
+    ewald_factors_free(&f);
+    return new_energy - old_energy;
+}
+
+/* wolf.rs:121-165 GlobalCache::move_molecule_cost */
+double orc_wolf_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    double alpha, ec, fc;
+    wolf_constants(s, &alpha, &ec, &fc);
+    double old_energy = 0.0, new_energy = 0.0;
+    int64_t first = s->mol_start[molecule], last = s->mol_start[molecule + 1];
+    for (int64_t part_i = first; part_i < last; part_i++) {
+        int64_t i = part_i - first;
+        double qi = s->charge[part_i];
+        if (qi == 0.0) continue;
+        for (int64_t other = 0; other < s->nmol; other++) {
+            if (other == molecule) continue;
+            for (int64_t part_j = s->mol_start[other]; part_j < s->mol_start[other + 1]; part_j++) {
+                double qj = s->charge[part_j];
+                if (qj == 0.0) continue;
+                int32_t path = orc_bond_path(s, part_i, part_j);
+                int32_t excluded;
+                double scaling;
+                orc_restriction_information(s->coulomb_restriction, s->coulomb_scale14, path, &excluded, &scaling);
+                if (excluded) continue;
+                double old_r = distance(s, &g, part_i, part_j);
+                double new_r = distance_points(&g, new_positions + 3 * i, s->position + 3 * part_j);
+                /* wolf.rs:90-96 energy_pair */
+                double old_e = old_r > s->rc ? 0.0 : (qi * qj) * (erfc(alpha * old_r) / old_r - ec) / ORC_FOUR_PI_EPSILON_0;
+                double new_e = new_r > s->rc ? 0.0 : (qi * qj) * (erfc(alpha * new_r) / new_r - ec) / ORC_FOUR_PI_EPSILON_0;
+                old_energy += scaling * old_e;
+                new_energy += scaling * new_e;
+            }
+        }
+    }
+    return new_energy - old_energy;
+}
+
+/* EnergyCache::move_molecule_cost (cache.rs:145-174) by term: out = {pairs_delta, coulomb real space (or the whole
+ * Wolf sum), coulomb k-space}; the cost is their sum (global potentials other than coulomb are out of scope). */
+void orc_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions, double out[3]) {
+    out[0] = orc_move_molecule_pairs_cost(s, molecule, new_positions);
+    out[1] = 0.0;
+    out[2] = 0.0;
+    if (s->coulomb == ORC_COULOMB_EWALD) {
+        /* SharedEwald::move_molecule_cost, ewald.rs:933-946: real + k_space, no self cost */
+        out[1] = orc_ewald_real_move_molecule_cost(s, molecule, new_positions);
+        out[2] = orc_ewald_kspace_move_molecule_cost(s, molecule, new_positions, 0, NULL);
+    } else if (s->coulomb == ORC_COULOMB_WOLF) {
+        out[1] = orc_wolf_move_molecule_cost(s, molecule, new_positions);
+    }
+}
+
+/* EnergyCache::move_all_molecules_cost (cache.rs:230-283): `before` is the system the cache was initialised with,
+ * `after` the system with every molecule moved rigidly (possibly in a new cell).  out = {pairs_delta over the
+ * inter-molecular pairs, pairs_tail - cache.pairs_tail, new_coulomb - cache.coulomb}. */
+void orc_move_all_molecules_cost(const orc_system* before, const orc_system* after, double out[3]) {
+    geom_t g_before, g_after;
+    geom_init(&g_before, before->cell, before->shape);
+    geom_init(&g_after, after->cell, after->shape);
+    double pairs_delta = 0.0;
+    for (int64_t mi = 0; mi < after->nmol; mi++) {
+        for (int64_t mj = mi + 1; mj < after->nmol; mj++) {
+            for (int64_t part_i = after->mol_start[mi]; part_i < after->mol_start[mi + 1]; part_i++) {
+                for (int64_t part_j = after->mol_start[mj]; part_j < after->mol_start[mj + 1]; part_j++) {
+                    double r = distance(after, &g_after, part_i, part_j);
+                    int32_t path = orc_bond_path(after, part_i, part_j);
+                    double energy = evaluator_pair(after, path, r, part_i, part_j);
+                    pairs_delta += energy;
+                    pairs_delta -= cached_pair(before, &g_before, part_i, part_j);
+                }
+            }
+        }
+    }
+    orc_energy_terms terms_before, terms_after;
+    orc_energy_terms_compute(before, &terms_before);
+    orc_energy_terms_compute(after, &terms_after);
+    out[0] = pairs_delta;
+    out[1] = terms_after.pairs_tail - terms_before.pairs_tail;
+    double coulomb_before = terms_before.coulomb_real + terms_before.coulomb_self + terms_before.coulomb_kspace;
+    double coulomb_after = terms_after.coulomb_real + terms_after.coulomb_self + terms_after.coulomb_kspace;
+    out[2] = coulomb_after - coulomb_before;
+}

@@ -250,6 +250,19 @@ int orc_berendsen_barostat_step(orc_system* s, double* position, double* velocit
 int orc_aniso_berendsen_barostat_step(orc_system* s, double* position, double* velocity, double* accelerations, double dt,
                                       const double stress[9], double tau, double eta[9], double maximum_cutoff);
 
+/* ---- Monte Carlo energy cache (sys/cache.rs:145-283; ewald.rs:572-613, 758-839; wolf.rs:121-165) -------- */
+/* new_positions: size-of-molecule x 3.  The old pair energies / phases / rho(k) the reference reads from its caches
+ * are re-evaluated on the spot from the system's positions (the caches are taken to be current). */
+double orc_move_molecule_pairs_cost(const orc_system* s, int64_t molecule, const double* new_positions);
+double orc_ewald_real_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions);
+double orc_ewald_kspace_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions,
+                                           int64_t capacity, double* delta_rho /* 2 per k, may be NULL */);
+double orc_wolf_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions);
+/* out = {pairs, coulomb real space (or Wolf), coulomb k-space}; EnergyCache::move_molecule_cost is their sum */
+void orc_move_molecule_cost(const orc_system* s, int64_t molecule, const double* new_positions, double out[3]);
+/* out = {inter-molecular pairs, pairs_tail, coulomb} differences; EnergyCache::move_all_molecules_cost is their sum */
+void orc_move_all_molecules_cost(const orc_system* before, const orc_system* after, double out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,12 @@ def library():
             "orc_rewrap": (None, [sp, _dp]),
             "orc_berendsen_barostat_step": (ctypes.c_int, [sp, _dp, _dp, _dp, d, d, d, _dp, d]),
             "orc_aniso_berendsen_barostat_step": (ctypes.c_int, [sp, _dp, _dp, _dp, d, _dp, d, _dp, d]),
+            "orc_move_molecule_pairs_cost": (d, [sp, ctypes.c_int64, _dp]),
+            "orc_ewald_real_move_molecule_cost": (d, [sp, ctypes.c_int64, _dp]),
+            "orc_ewald_kspace_move_molecule_cost": (d, [sp, ctypes.c_int64, _dp, ctypes.c_int64, _dp]),
+            "orc_wolf_move_molecule_cost": (d, [sp, ctypes.c_int64, _dp]),
+            "orc_move_molecule_cost": (None, [sp, ctypes.c_int64, _dp, _dp]),
+            "orc_move_all_molecules_cost": (None, [sp, sp, _dp]),
         }
         for name, (restype, argtypes) in signatures.items():
             function = getattr(lib, name)
@@ -426,3 +432,23 @@ class OracleSystem:
         rho = np.zeros((nk, 2))
         self.lib.orc_ewald_rho(self.ref, nk, dptr(rho))
         return rho
+
+    # ---- Monte Carlo energy cache (sys/cache.rs) ---------------------------------------------------------
+    def move_molecule_cost(self, molecule, new_positions):
+        """(pairs, coulomb real space or Wolf, coulomb k-space) terms of ``EnergyCache::move_molecule_cost``."""
+        positions = np.ascontiguousarray(new_positions, dtype=np.float64)
+        out = np.zeros(3)
+        self.lib.orc_move_molecule_cost(self.ref, molecule, dptr(positions), dptr(out))
+        return out
+
+    def ewald_kspace_move_molecule_cost(self, molecule, new_positions, nk):
+        positions = np.ascontiguousarray(new_positions, dtype=np.float64)
+        delta = np.zeros((nk, 2))
+        cost = self.lib.orc_ewald_kspace_move_molecule_cost(self.ref, molecule, dptr(positions), nk, dptr(delta))
+        return cost, delta
+
+    def move_all_molecules_cost(self, after):
+        """(pairs, tail, coulomb) terms of ``EnergyCache::move_all_molecules_cost``; ``self`` is the cached system."""
+        out = np.zeros(3)
+        self.lib.orc_move_all_molecules_cost(self.ref, after.ref, dptr(out))
+        return out

@@ -188,3 +188,107 @@ def random_velocities(system, temperature, seed):
 
 
 from lumol_b200.synthetic import lj_box, spce_box  # noqa: E402,F401  (synthetic boxes of SURVEY section 8d)
+
+
+# ---- Monte Carlo energy cache: the systems and trial positions of the reference's own cache tests --------------
+
+def cache_testing_system():
+    """sys/cache.rs:306-394 ``testing_system``: two H-O-O-H molecules, LJ / null pairs, harmonic bonded terms, Wolf(5)."""
+    system = lumol.system_from_xyz("""8
+    cell: 10.0
+    H     0.895669     0.000000    -0.316667
+    O     0.000000     0.000000     0.000000
+    O     0.000000     0.000000     1.480000
+    H    -0.895669     0.000000     1.796667
+    O     3.000000     0.000000     0.000000
+    O     3.000000     0.000000     1.480000
+    H     3.895669     0.000000    -0.316667
+    H     2.104330     0.000000     1.796667
+    """)
+    for (i, j) in ((0, 1), (0, 2), (1, 3), (4, 5), (4, 6), (5, 7)):
+        assert system.add_bond(i, j) == []
+    assert len(system.molecules()) == 2
+    system.set_pair_potential(("H", "H"), lumol.PairInteraction(lumol.LennardJones(sigma=3.0, epsilon=units.from_(0.5, "kJ/mol")), 3.0))
+    system.set_pair_potential(("O", "O"), lumol.PairInteraction(lumol.NullPotential(), 3.0))
+    system.set_pair_potential(("O", "H"), lumol.PairInteraction(lumol.LennardJones(sigma=1.0, epsilon=units.from_(0.3, "kJ/mol")), 3.0))
+    system.set_bond_potential(("O", "O"), lumol.Harmonic(x0=2.4, k=units.from_(522.0, "kJ/mol/A^2")))
+    system.set_bond_potential(("O", "H"), lumol.Harmonic(x0=1.4, k=units.from_(122.0, "kJ/mol/A^2")))
+    system.set_angle_potential(("O", "O", "H"), lumol.Harmonic(x0=np.radians(120.0), k=units.from_(150.0, "kJ/mol/deg^2")))
+    system.set_dihedral_potential(("H", "O", "O", "H"), lumol.Harmonic(x0=np.radians(180.0), k=units.from_(800.0, "kJ/mol/deg^2")))
+    system.set_coulomb_potential(lumol.Wolf(5.0))
+    system.charges[:] = [-0.5 if name == "O" else 0.5 for name in system.names]
+    system.invalidate()
+    return system
+
+
+# cache.rs:413-418 and 434-439: two successive trial positions of molecule 0
+CACHE_MOVES = (
+    np.array([
+        [-0.987061, 0.59401, 0.427533],
+        [-1.0744137409578138, 1.2111820514074991, -0.2893833856814936],
+        [-1.4352068561309008, 2.5425486908430286, 0.24698514382209652],
+        [-1.5225595970887147, 3.159720742250528, -0.46993124185939705],
+    ]),
+    np.array([
+        [-0.49138099999999996, 1.08969, 0.923213],
+        [-1.0139188773839494, 1.7555242433058806, 1.3546291257885033],
+        [-2.4014453359903767, 1.2663193861239206, 1.5154051637316108],
+        [-2.923983213374326, 1.9321536294298012, 1.946821289520114],
+    ]),
+)
+# cache.rs:457 and 474: rigid translations of molecule 0, then of every molecule
+CACHE_TRANSLATIONS = (np.array([1.0, 0.5, -0.5]), np.array([-0.9, 0.0, 1.8]))
+
+
+def wolf_cache_system():
+    """energy/global/wolf.rs:447-474: two SPC/E-charged waters in a 20 A box, O first."""
+    system = lumol.system_from_xyz("""6
+    cell: 20.0
+    O  0.0  0.0  0.0
+    H -0.7 -0.7  0.3
+    H  0.3 -0.3 -0.8
+    O  2.0  2.0  0.0
+    H  1.3  1.3  0.3
+    H  2.3  1.7 -0.8
+    """)
+    for (i, j) in ((0, 1), (0, 2), (3, 4), (3, 5)):
+        assert system.add_bond(i, j) == []
+    assert len(system.molecules()) == 2
+    system.charges[:] = [-0.8476 if name == "O" else 0.4238 for name in system.names]
+    system.invalidate()
+    return system
+
+
+# wolf.rs:486-490
+WOLF_CACHE_MOVE = np.array([
+    [4.0, 0.0, -2.0],
+    [3.010010191494968, 0.19045656166589708, -2.1166435218719863],
+    [4.0761078062722484, -0.8995901989882638, -2.0703212322750546],
+])
+
+
+def ewald_cache_system():
+    """energy/global/ewald.rs:1291-1312: the same two waters with the oxygen in the middle of each molecule."""
+    system = lumol.system_from_xyz("""6
+    cell: 20.0
+    H  0.3 -0.3 -0.8
+    O  0.0  0.0  0.0
+    H -0.7 -0.7  0.3
+    H  2.3  1.7 -0.8
+    O  2.0  2.0  0.0
+    H  1.3  1.3  0.3
+    """)
+    for (i, j) in ((0, 1), (1, 2), (3, 4), (4, 5)):
+        assert system.add_bond(i, j) == []
+    assert len(system.molecules()) == 2
+    system.charges[:] = [-0.8476 if name == "O" else 0.4238 for name in system.names]
+    system.invalidate()
+    return system
+
+
+# ewald.rs:1329-1333
+EWALD_CACHE_MOVE = np.array([
+    [0.41727, 2.29401, -0.0558],
+    [0.5097743599026461, 3.194114034722624, -0.020364564697826326],
+    [-0.2501317777731211, 3.562366060753896, -0.6178033542374419],
+])
