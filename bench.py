@@ -249,6 +249,39 @@ def bench_system_latencies(repeats=30):
             for _ in range(repeats):
                 estimator.compute(system)
             row[label] = (time.perf_counter() - start) / repeats * 1e6
+        try:
+            # benches/*.rs `move_molecule_cost` / `move_all_molecules_cost`: one trial per call, and 64 trials per batch
+            import lumol_b200 as lumol
+
+            rng = np.random.Generator(np.random.PCG64(17))
+            cache = lumol.EnergyCache()
+            cache.init(system)
+            nmol = len(system.molecules())
+
+            def trial():
+                molecule = int(rng.integers(0, nmol))
+                bonding = system.molecule(molecule)
+                return molecule, system.positions[bonding.start:bonding.end] + rng.uniform(-1.0, 1.0, 3)
+
+            trials = [trial() for _ in range(64)]
+            for molecule, positions in trials[:3]:
+                cache.move_molecule_cost(system, molecule, positions)
+            start = time.perf_counter()
+            for molecule, positions in trials[:repeats]:
+                cache.move_molecule_cost(system, molecule, positions)
+            row["move_molecule_cost"] = (time.perf_counter() - start) / repeats * 1e6
+            ids, news = [t[0] for t in trials], [t[1] for t in trials]
+            cache.move_molecules_cost(system, ids, news)
+            start = time.perf_counter()
+            for _ in range(5):
+                cache.move_molecules_cost(system, ids, news)
+            row["move_molecule_cost_batch64_per_trial"] = (time.perf_counter() - start) / (5 * 64) * 1e6
+            start = time.perf_counter()
+            for _ in range(5):
+                cache.move_all_molecules_cost(system)
+            row["move_all_molecules_cost"] = (time.perf_counter() - start) / 5 * 1e6
+        except Exception as error:  # the headline numbers must survive a failure of this extra
+            row["move_molecule_cost_error"] = str(error)
         system._device.close()
         out[name] = row
     # device-resident MD of the smallest system (300 atoms): launch-latency bound, replayed from a CUDA graph
@@ -525,7 +558,10 @@ def main():
                             False)
     if rank == 0:
         if world == 1 and args.workload == "lj" and not args.no_spce:
-            result["criterion_us_per_call"] = bench_system_latencies()
+            try:
+                result["criterion_us_per_call"] = bench_system_latencies()
+            except Exception as error:  # an extra: never lose the JSON line to it
+                result["criterion_us_per_call"] = {"error": str(error)}
         if companion is not None:
             keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "ns_per_day", "config", "e2e", "gpu_launches",
                     "roofline", "roofline_extra")

@@ -257,6 +257,26 @@ int32_t lumol_cuda_kinetic_tensor(lumol_cuda_context* ctx, double tensor[9]);
 int32_t lumol_cuda_ewald_kvectors(lumol_cuda_context* ctx, int64_t capacity, int64_t* count, int32_t* index /* 3 per k */,
                                   double* energy_factor, double* rho /* 2 per k */);
 
+/* ---- Monte Carlo energy cache (EnergyCache, sys/cache.rs; GlobalCache, energy/global/mod.rs:169-189) --------- */
+/* EnergyCache::move_molecule_cost (cache.rs:145-213) with the coulomb part of SharedEwald / Wolf
+ * (ewald.rs:572-613, 758-839, 933-946; wolf.rs:121-165): energy change of moving the rigid molecule `molecule`
+ * to new_positions (its size x 3), by term: cost->pairs, cost->coulomb_real, cost->coulomb_kspace are new minus old,
+ * the other fields 0 (tail, bonded and self terms do not change); the cost is their sum.  The resident state is
+ * NOT changed.  The old pair energies the reference reads from its N x N pairs_cache are re-evaluated from the
+ * resident positions; rho(k) is the one of the resident positions (recomputed only when they changed since the last
+ * Ewald evaluation). */
+int32_t lumol_cuda_move_molecule_cost(lumol_cuda_context* ctx, int64_t molecule, const double* new_positions,
+                                      lumol_cuda_energy* cost);
+/* The same for `ntrials` independent trial moves, each against the same resident state, in one batch of launches:
+ * new_positions holds the new positions of molecules[0], molecules[1], ... one after the other. */
+int32_t lumol_cuda_move_molecules_cost(lumol_cuda_context* ctx, int64_t ntrials, const int64_t* molecules,
+                                       const double* new_positions, lumol_cuda_energy* costs);
+/* EnergyCache::update after an accepted move (cache.rs:115-128, 175-211) plus what the reference's move does to the
+ * system (mc/moves/translate.rs:115-120): the molecule of trial `trial` of the last cost call takes its new
+ * positions on the device and rho(k) += delta rho(k) (ewald.rs:833-837).  Fails with LUMOL_CUDA_ERROR_STATE and the
+ * reference's message when no cost call is pending or the resident positions changed since. */
+int32_t lumol_cuda_move_molecule_accept(lumol_cuda_context* ctx, int64_t trial);
+
 /* ---- device-resident molecular dynamics (lumol-sim/src/md) ------------------------------------------ */
 /* Integrator::setup (integrators.rs:40-42, 92-101, 146-148) */
 int32_t lumol_cuda_md_setup(lumol_cuda_context* ctx, int32_t integrator, double timestep);

@@ -9,6 +9,7 @@ built library or without a CUDA device every evaluation raises ``LumolCudaError`
 
 from . import consts, units
 from ._ffi import LumolCudaError
+from .cache import EnergyCache
 from .energy import (
     BornMayerHuggins, Buckingham, CosineHarmonic, Ewald, Gaussian, Harmonic, LennardJones, Mie, Morse,
     NullPotential, PairInteraction, PairPotential, PairRestriction, Potential, SharedEwald, TableComputation,
@@ -17,7 +18,7 @@ from .energy import (
 from .sys import Molecule, Particle, System, UnitCell, system_from_xyz
 
 __all__ = [
-    "consts", "units", "LumolCudaError", "BornMayerHuggins", "Buckingham", "CosineHarmonic", "Ewald", "Gaussian",
+    "consts", "units", "LumolCudaError", "EnergyCache", "BornMayerHuggins", "Buckingham", "CosineHarmonic", "Ewald", "Gaussian",
     "Harmonic", "LennardJones", "Mie", "Morse", "NullPotential", "PairInteraction", "PairPotential",
     "PairRestriction", "Potential", "SharedEwald", "TableComputation", "Torsion", "Wolf", "Molecule", "Particle",
     "System", "UnitCell", "system_from_xyz",

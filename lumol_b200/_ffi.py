@@ -142,6 +142,9 @@ SIGNATURES = {
         _c.c_int32,
         [_ctx, _c.c_int64, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _dp, _dp],
     ),
+    "lumol_cuda_move_molecule_cost": (_c.c_int32, [_ctx, _c.c_int64, _dp, _c.POINTER(Energy)]),
+    "lumol_cuda_move_molecules_cost": (_c.c_int32, [_ctx, _c.c_int64, _c.POINTER(_c.c_int64), _dp, _c.POINTER(Energy)]),
+    "lumol_cuda_move_molecule_accept": (_c.c_int32, [_ctx, _c.c_int64]),
     "lumol_cuda_md_setup": (_c.c_int32, [_ctx, _c.c_int32, _c.c_double]),
     "lumol_cuda_md_set_degrees_of_freedom": (_c.c_int32, [_ctx, _c.c_int32, _c.c_int64]),
     "lumol_cuda_md_set_thermostat": (_c.c_int32, [_ctx, _c.c_int32, _c.c_double, _c.c_double]),

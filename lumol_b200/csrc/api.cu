@@ -20,6 +20,14 @@ static std::string g_create_error;
         return c->fail(LUMOL_CUDA_ERROR_CUDA, "cudaSetDevice(%d) failed", c->device); \
     }
 
+// Brackets every call that changes the resident positions (or charges): whatever was derived from them and is
+// kept between calls -- the structure factor the Monte Carlo cost calls reuse, a pending trial move -- is stale.
+struct PositionsChange {
+    Context* c;
+    explicit PositionsChange(Context* context) : c(context) { c->positions_epoch++; }
+    ~PositionsChange() { c->positions_epoch++; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +103,9 @@ extern "C" int32_t lumol_cuda_destroy(lumol_cuda_context* ctx) {
     c->nl_flags.release(); c->nlist.release(); c->ncount.release(); c->xref.release(); c->rel0.release();
     c->scan_scratch.release(); c->partials.release(); c->reduce_scratch.release(); c->results.release();
     c->csvr_noise_dev.release();
+    c->mc_trials.release(); c->mc_new_pos.release(); c->mc_delta_rho.release(); c->mc_pair_partials.release();
+    c->mc_k_partials.release(); c->mc_results.release();
+    if (c->mc_host_results) cudaFreeHost(c->mc_host_results);
     if (c->host_results) cudaFreeHost(c->host_results);
     if (c->timer.start) cudaEventDestroy(c->timer.start);
     if (c->timer.stop) cudaEventDestroy(c->timer.stop);
@@ -183,7 +194,9 @@ static int reset_molecules(Context* c) {
     c->nmol = n;
     c->max_mol_size = 1;
     c->has_molecules = false;
+    c->host_mol_start.clear();
     c->structure_generation++;
+    c->positions_epoch++;  // a pending trial move refers to molecules that no longer exist
     return 0;
 }
 
@@ -194,6 +207,7 @@ extern "C" int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, 
     if (n < 0 || n > 400000000 || (n > 0 && (position == nullptr || mass == nullptr || charge == nullptr || kind == nullptr))) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_set_particles: bad size or null array");
     }
+    PositionsChange change(c);
     const bool resized = n != c->n;
     c->n = n;
     c->structure_generation++;
@@ -233,6 +247,7 @@ extern "C" int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, 
 extern "C" int32_t lumol_cuda_set_positions(lumol_cuda_context* ctx, const double* position) {
     CTX_OR_FAIL(ctx);
     if (position == nullptr && c->n > 0) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null positions");
+    PositionsChange change(c);
     if (c->n > 0) {
         int status = upload(c, c->position.ptr, position, (size_t)c->n * 3 * sizeof(double));
         if (status) return status;
@@ -331,7 +346,9 @@ extern "C" int32_t lumol_cuda_set_molecules(lumol_cuda_context* ctx, int64_t nmo
     c->nmol = nmol;
     c->max_mol_size = max_size;
     c->has_molecules = true;
+    c->host_mol_start = starts;
     c->structure_generation++;
+    c->positions_epoch++;
     return LUMOL_CUDA_SUCCESS;
 }
 
@@ -851,6 +868,109 @@ extern "C" int32_t lumol_cuda_ewald_kvectors(lumol_cuda_context* ctx, int64_t ca
 }
 
 // ------------------------------------------------------------------------------------------------
+// Monte Carlo energy cache (sys/cache.rs)
+// ------------------------------------------------------------------------------------------------
+
+extern "C" int32_t lumol_cuda_move_molecules_cost(lumol_cuda_context* ctx, int64_t ntrials, const int64_t* molecules,
+                                                  const double* new_positions, lumol_cuda_energy* costs) {
+    CTX_OR_FAIL(ctx);
+    if (ntrials < 0 || ntrials > 65535 || (ntrials > 0 && (molecules == nullptr || new_positions == nullptr || costs == nullptr))) {
+        return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_move_molecules_cost: bad trial count or null array");
+    }
+    if (c->nranks > 1) {
+        return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "Monte Carlo trial moves are evaluated on a single GPU only");
+    }
+    if (c->coulomb.kind == 1 && c->cell.shape == LUMOL_CUDA_CELL_INFINITE) {
+        return c->fail(LUMOL_CUDA_ERROR_INFINITE_CELL, "Ewald is not defined with infinite unit cell");  // ewald.rs:124
+    }
+    c->mc_positions_epoch = ~0ull;
+    if (ntrials == 0) return LUMOL_CUDA_SUCCESS;
+
+    // rows of new_positions per trial, from the molecule sizes
+    c->mc_host_trials.resize((size_t)ntrials);
+    int64_t rows = 0;
+    int max_size = 1;
+    for (int64_t t = 0; t < ntrials; t++) {
+        const int64_t m = molecules[t];
+        if (m < 0 || m >= c->nmol) {
+            return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "trial %lld: molecule %lld is out of range", (long long)t, (long long)m);
+        }
+        const int size = c->has_molecules ? c->host_mol_start[(size_t)m + 1] - c->host_mol_start[(size_t)m] : 1;
+        if (size > max_size) max_size = size;
+        c->mc_host_trials[(size_t)t] = make_int2((int)m, (int)rows);
+        rows += size;
+        if (rows > 2000000000ll / 3) return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many trial positions");
+    }
+    int status = sync_tables(c);
+    if (status) return status;
+    LUMOL_CUDA_CHECK(c, c->mc_trials.reserve((size_t)ntrials));
+    LUMOL_CUDA_CHECK(c, c->mc_new_pos.reserve((size_t)rows * 3));
+    if ((status = upload(c, c->mc_trials.ptr, c->mc_host_trials.data(), (size_t)ntrials * sizeof(int2)))) return status;
+    if ((status = upload(c, c->mc_new_pos.ptr, new_positions, (size_t)rows * 3 * sizeof(double)))) return status;
+
+    if (c->coulomb.kind == 1) {
+        // the reference reads rho(k) from the cache its last energy / forces call left (ewald.rs:810-819); here it is
+        // recomputed only when the resident positions, the cell or the Ewald parameters changed since it was formed
+        if ((status = ewald_prepare(c))) return status;
+        if (c->rho_positions_epoch != c->positions_epoch || c->rho_table_version != c->ewald_table_version) {
+            ComputeRequest rho_only{};
+            rho_only.coulomb = true;
+            if ((status = launch_ewald_kspace(c, rho_only))) return status;
+        }
+    }
+    if ((status = launch_move_cost(c, (int)ntrials, max_size))) return status;
+
+    if (c->mc_host_capacity < (size_t)ntrials * 6) {
+        if (c->mc_host_results) cudaFreeHost(c->mc_host_results);
+        c->mc_host_results = nullptr;
+        c->mc_host_capacity = 0;
+        const size_t want = (size_t)ntrials * 6 + 60;
+        LUMOL_CUDA_CHECK(c, cudaMallocHost(reinterpret_cast<void**>(&c->mc_host_results), want * sizeof(double)));
+        c->mc_host_capacity = want;
+    }
+    LUMOL_CUDA_CHECK(c, cudaMemcpyAsync(c->mc_host_results, c->mc_results.ptr, (size_t)ntrials * 6 * sizeof(double),
+                                        cudaMemcpyDeviceToHost, c->stream));
+    LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int64_t t = 0; t < ntrials; t++) {
+        const double* r = c->mc_host_results + 6 * t;
+        std::memset(&costs[t], 0, sizeof(lumol_cuda_energy));
+        costs[t].pairs = r[0] - r[1];           // pair tail, bonds, angles, dihedrals do not change (cache.rs:165-167)
+        costs[t].coulomb_real = r[2] - r[3];    // ewald.rs:612 / wolf.rs:160; no self cost (ewald.rs:942)
+        costs[t].coulomb_kspace = r[4] - r[5];  // ewald.rs:838
+    }
+    c->mc_positions_epoch = c->positions_epoch;
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_move_molecule_cost(lumol_cuda_context* ctx, int64_t molecule, const double* new_positions,
+                                                 lumol_cuda_energy* cost) {
+    return lumol_cuda_move_molecules_cost(ctx, 1, &molecule, new_positions, cost);
+}
+
+extern "C" int32_t lumol_cuda_move_molecule_accept(lumol_cuda_context* ctx, int64_t trial) {
+    CTX_OR_FAIL(ctx);
+    if (c->mc_positions_epoch != c->positions_epoch) {
+        // cache.rs:123-126
+        return c->fail(LUMOL_CUDA_ERROR_STATE, "called EnergyCache::update without call a `*_cost` function first");
+    }
+    if (trial < 0 || trial >= (int64_t)c->mc_host_trials.size()) {
+        return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "trial %lld is not one of the last cost call", (long long)trial);
+    }
+    const int2 entry = c->mc_host_trials[(size_t)trial];
+    const int first = c->has_molecules ? c->host_mol_start[(size_t)entry.x] : entry.x;
+    const int size = c->has_molecules ? c->host_mol_start[(size_t)entry.x + 1] - first : 1;
+    const bool rho_current = c->coulomb.kind == 1 && c->rho_positions_epoch == c->positions_epoch;
+    int status = launch_move_accept(c, (int)trial, first, size, entry.y);
+    if (status) return status;
+    LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    // the resident positions changed; rho(k) was updated with them; the other trials of the batch are stale
+    c->positions_epoch++;
+    if (rho_current) c->rho_positions_epoch = c->positions_epoch;
+    c->mc_positions_epoch = ~0ull;
+    return LUMOL_CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
 // molecular dynamics
 // ------------------------------------------------------------------------------------------------
 
@@ -946,6 +1066,7 @@ extern "C" int32_t lumol_cuda_remove_rotation(lumol_cuda_context* ctx) {
 extern "C" int32_t lumol_cuda_rewrap(lumol_cuda_context* ctx) {
     CTX_OR_FAIL(ctx);
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
+    PositionsChange change(c);
     int status = launch_rewrap(c);
     if (status) return status;
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -1058,6 +1179,7 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
     CTX_OR_FAIL(ctx);
     if (c->integrator < 0) return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_setup was not called");
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
+    PositionsChange change(c);
     // Small systems (all-pairs path: every system of the reference's tests and benches) are bound by launch latency:
     // one step in the middle of the run is captured into a CUDA graph and replayed.  The first
     // step runs eagerly (it allocates and settles the path), the last one as well (it ends with the half kick).

@@ -160,6 +160,21 @@ struct Context {
     int kspace_algorithm = -1;       // -1 automatic, 0 direct kernels, 1 tiled kernels
     DeviceBuffer<double> kgmat, kforce_partial;
     double kbasis[9] = {0};  // k_vector of the three unit indices, one per row
+    uint64_t ewald_table_version = 0;  // bumped whenever ewald_prepare rebuilds the factor table
+    // rho(k) on the device describes the resident positions iff these match positions_epoch / ewald_table_version
+    uint64_t rho_positions_epoch = ~0ull, rho_table_version = ~0ull;
+
+    // ---- Monte Carlo trial moves (mc.cu) ---------------------------------------------------------
+    uint64_t positions_epoch = 0;          // bumped by every call that changes the resident positions or charges
+    std::vector<int> host_mol_start;       // nmol + 1 (empty while every atom is its own molecule)
+    DeviceBuffer<int2> mc_trials;          // (molecule, first row of its new positions) per trial
+    DeviceBuffer<double> mc_new_pos;       // rows of 3: new positions of the trials, concatenated
+    DeviceBuffer<double2> mc_delta_rho;    // ntrials x nk
+    DeviceBuffer<double> mc_pair_partials, mc_k_partials, mc_results;
+    std::vector<int2> mc_host_trials;      // of the last cost call
+    uint64_t mc_positions_epoch = ~0ull;   // resident state the last cost call was evaluated against
+    double* mc_host_results = nullptr;     // pinned
+    size_t mc_host_capacity = 0;
 
     // ---- neighbour search ----------------------------------------------------------------------
     int forced_path = -1;
@@ -308,6 +323,8 @@ int comm_allgather_positions(Context* ctx);                                     
 int comm_allreduce(Context* ctx, double* data, int64_t count);                                   // comm.cu
 int comm_allgather_blocks(Context* ctx, double* data, int64_t total);                            // comm.cu
 void comm_destroy(Context* ctx);                                                                 // comm.cu
+int launch_move_cost(Context* ctx, int ntrials, int max_size);                                   // mc.cu
+int launch_move_accept(Context* ctx, int trial, int first, int size, int64_t row);               // mc.cu
 int measure_fp64_peak(Context* ctx, double* tflops);                                             // peaks.cu
 int measure_copy_bandwidth(Context* ctx, double* gbs);                                           // peaks.cu
 

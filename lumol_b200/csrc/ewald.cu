@@ -154,6 +154,7 @@ int ewald_prepare(Context* ctx) {
         LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // the vectors above go out of scope
     }
     ctx->ewald_generation = ctx->cell_generation;
+    ctx->ewald_table_version++;
     return 0;
 }
 
@@ -944,6 +945,8 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
             status = comm_allreduce(ctx, reinterpret_cast<double*>(ctx->rho.ptr), 2 * (int64_t)nk);
             if (status != 0) return status;
         }
+        ctx->rho_positions_epoch = ctx->positions_epoch;
+        ctx->rho_table_version = ctx->ewald_table_version;
     }
 
     // ---- energy and virial ------------------------------------------------------------------------

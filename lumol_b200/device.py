@@ -268,9 +268,11 @@ class DeviceSystem:
         self._check(self.lib.lumol_cuda_set_kspace_algorithm(self.ctx, algorithm))
 
 
-def device_for(system, coulomb="system", velocities=False):
-    """The ``DeviceSystem`` of ``system``, created on first use and synchronised with the host arrays."""
+def device_for(system, coulomb="system", velocities=False, positions=True):
+    """The ``DeviceSystem`` of ``system``, created on first use and synchronised with the host arrays.
+    ``positions=False`` keeps the resident positions (after device-side Monte Carlo moves) unless the structure of
+    the system changed."""
     if system._device is None:
         system._device = DeviceSystem(getattr(system, "device_ordinal", 0))
-    system._device.sync(system, coulomb=coulomb, velocities=velocities)
+    system._device.sync(system, coulomb=coulomb, positions=positions, velocities=velocities)
     return system._device

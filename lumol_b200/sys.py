@@ -475,6 +475,18 @@ class System:
         total = float(np.sum(self.masses))
         return (self.masses[:, None] * self.positions).sum(axis=0) / total
 
+    def clone(self):
+        """``System: Clone``: per-particle arrays and topology are copied, potentials are shared, and the copy gets
+        its own device state on first use."""
+        import copy
+
+        device, self._device = self._device, None
+        try:
+            other = copy.deepcopy(self)
+        finally:
+            self._device = device
+        return other
+
     def invalidate(self):
         """Call after writing into ``charges``, ``masses`` or ``kinds`` in place (positions and velocities are
         re-read at every evaluation; the other per-particle vectors are cached on the device)."""
