@@ -78,6 +78,29 @@ impl DeviceSystem {
     }
 }
 
+/// Monte Carlo: what `EnergyCache::move_molecule_cost` (sys/cache.rs:145-213) becomes.  The N x N `pairs_cache`
+/// and the `Ewald::updater` closure disappear: the resident positions and rho(k) are the cache, and
+/// `EnergyCache::update` (cache.rs:119-128) accepts the pending trial on the device.
+impl DeviceSystem {
+    /// `system` still holds the old positions; they are the resident ones (no upload here).
+    pub fn move_molecule_cost(&mut self, molecule_id: usize, new_positions: &[Vector3D]) -> (f64, f64) {
+        let ctx = *self.ctx.lock().unwrap();
+        let mut cost = lumol_cuda_energy::default();
+        check(ctx, unsafe {
+            lumol_cuda_move_molecule_cost(ctx, molecule_id as i64, new_positions.as_ptr() as *const f64, &mut cost)
+        });
+        // (pairs_delta, coulomb_delta) of cache.rs:171-178
+        (cost.pairs, cost.coulomb_real + cost.coulomb_kspace)
+    }
+
+    /// `cache.pairs += pairs_delta; cache.coulomb += coulomb_delta; coulomb.update()` (cache.rs:175-211): the host
+    /// sums are updated by the caller, positions and rho(k) here.
+    pub fn accept_move(&mut self) {
+        let ctx = *self.ctx.lock().unwrap();
+        check(ctx, unsafe { lumol_cuda_move_molecule_accept(ctx, 0) });
+    }
+}
+
 impl Drop for DeviceSystem {
     fn drop(&mut self) {
         unsafe { lumol_cuda_destroy(*self.ctx.lock().unwrap()) };

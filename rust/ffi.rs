@@ -88,6 +88,14 @@ extern "C" {
     ) -> i32;
     pub fn lumol_cuda_kinetic_energy(ctx: *mut lumol_cuda_context, kinetic: *mut f64) -> i32;
     pub fn lumol_cuda_kinetic_tensor(ctx: *mut lumol_cuda_context, tensor: *mut f64) -> i32;
+    pub fn lumol_cuda_move_molecule_cost(
+        ctx: *mut lumol_cuda_context, molecule: i64, new_positions: *const f64, cost: *mut lumol_cuda_energy,
+    ) -> i32;
+    pub fn lumol_cuda_move_molecules_cost(
+        ctx: *mut lumol_cuda_context, ntrials: i64, molecules: *const i64, new_positions: *const f64,
+        costs: *mut lumol_cuda_energy,
+    ) -> i32;
+    pub fn lumol_cuda_move_molecule_accept(ctx: *mut lumol_cuda_context, trial: i64) -> i32;
     pub fn lumol_cuda_md_setup(ctx: *mut lumol_cuda_context, integrator: i32, timestep: f64) -> i32;
     pub fn lumol_cuda_md_set_degrees_of_freedom(ctx: *mut lumol_cuda_context, mode: i32, frozen: i64) -> i32;
     pub fn lumol_cuda_md_set_thermostat(ctx: *mut lumol_cuda_context, thermostat: i32, temperature: f64, parameter: f64) -> i32;
