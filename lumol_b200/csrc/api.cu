@@ -98,7 +98,7 @@ extern "C" int32_t lumol_cuda_destroy(lumol_cuda_context* ctx) {
     c->angles.release(); c->dihedrals.release(); c->kindex.release(); c->kenergy.release(); c->kvirial.release();
     c->rho.release(); c->rho_partial.release(); c->cell_of.release(); c->cell_count.release();
     c->cell_start.release(); c->order.release(); c->sorted_pos.release(); c->sorted_f32.release(); c->sorted_info.release();
-    c->krows.release(); c->kgmat.release(); c->kforce_partial.release();
+    c->krows.release(); c->kgmat.release(); c->kforce_partial.release(); c->kxy_scratch.release();
     c->sorted_cell.release(); c->cell_needed.release(); c->frame_pos.release(); c->blk_runs.release(); c->blk_header.release(); c->blk_entries.release(); c->self_local.release();
     c->nl_flags.release(); c->nlist.release(); c->ncount.release(); c->xref.release(); c->rel0.release();
     c->scan_scratch.release(); c->partials.release(); c->reduce_scratch.release(); c->results.release();

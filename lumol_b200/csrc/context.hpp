@@ -159,6 +159,7 @@ struct Context {
     bool krows_regular = false;
     int kspace_algorithm = -1;       // -1 automatic, 0 direct kernels, 1 tiled kernels
     DeviceBuffer<double> kgmat, kforce_partial;
+    DeviceBuffer<double2> kxy_scratch;  // e_x | e_y phase tables of the resident blocks of the tiled force kernel (large kmax)
     double kbasis[9] = {0};  // k_vector of the three unit indices, one per row
     uint64_t ewald_table_version = 0;  // bumped whenever ewald_prepare rebuilds the factor table
     // rho(k) on the device describes the resident positions iff these match positions_epoch / ewald_table_version

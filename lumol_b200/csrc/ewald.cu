@@ -642,6 +642,7 @@ constexpr int TF_TA = 4;          // atoms per thread
 constexpr int TF_TR = 4;          // rows per thread: 12 LDS.128 per 136 FP64 instructions and |l| step
 constexpr int TF_ROW_GROUPS = 8;  // thread rows
 constexpr int TF_ROWS = TF_ROW_GROUPS * TF_TR;  // rows per staged tile: 32
+static_assert(TF_ROWS == 32, "the first warp of the tiled force kernel loads one row per lane");
 
 struct TiledForceArgs {
     const double* __restrict__ pos;
@@ -655,149 +656,174 @@ struct TiledForceArgs {
     const double* __restrict__ gmat;
     double* __restrict__ force;    // nsplit == 1: accumulated directly
     double* __restrict__ partial;  // nsplit > 1: [split][owned atom][3] (sum_h, sum_k, sum_l), reduced afterwards
+    double2* xy_scratch;           // XY_GLOBAL: per block, e_x | e_y tables of its atom tile ((kmax + 1) x TF_ATOMS each)
 };
 
 // Shared: tables [axis][m][atom] (3 x (kmax + 1) x TF_ATOMS complex) + G tile (TF_ROWS x (kmax + 1) x 4 doubles).
-// TF_ATOMS atoms per block (64, or 32 when kmax is large), TF_ATOMS / TF_TA x TF_ROW_GROUPS threads.
-template <int TF_ATOMS>
+// TF_ATOMS atoms per tile, TF_ATOMS / TF_TA x TF_ROW_GROUPS threads.  XY_GLOBAL (large kmax): only the e_z table,
+// which the inner loop streams, stays in shared memory; e_x and e_y, read once per row and atom in the epilogue of a
+// row tile, live in a per-block scratch in global memory (L2-resident), so that two blocks of 64 atoms still fit on
+// an SM at kmax = 54 (a 1M-atom SPC/E box) where three tables allowed one block of 32 atoms, i.e. two warps per SM.
+// A block walks the atom tiles blockIdx.x, blockIdx.x + gridDim.x, ... (one tile per block unless XY_GLOBAL).
+template <int TF_ATOMS, bool XY_GLOBAL>
 __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_tiled_kernel(TiledForceArgs a) {
     constexpr int TF_THREADS = TF_ATOMS / TF_TA * TF_ROW_GROUPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lp = a.kmax + 1;
     double2* table = reinterpret_cast<double2*>(smem_raw);
-    double* gtile = reinterpret_cast<double*>(table + (size_t)3 * lp * TF_ATOMS);
+    double* gtile = reinterpret_cast<double*>(table + (size_t)(XY_GLOBAL ? 1 : 3) * lp * TF_ATOMS);
     const int gstride = lp * 4 + 4;  // doubles per row of the staged G tile: neighbouring rows in different banks
     __shared__ KRow s_rows[TF_ROWS];
+    __shared__ int s_mend;
+    // e_x | e_y of this block's atom tile: in shared memory, or in this block's slice of the global scratch (plain
+    // loads and stores: written and read by the same block on either side of a barrier)
+    double2* xy = XY_GLOBAL ? a.xy_scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * lp * TF_ATOMS : table;
+    double2* ez_table = XY_GLOBAL ? table : table + (size_t)2 * lp * TF_ATOMS;
 
     const int t = threadIdx.x;
-    const int base = a.a_lo + blockIdx.x * TF_ATOMS;
-    const int count = min(TF_ATOMS, a.a_hi - base);
-    for (int w = t; w < 3 * TF_ATOMS; w += TF_THREADS) {
-        const int atom = w % TF_ATOMS, axis = w / TF_ATOMS;
-        const int i = base + min(atom, count - 1);
-        const double phase = a.basis.b[3 * axis] * a.pos[3 * i] + a.basis.b[3 * axis + 1] * a.pos[3 * i + 1] +
-                             a.basis.b[3 * axis + 2] * a.pos[3 * i + 2];
-        double sn, cs;
-        sincos(phase, &sn, &cs);
-        double2* column = table + (size_t)axis * lp * TF_ATOMS + atom;
-        const double2 e1 = make_double2(cs, sn);
-        double2 e = make_double2(1.0, 0.0);
-        column[0] = e;
-        if (a.kmax >= 1) {
-            e = e1;
-            column[TF_ATOMS] = e;
-        }
-        for (int m = 2; m <= a.kmax; m++) {
-            e = cmul(e, e1);
-            column[(size_t)m * TF_ATOMS] = e;
-        }
-    }
-
     // thread (ag, rg) owns atoms ag + x * AG and rows rg + r * TF_ROW_GROUPS: for a given x the threads of a warp
     // read consecutive 16-byte words of the phase tables
     constexpr int AG = TF_ATOMS / TF_TA;
     const int ag = t % AG, rg = t / AG;
-    double sh[TF_TA], sk[TF_TA], sl[TF_TA];
-#pragma unroll
-    for (int x = 0; x < TF_TA; x++) sh[x] = sk[x] = sl[x] = 0.0;
-
     // rows of this block: [row_lo, row_hi), walked in tiles of TF_ROWS
     const int rows_per_split = ((a.nrows + a.nsplit - 1) / a.nsplit + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
     const int row_lo = blockIdx.y * rows_per_split;
     const int row_hi = min(a.nrows, row_lo + rows_per_split);
-    const double2* ez = table + (size_t)2 * lp * TF_ATOMS + ag;
-    for (int tile = row_lo; tile < row_hi; tile += TF_ROWS) {
-        __syncthreads();
-        const int nrows = min(TF_ROWS, row_hi - tile);
-        {
-            const double* src = a.gmat + (size_t)tile * lp * 4;
-            for (int w = t; w < TF_ROWS * lp * 4; w += TF_THREADS) {
-                const int r = w / (lp * 4), c = w - r * (lp * 4);
-                gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
+    const int natiles = (a.a_hi - a.a_lo + TF_ATOMS - 1) / TF_ATOMS;
+
+    for (int atile = blockIdx.x; atile < natiles; atile += gridDim.x) {
+        const int base = a.a_lo + atile * TF_ATOMS;
+        const int count = min(TF_ATOMS, a.a_hi - base);
+        __syncthreads();  // the sums of the previous atom tile were read from the memory of the tables
+        for (int w = t; w < 3 * TF_ATOMS; w += TF_THREADS) {
+            const int atom = w % TF_ATOMS, axis = w / TF_ATOMS;
+            const int i = base + min(atom, count - 1);
+            const double phase = a.basis.b[3 * axis] * a.pos[3 * i] + a.basis.b[3 * axis + 1] * a.pos[3 * i + 1] +
+                                 a.basis.b[3 * axis + 2] * a.pos[3 * i + 2];
+            double sn, cs;
+            sincos(phase, &sn, &cs);
+            double2* column = (axis == 2 ? ez_table : xy + (size_t)axis * lp * TF_ATOMS) + atom;
+            const double2 e1 = make_double2(cs, sn);
+            double2 e = make_double2(1.0, 0.0);
+            column[0] = e;
+            if (a.kmax >= 1) {
+                e = e1;
+                column[TF_ATOMS] = e;
             }
-            if (t < TF_ROWS) {
+            for (int m = 2; m <= a.kmax; m++) {
+                e = cmul(e, e1);
+                column[(size_t)m * TF_ATOMS] = e;
+            }
+        }
+
+        double sh[TF_TA], sk[TF_TA], sl[TF_TA];
+#pragma unroll
+        for (int x = 0; x < TF_TA; x++) sh[x] = sk[x] = sl[x] = 0.0;
+
+        const double2* ez = ez_table + ag;
+        for (int tile = row_lo; tile < row_hi; tile += TF_ROWS) {
+            __syncthreads();
+            const int nrows = min(TF_ROWS, row_hi - tile);
+            if (t < TF_ROWS) {  // exactly the first warp
                 KRow row;
                 row.h = row.k = row.base = 0;
                 row.l_lo_hi = 1;
-                if (t < nrows) row = a.rows[tile + t];
+                int reach = 0;
+                if (t < nrows) {
+                    row = a.rows[tile + t];
+                    const int l_lo = (int)(short)(row.l_lo_hi & 0xffff), l_hi = row.l_lo_hi >> 16;
+                    reach = max(abs(l_lo), abs(l_hi));
+                }
                 s_rows[t] = row;
+                // |l| beyond the reach of every row of the tile multiplies zeros of the G matrix: not visited
+                reach = __reduce_max_sync(0xffffffffu, reach);
+                if (t == 0) s_mend = min(lp, reach + 1);
             }
-        }
-        __syncthreads();
-        double w0[TF_TR][TF_TA][2], w1[TF_TR][TF_TA][2];
-#pragma unroll
-        for (int r = 0; r < TF_TR; r++)
-#pragma unroll
-            for (int x = 0; x < TF_TA; x++) w0[r][x][0] = w0[r][x][1] = w1[r][x][0] = w1[r][x][1] = 0.0;
-        const double* g0 = gtile + (size_t)rg * gstride;
-        for (int m = 0; m < lp; m++) {
-            double2 z[TF_TA], zl[TF_TA];
-            const double weight = (double)m;
-#pragma unroll
-            for (int x = 0; x < TF_TA; x++) {
-                z[x] = ez[(size_t)m * TF_ATOMS + x * AG];
-                zl[x] = make_double2(weight * z[x].x, weight * z[x].y);
+            __syncthreads();
+            const int mend = s_mend;
+            {
+                const double* src = a.gmat + (size_t)tile * lp * 4;
+                for (int w = t; w < TF_ROWS * lp * 4; w += TF_THREADS) {
+                    const int r = w / (lp * 4), c = w - r * (lp * 4);
+                    if (c < mend * 4) gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
+                }
             }
+            __syncthreads();
+            double w0[TF_TR][TF_TA][2], w1[TF_TR][TF_TA][2];
 #pragma unroll
-            for (int r = 0; r < TF_TR; r++) {
-                // S.re, S.im, D.re, D.im
-                const double4 g = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 4);
+            for (int r = 0; r < TF_TR; r++)
+#pragma unroll
+                for (int x = 0; x < TF_TA; x++) w0[r][x][0] = w0[r][x][1] = w1[r][x][0] = w1[r][x][1] = 0.0;
+            const double* g0 = gtile + (size_t)rg * gstride;
+            for (int m = 0; m < mend; m++) {
+                double2 z[TF_TA], zl[TF_TA];
+                const double weight = (double)m;
 #pragma unroll
                 for (int x = 0; x < TF_TA; x++) {
-                    w0[r][x][0] = fma(z[x].x, g.x, fma(-z[x].y, g.w, w0[r][x][0]));
-                    w0[r][x][1] = fma(z[x].x, g.y, fma(z[x].y, g.z, w0[r][x][1]));
-                    w1[r][x][0] = fma(zl[x].x, g.z, fma(-zl[x].y, g.y, w1[r][x][0]));
-                    w1[r][x][1] = fma(zl[x].x, g.w, fma(zl[x].y, g.x, w1[r][x][1]));
+                    z[x] = ez[(size_t)m * TF_ATOMS + x * AG];
+                    zl[x] = make_double2(weight * z[x].x, weight * z[x].y);
+                }
+#pragma unroll
+                for (int r = 0; r < TF_TR; r++) {
+                    // S.re, S.im, D.re, D.im
+                    const double4 g = *reinterpret_cast<const double4*>(g0 + (size_t)r * TF_ROW_GROUPS * gstride + m * 4);
+#pragma unroll
+                    for (int x = 0; x < TF_TA; x++) {
+                        w0[r][x][0] = fma(z[x].x, g.x, fma(-z[x].y, g.w, w0[r][x][0]));
+                        w0[r][x][1] = fma(z[x].x, g.y, fma(z[x].y, g.z, w0[r][x][1]));
+                        w1[r][x][0] = fma(zl[x].x, g.z, fma(-zl[x].y, g.y, w1[r][x][0]));
+                        w1[r][x][1] = fma(zl[x].x, g.w, fma(zl[x].y, g.x, w1[r][x][1]));
+                    }
+                }
+            }
+            // Im(u W) with u = e_x(h) e_y(k)
+#pragma unroll
+            for (int r = 0; r < TF_TR; r++) {
+                const KRow row = s_rows[rg + r * TF_ROW_GROUPS];
+#pragma unroll
+                for (int x = 0; x < TF_TA; x++) {
+                    const double2 ex = xy[(size_t)row.h * TF_ATOMS + ag + x * AG];
+                    double2 ey = xy[(size_t)(lp + abs(row.k)) * TF_ATOMS + ag + x * AG];
+                    if (row.k < 0) ey.y = -ey.y;
+                    const double2 u = cmul(ex, ey);
+                    const double t0 = u.x * w0[r][x][1] + u.y * w0[r][x][0];
+                    const double t1 = u.x * w1[r][x][1] + u.y * w1[r][x][0];
+                    sh[x] = fma(t0, (double)row.h, sh[x]);
+                    sk[x] = fma(t0, (double)row.k, sk[x]);
+                    sl[x] += t1;
                 }
             }
         }
-        // Im(u W) with u = e_x(h) e_y(k)
+        // sum over the row groups of the block, in a fixed order (the phase tables are dead: reuse their memory)
+        __syncthreads();
+        double (*s_sum)[TF_ATOMS][3] = reinterpret_cast<double (*)[TF_ATOMS][3]>(smem_raw);
 #pragma unroll
-        for (int r = 0; r < TF_TR; r++) {
-            const KRow row = s_rows[rg + r * TF_ROW_GROUPS];
+        for (int x = 0; x < TF_TA; x++) {
+            s_sum[rg][ag + x * AG][0] = sh[x];
+            s_sum[rg][ag + x * AG][1] = sk[x];
+            s_sum[rg][ag + x * AG][2] = sl[x];
+        }
+        __syncthreads();
+        if (t < count) {
+            double th = 0.0, tk = 0.0, tl = 0.0;
 #pragma unroll
-            for (int x = 0; x < TF_TA; x++) {
-                const double2 ex = table[(size_t)row.h * TF_ATOMS + ag + x * AG];
-                double2 ey = table[(size_t)(lp + abs(row.k)) * TF_ATOMS + ag + x * AG];
-                if (row.k < 0) ey.y = -ey.y;
-                const double2 u = cmul(ex, ey);
-                const double t0 = u.x * w0[r][x][1] + u.y * w0[r][x][0];
-                const double t1 = u.x * w1[r][x][1] + u.y * w1[r][x][0];
-                sh[x] = fma(t0, (double)row.h, sh[x]);
-                sk[x] = fma(t0, (double)row.k, sk[x]);
-                sl[x] += t1;
+            for (int g = 0; g < TF_ROW_GROUPS; g++) {
+                th += s_sum[g][t][0];
+                tk += s_sum[g][t][1];
+                tl += s_sum[g][t][2];
             }
-        }
-    }
-    // sum over the row groups of the block, in a fixed order (the phase tables are dead: reuse their memory)
-    __syncthreads();
-    double (*s_sum)[TF_ATOMS][3] = reinterpret_cast<double (*)[TF_ATOMS][3]>(smem_raw);
-#pragma unroll
-    for (int x = 0; x < TF_TA; x++) {
-        s_sum[rg][ag + x * AG][0] = sh[x];
-        s_sum[rg][ag + x * AG][1] = sk[x];
-        s_sum[rg][ag + x * AG][2] = sl[x];
-    }
-    __syncthreads();
-    if (t < count) {
-        double th = 0.0, tk = 0.0, tl = 0.0;
-#pragma unroll
-        for (int g = 0; g < TF_ROW_GROUPS; g++) {
-            th += s_sum[g][t][0];
-            tk += s_sum[g][t][1];
-            tl += s_sum[g][t][2];
-        }
-        const int i = base + t;
-        if (a.nsplit == 1) {
-            const double scale = a.charge[i] / FOUR_PI_EPSILON_0;  // ewald.rs:716-718
-            a.force[3 * i] += scale * (th * a.basis.b[0] + tk * a.basis.b[3] + tl * a.basis.b[6]);
-            a.force[3 * i + 1] += scale * (th * a.basis.b[1] + tk * a.basis.b[4] + tl * a.basis.b[7]);
-            a.force[3 * i + 2] += scale * (th * a.basis.b[2] + tk * a.basis.b[5] + tl * a.basis.b[8]);
-        } else {
-            double* out = a.partial + ((size_t)blockIdx.y * (a.a_hi - a.a_lo) + (i - a.a_lo)) * 3;
-            out[0] = th;
-            out[1] = tk;
-            out[2] = tl;
+            const int i = base + t;
+            if (a.nsplit == 1) {
+                const double scale = a.charge[i] / FOUR_PI_EPSILON_0;  // ewald.rs:716-718
+                a.force[3 * i] += scale * (th * a.basis.b[0] + tk * a.basis.b[3] + tl * a.basis.b[6]);
+                a.force[3 * i + 1] += scale * (th * a.basis.b[1] + tk * a.basis.b[4] + tl * a.basis.b[7]);
+                a.force[3 * i + 2] += scale * (th * a.basis.b[2] + tk * a.basis.b[5] + tl * a.basis.b[8]);
+            } else {
+                double* out = a.partial + ((size_t)blockIdx.y * (a.a_hi - a.a_lo) + (i - a.a_lo)) * 3;
+                out[0] = th;
+                out[1] = tk;
+                out[2] = tl;
+            }
         }
     }
 }
@@ -850,9 +876,15 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
     const int row_groups = TK_THREADS / lq;
     const size_t rho_smem = rho_tables + (size_t)row_groups * TK_TR * TK_ATOMS * sizeof(double2);
     const size_t force_tables64 = (size_t)3 * (kmax + 1) * 64 * sizeof(double2), gtile = (size_t)TF_ROWS * ((kmax + 1) * 4 + 4) * sizeof(double);
+    // force kernel: three phase tables in shared memory (small kmax) or the e_z table alone (XY_GLOBAL)
+    const bool force_wide = force_tables64 + gtile <= 110 * 1024;
     const bool tiled_possible = ctx->krows_regular && kmax >= 8 && kmax <= 255 && rho_smem <= 200 * 1024 &&
-                                force_tables64 / 2 + gtile <= 200 * 1024;
-    bool tiled = tiled_possible && (ctx->kspace_algorithm == 1 || (ctx->kspace_algorithm < 0 && (int64_t)owned * nk >= (int64_t)1 << 24));
+                                (force_wide || force_tables64 / 3 + gtile + 1024 <= 226 * 1024);
+    // the direct force kernel holds the phase tables of 128 atoms: beyond kmax = 34 only the tiled kernels fit
+    const size_t direct_force_smem = (size_t)3 * (kmax + 1) * KFORCE_THREADS * sizeof(double2) +
+                                     KFORCE_STAGE * (sizeof(double2) + sizeof(double) + sizeof(short4));
+    bool tiled = tiled_possible && (ctx->kspace_algorithm == 1 ||
+                                    (ctx->kspace_algorithm < 0 && ((int64_t)owned * nk >= (int64_t)1 << 24 || direct_force_smem > 220 * 1024)));
     const bool tiled_forces = tiled && !req.molecular_virial;
 
     // ---- rho(k) ---------------------------------------------------------------------------------
@@ -971,16 +1003,20 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
                                                                            ctx->rho.ptr, ctx->kenergy.ptr, ctx->kgmat.ptr);
         ctx->launches++;
         LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
-        // 64 atoms per block when two blocks fit on an SM, 32 atoms for large kmax
-        const bool wide = force_tables64 + gtile <= 110 * 1024;
-        const int atoms = wide ? 64 : 32;
-        const size_t smem = force_tables64 / (wide ? 1 : 2) + gtile;
-        const int ablocks = (owned + atoms - 1) / atoms;
-        int nsplit = (2 * ctx->sm_count + ablocks - 1) / ablocks;
+        // small kmax: the three phase tables of 64 atoms in shared memory, two blocks per SM.  Large kmax: e_z only
+        // (e_x, e_y in a global scratch); blocks then walk the atom tiles.
+        const bool wide = force_wide;
+        const bool xy_global = !wide;
+        const int atoms = 64;
+        const size_t smem = wide ? force_tables64 + gtile : force_tables64 / 3 + gtile;
+        const int atiles = (owned + atoms - 1) / atoms;
+        int nsplit = (2 * ctx->sm_count + atiles - 1) / atiles;
         const int max_split = (nrows + TF_ROWS - 1) / TF_ROWS;
         if (nsplit > max_split) nsplit = max_split;
         if (nsplit > 64) nsplit = 64;
         if (nsplit < 1) nsplit = 1;
+        int ablocks = atiles;
+        if (xy_global && ablocks > 2 * ctx->sm_count) ablocks = 2 * ctx->sm_count;
         TiledForceArgs a;
         a.pos = ctx->position.ptr;
         a.charge = ctx->charge.ptr;
@@ -994,12 +1030,19 @@ int launch_ewald_kspace(Context* ctx, const ComputeRequest& req) {
         a.gmat = ctx->kgmat.ptr;
         a.force = ctx->force.ptr;
         a.partial = nullptr;
+        a.xy_scratch = nullptr;
         if (nsplit > 1) {
             LUMOL_CUDA_CHECK(ctx, ctx->kforce_partial.reserve((size_t)nsplit * owned * 3));
             a.partial = ctx->kforce_partial.ptr;
         }
-        const void* kernel = wide ? (const void*)ewald_force_tiled_kernel<64> : (const void*)ewald_force_tiled_kernel<32>;
+        if (xy_global) {
+            LUMOL_CUDA_CHECK(ctx, ctx->kxy_scratch.reserve((size_t)ablocks * nsplit * 2 * lp * atoms));
+            a.xy_scratch = ctx->kxy_scratch.ptr;
+        }
+        const void* kernel = wide ? (const void*)ewald_force_tiled_kernel<64, false> : (const void*)ewald_force_tiled_kernel<64, true>;
         LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // two blocks of 57 KB tables + 57 KB G tile at kmax = 54 need the whole 228 KB of the SM
+        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         {
             ScopedClock clock(ctx, &ctx->clk_kspace);
             void* params[] = {&a};

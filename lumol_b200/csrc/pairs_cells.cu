@@ -1024,8 +1024,8 @@ __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const Pai
 // General kernel (any potential, restrictions, Ewald real space / Wolf): every block uses the global format.
 // SPLIT threads (neighbouring lanes) share an atom and take every SPLIT-th word of its column: a 100k-atom water box
 // has only 3072 warps of one thread per atom, too few to hide the latency of the erfc / exp chains.
-template <int MODE, int SPLIT>
-__global__ void __launch_bounds__(NL_THREADS) list_force_kernel(ForceArgs a) {
+template <int MODE, int SPLIT, int MINB>
+__global__ void __launch_bounds__(NL_THREADS, MINB) list_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairParams* sp = reinterpret_cast<PairParams*>(smem_raw);
     __shared__ double offset64[27][3];  // (a, b, c) * edge for the 27 neighbour-cell offsets
@@ -1596,12 +1596,17 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     if (lj_only) {
         kernel = full ? (const void*)lj_force_kernel<NL_MODE_FULL> : (const void*)lj_force_kernel<NL_MODE_FORCES>;
     } else {
+        // forces-only evaluations (every MD step): experiment knob, four resident blocks per SM (128 registers)
+        static const bool capped = std::getenv("LUMOL_CUDA_LIST_MINBLOCKS4") != nullptr;
         if (split == 4) {
-            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 4> : (const void*)list_force_kernel<NL_MODE_FORCES, 4>;
+            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 4, 1>
+                          : (capped ? (const void*)list_force_kernel<NL_MODE_FORCES, 4, 4> : (const void*)list_force_kernel<NL_MODE_FORCES, 4, 1>);
         } else if (split == 2) {
-            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 2> : (const void*)list_force_kernel<NL_MODE_FORCES, 2>;
+            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 2, 1>
+                          : (capped ? (const void*)list_force_kernel<NL_MODE_FORCES, 2, 4> : (const void*)list_force_kernel<NL_MODE_FORCES, 2, 1>);
         } else {
-            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 1> : (const void*)list_force_kernel<NL_MODE_FORCES, 1>;
+            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 1, 1>
+                          : (capped ? (const void*)list_force_kernel<NL_MODE_FORCES, 1, 4> : (const void*)list_force_kernel<NL_MODE_FORCES, 1, 1>);
         }
     }
     if (smem > 40 * 1024) {

@@ -79,15 +79,20 @@ class DeviceSystem:
             self._check(lib.lumol_cuda_set_cell(ctx, _ffi.as_double_pointer(matrix), cell.shape()))
             self._synced_cell = cell_key
 
+        # arrays a device-resident MD run left newer on the device than on the host (md.py): never overwritten
+        # by the stale host copy; the host copy is refreshed by download()
+        resident = getattr(system, "_resident", None) or set()
         full = system._version != self._synced_version
         if full:
+            if resident and self._n == system.size():
+                self.download(system, positions="positions" in resident, velocities="velocities" in resident)
             self._upload_structure(system)
             self._synced_version = system._version
         else:
-            if positions:
+            if positions and "positions" not in resident:
                 array = np.ascontiguousarray(system.positions, dtype=np.float64)
                 self._check(lib.lumol_cuda_set_positions(ctx, _ffi.as_double_pointer(array)))
-            if velocities:
+            if velocities and "velocities" not in resident:
                 array = np.ascontiguousarray(system.velocities, dtype=np.float64)
                 self._check(lib.lumol_cuda_set_velocities(ctx, _ffi.as_double_pointer(array)))
 
@@ -247,14 +252,19 @@ class DeviceSystem:
         return tensor
 
     def download(self, system, positions=True, velocities=True):
+        resident = getattr(system, "_resident", None)
         if positions:
             array = np.zeros((self._n, 3))
             self._check(self.lib.lumol_cuda_get_positions(self.ctx, _ffi.as_double_pointer(array)))
             system.positions = array
+            if resident:
+                resident.discard("positions")
         if velocities:
             array = np.zeros((self._n, 3))
             self._check(self.lib.lumol_cuda_get_velocities(self.ctx, _ffi.as_double_pointer(array)))
             system.velocities = array
+            if resident:
+                resident.discard("velocities")
 
     def stats(self):
         stats = _ffi.Stats()

@@ -247,6 +247,8 @@ class MolecularDynamics:
             _ffi.check(ctx, lib.lumol_cuda_get_cell(ctx, _ffi.as_double_pointer(matrix)))
             system.cell = type(system.cell)(matrix, system.cell.shape())  # scale_mut keeps the shape (cells.rs:203-207)
             device._synced_cell = (system.cell.shape(), system.cell.matrix().tobytes())
+        # positions and velocities are now newer on the device than in the host arrays
+        system._resident = {"positions", "velocities"}
         if download:
             device.download(system)
             # the host arrays now equal the device state: keep the device copy authoritative
@@ -254,14 +256,42 @@ class MolecularDynamics:
 
 
 class Simulation:
-    """``Simulation::run`` (lumol-sim/src/simulations.rs:69-101) for an MD propagator."""
+    """``Simulation`` (lumol-sim/src/simulations.rs:52-125) for an MD propagator.  Between two output steps the
+    propagator keeps positions, velocities and forces on the device; an output reads what it needs from the resident
+    state (output.py), and the host arrays are refreshed once, when the run ends."""
 
     def __init__(self, propagator):
         self.propagator = propagator
+        self.outputs = []
+
+    def add_output(self, output):
+        """simulations.rs:104-106"""
+        self.add_output_with_frequency(output, 1)
+
+    def add_output_with_frequency(self, output, frequency):
+        """simulations.rs:111-113: ``output`` is written every time ``system.step`` is a multiple of ``frequency``."""
+        if frequency < 1:
+            raise ValueError("the output frequency must be at least 1")
+        self.outputs.append((output, int(frequency)))
 
     def run(self, system, nsteps):
+        """simulations.rs:69-101"""
         self.propagator.setup(system)
-        self.propagator.propagate(system, nsteps)
+        for output, _ in self.outputs:
+            output.setup(system)
+        done = 0
+        while done < nsteps:
+            block = nsteps - done
+            for _, frequency in self.outputs:
+                block = min(block, frequency - system.step % frequency)
+            self.propagator.propagate(system, block, download=False)
+            done += block
+            for output, frequency in self.outputs:
+                if system.step % frequency == 0:
+                    output.write(system)
+        for output, _ in self.outputs:
+            output.finish(system)
+        system.sync_from_device()
 
 
 def forces_to_host(device, n):

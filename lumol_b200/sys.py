@@ -82,6 +82,22 @@ class UnitCell:
     def c(self):
         return float(np.linalg.norm(self._matrix[:, 2])) if self._shape == _ffi.CELL_TRICLINIC else float(self._matrix[2, 2])
 
+    def _angle(self, u, v):
+        """cells.rs:149-182: 90 for orthorhombic and infinite cells, else the angle of two cell vectors in degrees."""
+        if self._shape != _ffi.CELL_TRICLINIC:
+            return 90.0
+        cosine = float(np.dot(u, v) / (np.linalg.norm(u) * np.linalg.norm(v)))
+        return math.degrees(math.acos(max(-1.0, min(1.0, cosine))))
+
+    def alpha(self):
+        return self._angle(self._matrix[:, 1], self._matrix[:, 2])
+
+    def beta(self):
+        return self._angle(self._matrix[:, 0], self._matrix[:, 2])
+
+    def gamma(self):
+        return self._angle(self._matrix[:, 0], self._matrix[:, 1])
+
     def lengths(self):
         """Distances between opposite faces (cells.rs:134-146)."""
         if self.is_infinite():
@@ -279,6 +295,7 @@ class System:
         self.step = 0
         self._device = None
         self._version = 0  # bumped by every structural change, so the device state is rebuilt
+        self._resident = set()  # "positions" / "velocities" while the device copy is newer than the host arrays
 
     @classmethod
     def with_cell(cls, cell):
@@ -480,12 +497,19 @@ class System:
         its own device state on first use."""
         import copy
 
+        self.sync_from_device()
         device, self._device = self._device, None
         try:
             other = copy.deepcopy(self)
         finally:
             self._device = device
         return other
+
+    def sync_from_device(self):
+        """Refresh ``positions`` / ``velocities`` after device-resident steps (``propagate(..., download=False)``);
+        a no-op when the host arrays are current."""
+        if self._device is not None and self._resident:
+            self._device.download(self, positions="positions" in self._resident, velocities="velocities" in self._resident)
 
     def invalidate(self):
         """Call after writing into ``charges``, ``masses`` or ``kinds`` in place (positions and velocities are

@@ -577,6 +577,36 @@ def test_tiled_kspace_kernels_vs_oracle_and_direct():
     check_system(system)
 
 
+def test_tiled_kspace_kernels_large_kmax():
+    """kmax above 26: the tiled force kernel keeps only the e_z phase table in shared memory and e_x, e_y in its
+    global scratch (kmax = 54 is what Ewald::with_accuracy(9 A, 1e-5) gives a 1M-atom SPC/E box).  kmax 30 on a box
+    where every block walks several atom tiles and several row splits; kmax 60 on a small one."""
+    for n_side, kmax, alpha in ((10, 30, 0.45), (6, 60, 0.6)):
+        # kmax 60 exceeds what the direct force kernel holds in shared memory: the automatic choice is the tiled one
+        system = systems.spce_box(n_side)
+        ewald = lumol.SharedEwald(lumol.Ewald(9.0, kmax, alpha))
+        ewald.set_restriction(lumol.PairRestriction.InterMolecular)
+        system.set_coulomb_potential(ewald)
+        device = device_for(system)
+        device.set_kspace_algorithm(1 if kmax == 30 else -1)
+        reference = oracle.OracleSystem(system)
+        tiled = device.compute(forces=True, energy=True, virial=True, parts=_ffi.PART_COULOMB)
+        assert_forces(tiled.forces, reference.coulomb_forces())
+        assert_energy_terms(tiled.energy, ewald_only_terms(reference))
+        assert_virial(tiled.virial, reference.coulomb_atomic_virial())
+        if kmax == 30:
+            device.set_kspace_algorithm(0)
+            direct = device.compute(forces=True, parts=_ffi.PART_COULOMB)
+            assert np.abs(tiled.forces - direct.forces).max() < 1e-11 * np.abs(direct.forces).max()
+
+
+def ewald_only_terms(reference):
+    terms = reference.energy_terms()
+    for name in ("pairs", "pairs_tail", "bonds", "angles", "dihedrals"):
+        setattr(terms, name, 0.0)
+    return terms
+
+
 # ---- kinetic estimators ----------------------------------------------------------------------------------------------
 
 def test_kinetic_estimators():
