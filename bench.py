@@ -451,6 +451,10 @@ def measure(args, env, workload, lattice_text, steps, warmup, with_e2e, with_cpu
             "kernel": "ewald_rho_tiled_kernel + ewald_force_tiled_kernel", "bound": "fp64", "achieved": achieved,
             "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": achieved / fp64_peak.value, "peak_source": fp64_source,
             "nkvectors": nk, "rho_plus_force_ms": total_ms, "algorithmic_flop_per_evaluation": flops,
+            "note": "algorithmic count of SURVEY 8d (16 + 21 FLOP per atom-k pair, the reference's arithmetic); the tiled "
+                    "kernels share the +l/-l products (2 + 4 DFMA per pair = 12 FLOP issued) and skip |l| outside the "
+                    "k sphere, so frac can exceed 1; the FP64 pipe is 44-48 % busy (profiles/r1z_ewald_kernels_*_metrics.csv)",
+            "issued_frac": achieved / fp64_peak.value * 12.0 / (FLOP_PER_ATOM_K_RHO + FLOP_PER_ATOM_K_FORCE),
             "traffic": (traffic.get(f"ewald_kspace:{workload}:{n}") or {}).get("bytes"),
             "traffic_source": (traffic.get(f"ewald_kspace:{workload}:{n}") or {}).get("source"),
         }

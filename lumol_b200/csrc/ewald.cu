@@ -15,6 +15,7 @@
 #include "context.hpp"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace lumol {
 
@@ -724,6 +725,13 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
         for (int tile = row_lo; tile < row_hi; tile += TF_ROWS) {
             __syncthreads();
             const int nrows = min(TF_ROWS, row_hi - tile);
+            {
+                const double* src = a.gmat + (size_t)tile * lp * 4;
+                for (int w = t; w < TF_ROWS * lp * 4; w += TF_THREADS) {
+                    const int r = w / (lp * 4), c = w - r * (lp * 4);
+                    gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
+                }
+            }
             if (t < TF_ROWS) {  // exactly the first warp
                 KRow row;
                 row.h = row.k = row.base = 0;
@@ -741,14 +749,6 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
             }
             __syncthreads();
             const int mend = s_mend;
-            {
-                const double* src = a.gmat + (size_t)tile * lp * 4;
-                for (int w = t; w < TF_ROWS * lp * 4; w += TF_THREADS) {
-                    const int r = w / (lp * 4), c = w - r * (lp * 4);
-                    if (c < mend * 4) gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
-                }
-            }
-            __syncthreads();
             double w0[TF_TR][TF_TA][2], w1[TF_TR][TF_TA][2];
 #pragma unroll
             for (int r = 0; r < TF_TR; r++)
