@@ -91,6 +91,14 @@ def main():
     synthetic.maxwell_boltzmann(tiled, 300.0, seed=5)
     check("spce-3000 (tiled k-space kernels)", tiled, rank, world, local_rank, kspace=1)
 
+    # kmax above 26: the tiled force kernel keeps e_x, e_y in its global scratch and walks atom tiles
+    large = synthetic.spce_box(10, flexible=True)
+    ewald = lumol.SharedEwald(lumol.Ewald(9.0, 30, 0.45))
+    ewald.set_restriction(lumol.PairRestriction.InterMolecular)
+    large.set_coulomb_potential(ewald)
+    synthetic.maxwell_boltzmann(large, 300.0, seed=5)
+    check("spce-3000 (tiled k-space kernels, kmax 30)", large, rank, world, local_rank, kspace=1)
+
     nacl = systems.md_nacl("wolf")
     nacl.positions += np.random.Generator(np.random.PCG64(9)).uniform(-0.2, 0.2, nacl.positions.shape)  # perfect lattice: zero forces
     synthetic.maxwell_boltzmann(nacl, 300.0, seed=6)
