@@ -693,9 +693,7 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
     if (req.molecular_virial && c->nranks > 1) {
         return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the molecular virial is evaluated on a single GPU only");
     }
-    if (req.forces && forces == nullptr && false) {
-        return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null forces");
-    }
+    // forces == NULL with LUMOL_CUDA_FORCES is allowed: the forces stay on the device (lumol_cuda_get_forces)
 
     int status = evaluate_forces_device(c, req);
     if (status) return status;
