@@ -940,8 +940,14 @@ int64_t orc_pair_forces_sample(const orc_system* s, int64_t nrows, const int64_t
     geom_t g;
     geom_init(&g, s->cell, s->shape);
     int64_t n = s->n;
-    thread_vec_t tv;
-    thread_vec_init(&tv, 3 * n);
+    /* The per-thread buffers (ThreadLocalVec, threads x 3N doubles) are set up once per full evaluation in the
+     * reference; a sample of a few rows must not pay for them at every call (400 MB of page faults against a few
+     * milliseconds of pair visits), so they are kept between calls.  Their content is never read back here. */
+    static thread_vec_t tv = {0, 0, NULL};
+    if (tv.data == NULL || tv.nthreads != max_threads() || tv.n3 != 3 * n) {
+        free(tv.data);
+        thread_vec_init(&tv, 3 * n);
+    }
     int64_t inside = 0;
     double sum = 0.0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : inside, sum)
@@ -976,7 +982,6 @@ int64_t orc_pair_forces_sample(const orc_system* s, int64_t nrows, const int64_t
         }
         sum += fabs(force_i[0]) + fabs(force_i[1]) + fabs(force_i[2]);
     }
-    free(tv.data);
     if (checksum) *checksum = sum;
     return inside;
 }
