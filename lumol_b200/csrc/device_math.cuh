@@ -247,6 +247,32 @@ __device__ __forceinline__ void wolf_pair(const CoulombView& c, double qiqj, dou
     force_over_r = qiqj * (factor - c.wolf_force_constant) / (r * FOUR_PI_EPSILON_0);
 }
 
+// The same two terms with 1 / r supplied by the caller (one rsqrt of r^2 instead of a square root and three
+// divisions per pair; constants folded).  Used by the neighbour-list kernel, where the pair rate matters; results
+// differ from the divisions above in the last bit or two.
+constexpr double INV_FOUR_PI_EPSILON_0 = 1.0 / FOUR_PI_EPSILON_0;
+
+__device__ __forceinline__ void ewald_real_pair_rinv(const CoulombView& c, bool excluded, double qiqj, double r, double rinv,
+                                                     double& energy, double& force_over_r) {
+    const double ar = c.alpha * r;
+    const double gauss = c.alpha * FRAC_2_SQRT_PI * exp(-ar * ar);
+    const double q = qiqj * INV_FOUR_PI_EPSILON_0;
+    // excluded pairs: -erf(ar) / r = (erfc(ar) - 1) / r (ewald.rs:395-399, 419-425)
+    const double e = (excluded ? -erf(ar) : erfc(ar)) * rinv;
+    energy = q * e;
+    force_over_r = q * (rinv * rinv) * (gauss + e);
+}
+
+__device__ __forceinline__ void wolf_pair_rinv(const CoulombView& c, double qiqj, double r, double rinv, double& energy,
+                                               double& force_over_r) {
+    const double ar = c.alpha * r;
+    const double ec = erfc(ar);
+    const double q = qiqj * INV_FOUR_PI_EPSILON_0;
+    energy = q * (ec * rinv - c.wolf_energy_constant);
+    const double factor = ec * (rinv * rinv) + c.alpha * FRAC_2_SQRT_PI * exp(-ar * ar) * rinv;
+    force_over_r = q * (factor - c.wolf_force_constant) * rinv;
+}
+
 // ------------------------------------------------------------------------------------------------
 // reductions: warp shuffle, then one shared-memory pass, then per-block partials that a second
 // kernel sums in a fixed order, so results do not depend on scheduling.

@@ -901,7 +901,9 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
     const double r2 = dx * dx + dy * dy + dz * dz;
     const bool count = s_j > s_i;
     if (!(r2 < a.cutoff2 * 1.0000000001)) return;
-    const double r = sqrt(r2);
+    // one reciprocal square root serves the distance, f / r and the coulomb terms (no division in the pair loop)
+    const double rinv = rsqrt(r2);
+    const double r = r2 * rinv;
     const int4 info_j = a.sorted_info[s_j];
     const bool same_molecule = info_i.y == info_j.y;
     const unsigned bits = same_molecule ? a.bond_dist[info_i.z + (info_j.w - info_j.y)] : 0u;
@@ -912,7 +914,7 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
             if (!restriction_excluded(pp.restriction, bits, pp.scale14, scaling)) {
                 double e, f;
                 pair_eval(pp, a.tables, a.table_energy, a.table_force, r, e, f);
-                const double fr = scaling * f / r;
+                const double fr = scaling * f * rinv;
                 fx += fr * dx;
                 fy += fr * dy;
                 fz += fr * dz;
@@ -937,9 +939,9 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
             double e = 0.0, fr = 0.0;
             bool active = true;
             if (a.coulomb.kind == 1) {
-                ewald_real_pair(a.coulomb, excluded, qi * qj, r, e, fr);
+                ewald_real_pair_rinv(a.coulomb, excluded, qi * qj, r, rinv, e, fr);
             } else if (!excluded) {
-                wolf_pair(a.coulomb, qi * qj, r, e, fr);
+                wolf_pair_rinv(a.coulomb, qi * qj, r, rinv, e, fr);
                 e *= scaling;
                 fr *= scaling;
             } else {
