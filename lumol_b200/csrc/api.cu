@@ -368,8 +368,10 @@ extern "C" int32_t lumol_cuda_set_pairs(lumol_cuda_context* ctx, int32_t nkinds,
     c->max_pair_cutoff = 0.0;
     c->any_pair = false;
     bool single_lj = count > 0;
+    bool simple_pairs = true;
     for (size_t k = 0; k < count; k++) {
         const lumol_cuda_pair& p = pairs[k];
+        if (p.potential > LUMOL_CUDA_POTENTIAL_HARMONIC) simple_pairs = false;  // anything with exp, pow or a table
         if (p.potential < LUMOL_CUDA_POTENTIAL_ABSENT || p.potential > LUMOL_CUDA_POTENTIAL_TABLE ||
             p.potential == LUMOL_CUDA_POTENTIAL_COSINE_HARMONIC || p.potential == LUMOL_CUDA_POTENTIAL_TORSION) {
             return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "pair entry %zu: potential %d is not a pair potential", k, p.potential);
@@ -403,6 +405,7 @@ extern "C" int32_t lumol_cuda_set_pairs(lumol_cuda_context* ctx, int32_t nkinds,
         }
     }
     c->single_lj = single_lj;
+    c->simple_pairs = simple_pairs;
     c->nkinds = nkinds;
     c->structure_generation++;
     c->host_pairs.assign(pairs, pairs + count);

@@ -131,6 +131,7 @@ struct Context {
     double max_pair_cutoff = 0.0;
     bool any_pair = false;
     bool single_lj = false;  // every present pair is plain LJ with restriction None: fast path
+    bool simple_pairs = false;  // every entry is absent, null, LJ or harmonic: the list kernel drops the other closed forms
     std::vector<TableDesc> host_tables;
     std::vector<double> host_table_energy, host_table_force;
     DeviceBuffer<TableDesc> tables;

@@ -185,6 +185,27 @@ __device__ __forceinline__ void pair_eval(const PairParams& pp, const TableDesc*
     energy -= pp.shift;
 }
 
+// The same for pair tables that only hold Lennard-Jones, harmonic and null entries (water models, ionic crystals
+// with LJ pairs): without the exp / pow / table branches the neighbour-list kernel is a third smaller, and that kernel
+// waits on instruction fetch (profiles/r1y_list_force_kernel_spce98k_summary.csv).
+__device__ __forceinline__ void pair_eval_simple(const PairParams& pp, double r, double rinv, double& energy, double& force) {
+    if (pp.potential == LUMOL_CUDA_POTENTIAL_LJ) {  // functions.rs:80-88 with 1 / r supplied
+        const double s = pp.p[0] * rinv;
+        const double s2 = s * s;
+        const double s6 = s2 * (s2 * s2);
+        energy = 4.0 * pp.p[1] * (s6 * s6 - s6);
+        force = -24.0 * pp.p[1] * (s6 - 2.0 * (s6 * s6)) * rinv;
+    } else if (pp.potential == LUMOL_CUDA_POTENTIAL_HARMONIC) {  // functions.rs:136-143
+        const double dx = r - pp.p[1];
+        energy = 0.5 * pp.p[0] * dx * dx;
+        force = pp.p[0] * (pp.p[1] - r);
+    } else {
+        energy = 0.0;
+        force = 0.0;
+    }
+    energy -= pp.shift;
+}
+
 // ------------------------------------------------------------------------------------------------
 // restrictions (restrictions.rs:85-114).  `bits` is the BondDistances byte of the pair, or 0 when
 // the two atoms are in different molecules (BondPath::None).

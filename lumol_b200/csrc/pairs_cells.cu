@@ -892,7 +892,7 @@ __device__ __forceinline__ void evaluate_lj(const ForceArgs& a, double xi, doubl
 }
 
 // One listed neighbour, FP64: exact cut-off test and pair evaluation for the thread's atom.
-template <bool LJ_ONLY, int MODE>
+template <bool SIMPLE, int MODE>
 __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const PairParams* __restrict__ sp, double xi,
                                                   double yi, double zi, double qi, const int4& info_i, int s_i,
                                                   int s_j, const double4& pj, double& fx, double& fy, double& fz,
@@ -913,7 +913,11 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
             double scaling;
             if (!restriction_excluded(pp.restriction, bits, pp.scale14, scaling)) {
                 double e, f;
-                pair_eval(pp, a.tables, a.table_energy, a.table_force, r, e, f);
+                if (SIMPLE) {
+                    pair_eval_simple(pp, r, rinv, e, f);
+                } else {
+                    pair_eval(pp, a.tables, a.table_energy, a.table_force, r, e, f);
+                }
                 const double fr = scaling * f * rinv;
                 fx += fr * dx;
                 fy += fr * dy;
@@ -969,7 +973,7 @@ __device__ __forceinline__ void evaluate_neighbor(const ForceArgs& a, const Pair
 // Walk of a column in the global format: four entries (one 16-byte word) at a time.  Software pipeline, per
 // thread: the list word two iterations ahead and the four neighbour positions one iteration ahead are in flight
 // while the current four neighbours are evaluated.
-template <bool LJ_ONLY, int MODE>
+template <bool LJ_ONLY, int MODE, bool SIMPLE = false>
 __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const PairParams* sp, const double (*offset64)[3],
                                                    int s_i, const int4& info_i, double& fx, double& fy, double& fz,
                                                    double (&acc)[NL_NV], int part = 0, int nparts = 1) {
@@ -1012,7 +1016,7 @@ __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const Pai
             if (LJ_ONLY) {
                 evaluate_lj<MODE>(a, pi.x - ox, pi.y - oy, pi.z - oz, s_i, s_j, listed, pcur[t], fx, fy, fz, acc);
             } else if (listed) {
-                evaluate_neighbor<LJ_ONLY, MODE>(a, sp, pi.x - ox, pi.y - oy, pi.z - oz, pi.w, info_i, s_i, s_j,
+                evaluate_neighbor<SIMPLE, MODE>(a, sp, pi.x - ox, pi.y - oy, pi.z - oz, pi.w, info_i, s_i, s_j,
                                                  pcur[t], fx, fy, fz, acc);
             }
         }
@@ -1026,7 +1030,7 @@ __device__ __forceinline__ void walk_global_column(const ForceArgs& a, const Pai
 // General kernel (any potential, restrictions, Ewald real space / Wolf): every block uses the global format.
 // SPLIT threads (neighbouring lanes) share an atom and take every SPLIT-th word of its column: a 100k-atom water box
 // has only 3072 warps of one thread per atom, too few to hide the latency of the erfc / exp chains.
-template <int MODE, int SPLIT, int MINB>
+template <int MODE, int SPLIT, int MINB, bool SIMPLE>
 __global__ void __launch_bounds__(NL_THREADS, MINB) list_force_kernel(ForceArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairParams* sp = reinterpret_cast<PairParams*>(smem_raw);
@@ -1061,7 +1065,7 @@ __global__ void __launch_bounds__(NL_THREADS, MINB) list_force_kernel(ForceArgs 
         active = info_i.w >= a.o_lo && info_i.w < a.o_hi;
     }
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (active) walk_global_column<false, MODE>(a, sp, offset64, s_i, info_i, fx, fy, fz, acc, part, SPLIT);
+    if (active) walk_global_column<false, MODE, SIMPLE>(a, sp, offset64, s_i, info_i, fx, fy, fz, acc, part, SPLIT);
 #pragma unroll
     for (int o = 1; o < SPLIT; o <<= 1) {
         fx += __shfl_xor_sync(0xffffffffu, fx, o);
@@ -1600,13 +1604,21 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     } else {
         // forces-only evaluations (every MD step) are capped at 128 registers: four resident blocks per SM instead
         // of three hide more of the erfc / exp latency (1.42 -> 1.33 ms on the 98k-atom SPC/E box, 64 bytes of spills)
+        // SIMPLE: pair tables of Lennard-Jones / harmonic / null entries only (smaller kernel); experiment knob to
+        // fall back to the general instance
+        static const bool general_only = std::getenv("LUMOL_CUDA_LIST_GENERAL") != nullptr;
+        const bool simple = ctx->simple_pairs && !general_only;
+#define LUMOL_LIST_KERNEL(S) \
+    (full ? (simple ? (const void*)list_force_kernel<NL_MODE_FULL, S, 1, true> : (const void*)list_force_kernel<NL_MODE_FULL, S, 1, false>) \
+          : (simple ? (const void*)list_force_kernel<NL_MODE_FORCES, S, 4, true> : (const void*)list_force_kernel<NL_MODE_FORCES, S, 4, false>))
         if (split == 4) {
-            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 4, 1> : (const void*)list_force_kernel<NL_MODE_FORCES, 4, 4>;
+            kernel = LUMOL_LIST_KERNEL(4);
         } else if (split == 2) {
-            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 2, 1> : (const void*)list_force_kernel<NL_MODE_FORCES, 2, 4>;
+            kernel = LUMOL_LIST_KERNEL(2);
         } else {
-            kernel = full ? (const void*)list_force_kernel<NL_MODE_FULL, 1, 1> : (const void*)list_force_kernel<NL_MODE_FORCES, 1, 4>;
+            kernel = LUMOL_LIST_KERNEL(1);
         }
+#undef LUMOL_LIST_KERNEL
     }
     if (smem > 40 * 1024) {
         LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
