@@ -75,9 +75,9 @@ class EnergyCache:
     def move_molecules_cost(self, system, molecule_ids, new_positions):
         """Costs of several independent trial moves against the same state, in one batch of launches; ``update``
         accepts the first one unless ``accept(trial)`` chose another."""
-        device = system._device
-        if device is None:
-            device = device_for(system)
+        # structure, cell and coulomb settings are re-checked (and re-uploaded if they changed); the positions
+        # resident on the device -- those of ``init`` plus every accepted move -- are kept
+        device = device_for(system, positions=system._device is None)
         ids = np.ascontiguousarray(molecule_ids, dtype=np.int64)
         for molecule_id, positions in zip(ids, new_positions):
             bonding = system.molecule(int(molecule_id))
