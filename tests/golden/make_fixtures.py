@@ -104,6 +104,27 @@ def main(reference):
     np.savez_compressed(target, **out)
     print(f"wrote {target}: {len(out)} arrays, {os.path.getsize(target)} bytes")
 
+    # second archive: the flexible-molecule MD inputs tests/data/md-{butane,methane} (cell = 20 in their nve.toml).
+    # The reference guesses the bonds with chemfiles (guess_bonds = true); both files list whole molecules one
+    # after the other (4 united-atom carbons; C H H H H), so the bonds are written down and checked by distance.
+    molecules = {}
+    names, positions, _ = read_xyz(os.path.join(data, "md-butane", "butane.xyz"))
+    bonds = [(4 * m + k, 4 * m + k + 1) for m in range(len(names) // 4) for k in range(3)]
+    lengths = [np.linalg.norm(positions[i] - positions[j]) for (i, j) in bonds]
+    assert len(names) == 200 and max(lengths) < 1.7 and min(lengths) > 1.3
+    molecules["md-butane/names"], molecules["md-butane/positions"] = np.array(names), positions
+    molecules["md-butane/cell"], molecules["md-butane/bonds"] = np.array([20.0] * 3), np.array(bonds, dtype=np.int64)
+    names, positions, _ = read_xyz(os.path.join(data, "md-methane", "methane.xyz"))
+    assert len(names) == 750 and names[:5] == ["C", "H", "H", "H", "H"]
+    bonds = [(5 * m, 5 * m + k) for m in range(len(names) // 5) for k in range(1, 5)]
+    lengths = [np.linalg.norm(positions[i] - positions[j]) for (i, j) in bonds]
+    assert max(lengths) < 1.3 and min(lengths) > 0.9
+    molecules["md-methane/names"], molecules["md-methane/positions"] = np.array(names), positions
+    molecules["md-methane/cell"], molecules["md-methane/bonds"] = np.array([20.0] * 3), np.array(bonds, dtype=np.int64)
+    target = os.path.join(os.path.dirname(os.path.abspath(__file__)), "md_molecules.npz")
+    np.savez_compressed(target, **molecules)
+    print(f"wrote {target}: {len(molecules)} arrays, {os.path.getsize(target)} bytes")
+
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
