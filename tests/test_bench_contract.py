@@ -73,3 +73,17 @@ def test_committed_bench_line_has_the_contract_keys():
     # the companion SPC/E run and the criterion-style latencies ride in the same line
     assert line["spce"]["config"]["ewald"]["kmax"] == 25 and line["spce"]["value"] > 0
     assert "move_molecule_cost" in line["criterion_us_per_call"]["water_ewald"]
+
+
+def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
+    """The driver launches the reference arm like the native one: under torchrun with N ranks, rank 0 alone runs and
+    prints the line, the other ranks exit 0 without work."""
+    command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29731", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--lattice", "8",
+               "--steps", "2", "--warmup", "1", "--cpu-seconds", "0.2"]
+    result = subprocess.run(command, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert result.returncode == 0, result.stderr[-2000:]
+    lines = [line for line in result.stdout.splitlines() if line.strip().startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
