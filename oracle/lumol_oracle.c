@@ -986,6 +986,45 @@ int64_t orc_pair_forces_sample(const orc_system* s, int64_t nrows, const int64_t
     return inside;
 }
 
+/* Total pair force on the atoms listed in `rows`, for boxes too large for the full O(N^2) loop: every pair (i, j),
+ * j != i, is evaluated exactly as compute.rs:40-53 evaluates it when its turn comes in the i < j loop: the atom with
+ * the smaller index is the first argument of nearest_image and receives +f, the other one -f.  out: nrows x 3. */
+void orc_pair_forces_rows(const orc_system* s, int64_t nrows, const int64_t* rows, double* out) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    int64_t n = s->n;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t row = 0; row < nrows; row++) {
+        int64_t t = rows[row];
+        double total[3] = {0.0, 0.0, 0.0};
+        for (int64_t o = 0; o < n; o++) {
+            if (o == t) continue;
+            int64_t i = t < o ? t : o, j = t < o ? o : t;
+            int32_t path = orc_bond_path(s, i, j);
+            double d[3];
+            nearest_image(s, &g, i, j, d);
+            double r = norm3(d);
+            double dn[3] = {d[0] / r, d[1] / r, d[2] / r};
+            const orc_pair* potential = pair_potential(s, i, j);
+            if (potential == NULL) continue;
+            int32_t excluded;
+            double scaling;
+            orc_restriction_information(potential->restriction, potential->scale14, path, &excluded, &scaling);
+            if (excluded) continue;
+            double f = scaling * orc_pair_force(potential, r);
+            for (int k = 0; k < 3; k++) {
+                double force = f * dn[k];
+                if (t == i) {
+                    total[k] += force;
+                } else {
+                    total[k] -= force;
+                }
+            }
+        }
+        for (int k = 0; k < 3; k++) out[3 * row + k] = total[k];
+    }
+}
+
 /* compute.rs:62-97 */
 void orc_bonded_forces(const orc_system* s, double* forces) {
     geom_t g;
@@ -1701,6 +1740,40 @@ void orc_ewald_real_forces(const orc_system* s, double* out) {
         }
     }
     thread_vec_sum_into(&tv, out);
+}
+
+/* The same loop body (ewald.rs:461-500) for the atoms listed in `rows` against every other atom.  out: nrows x 3. */
+void orc_ewald_real_forces_rows(const orc_system* s, int64_t nrows, const int64_t* rows, double* out) {
+    geom_t g;
+    geom_init(&g, s->cell, s->shape);
+    int64_t n = s->n;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t row = 0; row < nrows; row++) {
+        int64_t t = rows[row];
+        double total[3] = {0.0, 0.0, 0.0};
+        if (s->charge[t] != 0.0) {
+            for (int64_t o = 0; o < n; o++) {
+                if (o == t || s->charge[o] == 0.0) continue;
+                int64_t i = t < o ? t : o, j = t < o ? o : t;
+                int32_t path = orc_bond_path(s, i, j);
+                int32_t excluded;
+                double scaling;
+                orc_restriction_information(s->coulomb_restriction, s->coulomb_scale14, path, &excluded, &scaling);
+                double rij[3];
+                nearest_image(s, &g, i, j, rij);
+                double fr = ewald_real_force_pair(s, excluded, s->charge[i] * s->charge[j], norm3(rij));
+                for (int k = 0; k < 3; k++) {
+                    double force = fr * rij[k];
+                    if (t == i) {
+                        total[k] += force;
+                    } else {
+                        total[k] -= force;
+                    }
+                }
+            }
+        }
+        for (int k = 0; k < 3; k++) out[3 * row + k] = total[k];
+    }
 }
 
 /* ewald.rs:502-530 */

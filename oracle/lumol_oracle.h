@@ -194,6 +194,8 @@ int32_t orc_get_threads(void);
 void orc_pair_forces(const orc_system* s, double* forces);   /* compute.rs:37-60, zero-initialised output */
 void orc_bonded_forces(const orc_system* s, double* forces); /* compute.rs:62-97, accumulates */
 int64_t orc_pair_forces_sample(const orc_system* s, int64_t nrows, const int64_t* rows, double* checksum);
+/* total pair force on selected atoms (every j != i), for boxes too large for the full loop; out: nrows x 3 */
+void orc_pair_forces_rows(const orc_system* s, int64_t nrows, const int64_t* rows, double* out);
 void orc_coulomb_forces(const orc_system* s, double* forces); /* accumulates, like GlobalPotential::forces */
 void orc_forces(const orc_system* s, double* forces);         /* Forces::compute */
 double orc_pairs_energy(const orc_system* s);
@@ -222,6 +224,7 @@ double orc_ewald_real_energy(const orc_system* s);
 double orc_ewald_self_energy(const orc_system* s);
 double orc_ewald_kspace_energy(const orc_system* s);
 void orc_ewald_real_forces(const orc_system* s, double* forces);
+void orc_ewald_real_forces_rows(const orc_system* s, int64_t nrows, const int64_t* rows, double* out);
 void orc_ewald_kspace_forces(const orc_system* s, double* forces);
 void orc_ewald_real_atomic_virial(const orc_system* s, double w[9]);
 void orc_ewald_kspace_atomic_virial(const orc_system* s, double w[9]);

@@ -132,6 +132,8 @@ def library():
             "orc_pair_forces": (None, [sp, _dp]),
             "orc_bonded_forces": (None, [sp, _dp]),
             "orc_pair_forces_sample": (ctypes.c_int64, [sp, ctypes.c_int64, _ip, _dp]),
+            "orc_pair_forces_rows": (None, [sp, ctypes.c_int64, _ip, _dp]),
+            "orc_ewald_real_forces_rows": (None, [sp, ctypes.c_int64, _ip, _dp]),
             "orc_coulomb_forces": (None, [sp, _dp]),
             "orc_forces": (None, [sp, _dp]),
             "orc_pairs_energy": (d, [sp]),
@@ -382,6 +384,19 @@ class OracleSystem:
 
     def pair_forces(self):
         return self._vector(self.lib.orc_pair_forces)
+
+    def pair_forces_rows(self, rows):
+        """Total pair force on the atoms ``rows`` (every j != i): boxes too large for the full O(N^2) loop."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros((len(rows), 3))
+        self.lib.orc_pair_forces_rows(self.ref, len(rows), iptr(rows), dptr(out))
+        return out
+
+    def ewald_real_forces_rows(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros((len(rows), 3))
+        self.lib.orc_ewald_real_forces_rows(self.ref, len(rows), iptr(rows), dptr(out))
+        return out
 
     def coulomb_forces(self):
         return self._vector(self.lib.orc_coulomb_forces)

@@ -632,3 +632,25 @@ def test_berendsen_barostats_reduce_to_velocity_verlet_and_scale_the_cell():
     status = small.lib.orc_berendsen_barostat_step(small.ref, oracle.dptr(small.position), oracle.dptr(small.velocity), oracle.dptr(np.zeros((n, 3))),
                                                    1.0, target, 1000.0, ctypes.byref(eta), 12.0)
     assert status == 1
+
+
+def test_forces_on_selected_rows_equal_the_full_loops():
+    """``orc_pair_forces_rows`` / ``orc_ewald_real_forces_rows`` (total force on chosen atoms over every other atom, used to
+    pin the 1M-atom bench box) against the full i < j loops of compute.rs:37-55 and ewald.rs:461-500."""
+    import lumol_b200 as lumol
+
+    system = systems.lj_box(9, seed=5)
+    reference = oracle.OracleSystem(system)
+    rows = np.arange(0, system.size(), 5)
+    full = reference.pair_forces()
+    assert np.abs(reference.pair_forces_rows(rows) - full[rows]).max() <= 1e-13 * np.abs(full).max()
+
+    water = systems.nist_spce(1)
+    systems.set_nist_interactions(water, 9.0)
+    reference = oracle.OracleSystem(water)
+    rows = np.arange(1, water.size(), 7)
+    full = reference.pair_forces()
+    assert np.abs(reference.pair_forces_rows(rows) - full[rows]).max() <= 1e-13 * np.abs(full).max()
+    real = np.zeros((water.size(), 3))
+    reference.lib.orc_ewald_real_forces(reference.ref, oracle.dptr(real))
+    assert np.abs(reference.ewald_real_forces_rows(rows) - real[rows]).max() <= 1e-13 * np.abs(real).max()
