@@ -206,6 +206,13 @@ struct Context {
     DeviceBuffer<int4> blk_header, blk_entries;  // staging tables of the Lennard-Jones kernel (pairs_cells.cu)
     DeviceBuffer<double> frame_pos;            // x | y | z planes, sorted order, positions in the frame of the box
     DeviceBuffer<unsigned short> self_local;   // staged slot of each atom inside its own block
+    // pipelined Lennard-Jones path (pairs_lj2.cu): frames with ghost cells, radial levels, deferred cut-off pairs
+    DeviceBuffer<int> ext_start, fidx, kshift, frame_atom;
+    DeviceBuffer<unsigned short> cum_levels;
+    DeviceBuffer<int2> deferred;
+    int deferred_capacity = 0;
+    int rebuild2_grid = 0;
+    bool lj2_active = false;  // the current neighbour list was built by pairs_lj2.cu
 
     // ---- reductions ------------------------------------------------------------------------------
     DeviceBuffer<double> partials, reduce_scratch;
@@ -301,6 +308,8 @@ struct ComputeRequest {
 int launch_reduce(Context* ctx, int nblocks, int nvalues, int first_slot);                       // reduce.cu
 int launch_pairs_allpairs(Context* ctx, const ComputeRequest& req);                              // pairs_allpairs.cu
 int launch_pairs_cells(Context* ctx, const ComputeRequest& req);                                 // pairs_cells.cu
+int launch_pairs_lj2(Context* ctx, const ComputeRequest& req);                                   // pairs_lj2.cu
+bool lj2_enabled(const Context* ctx);                                                            // pairs_lj2.cu
 int choose_neighbor_path(Context* ctx, double cutoff);                                           // pairs_cells.cu
 int neighbor_list_status(Context* ctx, int* rebuilds, int* overflow);                            // pairs_cells.cu
 int launch_coulomb_self(Context* ctx);                                                           // pairs_allpairs.cu

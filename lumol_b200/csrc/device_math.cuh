@@ -76,6 +76,31 @@ __device__ __forceinline__ void vector_image(const CellView& c, double& x, doubl
     }
 }
 
+// The same image and the squared norm with the reference's roundings: Rust never contracts a * b + c, so neither do
+// these (explicit __dmul_rn / __dadd_rn).  Used where a pair may sit exactly on a cut-off (`r >= rc`, pairs.rs:186;
+// `r > rc`, ewald.rs:390): the all-pairs kernel, the Monte Carlo cost kernels and the fix-up of the list kernels.
+__device__ __forceinline__ double dot3_exact(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+
+__device__ __forceinline__ void vector_image_exact(const CellView& c, double& x, double& y, double& z) {
+    if (c.shape == LUMOL_CUDA_CELL_ORTHORHOMBIC) {
+        x = __dadd_rn(x, -__dmul_rn(round(__ddiv_rn(x, c.h[0])), c.h[0]));
+        y = __dadd_rn(y, -__dmul_rn(round(__ddiv_rn(y, c.h[4])), c.h[4]));
+        z = __dadd_rn(z, -__dmul_rn(round(__ddiv_rn(z, c.h[8])), c.h[8]));
+    } else if (c.shape == LUMOL_CUDA_CELL_TRICLINIC) {
+        double fx = dot3_exact(c.inv[0], c.inv[1], c.inv[2], x, y, z);
+        double fy = dot3_exact(c.inv[3], c.inv[4], c.inv[5], x, y, z);
+        double fz = dot3_exact(c.inv[6], c.inv[7], c.inv[8], x, y, z);
+        fx = __dadd_rn(fx, -round(fx));
+        fy = __dadd_rn(fy, -round(fy));
+        fz = __dadd_rn(fz, -round(fz));
+        x = dot3_exact(c.h[0], c.h[1], c.h[2], fx, fy, fz);
+        y = dot3_exact(c.h[3], c.h[4], c.h[5], fx, fy, fz);
+        z = dot3_exact(c.h[6], c.h[7], c.h[8], fx, fy, fz);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // potentials (energy/functions.rs).  Returns energy and force(r) = -dV/dr as the reference defines
 // it (Morse keeps the reference's formula, functions.rs:420-423).

@@ -44,8 +44,8 @@ struct MovePairsArgs {
 __device__ __forceinline__ double image_distance(const CellView& cell, double ax, double ay, double az, double bx, double by,
                                                  double bz) {
     double dx = ax - bx, dy = ay - by, dz = az - bz;
-    vector_image(cell, dx, dy, dz);
-    return sqrt(dx * dx + dy * dy + dz * dz);
+    vector_image_exact(cell, dx, dy, dz);
+    return sqrt(dot3_exact(dx, dy, dz, dx, dy, dz));
 }
 
 // grid: (blocks over the atoms of the system, trials)

@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(ALLPAIRS_THREADS) allpairs_kernel(AllPairsArgs
             double dx = xi - a.pos[3 * j];
             double dy = yi - a.pos[3 * j + 1];
             double dz = zi - a.pos[3 * j + 2];
-            vector_image(a.cell, dx, dy, dz);
-            const double r2 = dx * dx + dy * dy + dz * dz;
+            // image and norm with the reference's roundings: a pair on the cut-off falls on the reference's side
+            vector_image_exact(a.cell, dx, dy, dz);
+            const double r2 = dot3_exact(dx, dy, dz, dx, dy, dz);
             const double r = sqrt(r2);
             const unsigned bits = same_molecule ? a.bond_dist[rowi + (j - mfj)] : 0u;
             // which side of the pair accumulates the scalar sums

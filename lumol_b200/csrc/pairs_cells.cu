@@ -38,6 +38,7 @@
 //     17 FP64 instructions per listed pair; half of the energy and virial from each side of a pair.
 // No atomics on the pair path: every pair is evaluated from both sides, sums are reduced in a fixed order.
 #include "context.hpp"
+#include "neighbor_common.cuh"
 
 #include <cooperative_groups.h>
 
@@ -79,156 +80,9 @@ int choose_neighbor_path(Context* ctx, double cutoff) {
     return possible && ctx->n >= CELL_PATH_MIN_ATOMS ? 1 : 0;
 }
 
-// flags[0]: rebuild requested, flags[1]: a list column overflowed, flags[2]: number of rebuilds so far
-constexpr int FLAG_REBUILD = 0, FLAG_OVERFLOW = 1, FLAG_COUNT = 2;
-// flags[3]: blocks that could not be staged (FLAG_UNSTAGED); flags[4]: a position was not finite at the last rebuild
-constexpr int FLAG_UNSTAGED = 3;
-constexpr int FLAG_NONFINITE = 4;
-
-// ------------------------------------------------------------------------------------------------
-// counting sort (every kernel returns immediately when no rebuild is requested)
-// ------------------------------------------------------------------------------------------------
-
-struct GridView {
-    int nc[3];
-    double length[3];
-    double edge[3];
-};
-
-__device__ __forceinline__ double wrap_coordinate(double x, double length) {
-    // UnitCell::wrap_vector, orthorhombic branch (cells.rs:266-270)
-    return x - floor(x / length) * length;
-}
-
 // Box-frame arrays (read by the bulk copies of the Lennard-Jones kernel, 16-byte granularity): the atoms of cell c
 // start at an even index, one slot of padding per cell at most.
 __host__ __device__ __forceinline__ int frame_start(int cell, int first_sorted) { return (first_sorted + cell + 1) & ~1; }
-
-__device__ __forceinline__ int cell_coordinate(double wrapped, double length, int nc) {
-    int c = (int)(wrapped / length * (double)nc);
-    if (c >= nc) c = nc - 1;  // wrapped == length after rounding
-    if (c < 0) c = 0;
-    return c;
-}
-
-// The rebuild runs as the phases of ONE cooperative kernel (rebuild_kernel below) separated by grid-wide
-// barriers; `vb` is the virtual block a resident block is working on.
-constexpr int REBUILD_THREADS = 256;
-constexpr int REBUILD_WARPS = REBUILD_THREADS / 32;
-
-__device__ __forceinline__ void cell_zero_phase(int count, int* __restrict__ cell_count, unsigned char* __restrict__ cell_needed,
-                                                int* __restrict__ flags) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        flags[3] = 0;  // FLAG_UNSTAGED, counted by block_table_phase
-        flags[FLAG_NONFINITE] = 0;
-    }
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-        cell_count[k] = 0;
-        cell_needed[k] = 0;
-    }
-}
-
-__device__ __forceinline__ void cell_assign_phase(int vb, int n, const GridView& g, const double* __restrict__ pos,
-                                                  int* __restrict__ cell_of, int* __restrict__ slot_of,
-                                                  int* __restrict__ cell_count, int* __restrict__ flags) {
-    const int i = vb * REBUILD_THREADS + threadIdx.x;
-    if (i >= n) return;
-    // an exploded simulation must not turn the sort into a quadratic loop over one cell: the rebuild stops here
-    if (!(isfinite(pos[3 * i]) && isfinite(pos[3 * i + 1]) && isfinite(pos[3 * i + 2]))) flags[FLAG_NONFINITE] = 1;
-    const int cx = cell_coordinate(wrap_coordinate(pos[3 * i], g.length[0]), g.length[0], g.nc[0]);
-    const int cy = cell_coordinate(wrap_coordinate(pos[3 * i + 1], g.length[1]), g.length[1], g.nc[1]);
-    const int cz = cell_coordinate(wrap_coordinate(pos[3 * i + 2], g.length[2]), g.length[2], g.nc[2]);
-    const int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
-    cell_of[i] = c;
-    slot_of[i] = atomicAdd(cell_count + c, 1);
-}
-
-// exclusive scan of `count` ints in three passes (block scan, scan of block sums, add back)
-constexpr int SCAN_THREADS = REBUILD_THREADS;
-constexpr int SCAN_ITEMS = 4;
-constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ int block_exclusive_scan(int value, int* shared, int& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int v = value;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    if (lane == 31) shared[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < (blockDim.x >> 5) ? shared[lane] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        shared[lane] = w;  // inclusive scan of warp totals
-    }
-    __syncthreads();
-    const int warp_offset = warp == 0 ? 0 : shared[warp - 1];
-    total = shared[(blockDim.x >> 5) - 1];
-    __syncthreads();
-    return warp_offset + v - value;
-}
-
-__device__ __forceinline__ void scan_blocks_phase(int vb, int count, const int* __restrict__ in, int* __restrict__ out,
-                                                  int* __restrict__ block_sums, int* shared) {
-    const int base = vb * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    int items[SCAN_ITEMS];
-    int sum = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        items[k] = base + k < count ? in[base + k] : 0;
-        sum += items[k];
-    }
-    int total;
-    int offset = block_exclusive_scan(sum, shared, total);
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < count) out[base + k] = offset;
-        offset += items[k];
-    }
-    if (threadIdx.x == 0) block_sums[vb] = total;
-}
-
-// one block
-__device__ __forceinline__ void scan_sums_phase(int nblocks, int* __restrict__ block_sums, int* shared) {
-    int& carry = shared[32];
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < nblocks; base += blockDim.x) {
-        const int idx = base + threadIdx.x;
-        const int value = idx < nblocks ? block_sums[idx] : 0;
-        int total;
-        const int offset = block_exclusive_scan(value, shared, total);
-        if (idx < nblocks) block_sums[idx] = carry + offset;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void scan_add_phase(int vb, int count, int* __restrict__ out, const int* __restrict__ block_sums,
-                                               int total_count) {
-    const int base = vb * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    const int add = block_sums[vb];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < count) out[base + k] += add;
-    }
-    if (vb == 0 && threadIdx.x == 0) out[count] = total_count;
-}
-
-// first pass of the scatter: original indices grouped by cell, arrival order
-__device__ __forceinline__ void cell_group_phase(int vb, int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
-                                                 const int* __restrict__ cell_start, int* __restrict__ grouped) {
-    const int i = vb * REBUILD_THREADS + threadIdx.x;
-    if (i >= n) return;
-    grouped[cell_start[cell_of[i]] + slot_of[i]] = i;
-}
 
 struct ScatterArgs {
     int n;
@@ -1321,6 +1175,13 @@ static uint64_t mix(uint64_t h, uint64_t v) {
 
 int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     const int n = (int)ctx->n;
+    // single Lennard-Jones interaction, no charges in play: the pipelined kernel of pairs_lj2.cu (neighbour path 2 keeps
+    // the first-generation kernels with every block in the global list format, which the tests compare against)
+    if (ctx->any_pair && ctx->single_lj && ctx->coulomb.kind == 0 && ctx->forced_path != 2 && lj2_enabled(ctx)) {
+        ctx->lj2_active = true;
+        return launch_pairs_lj2(ctx, req);
+    }
+    ctx->lj2_active = false;
     if (ctx->n >= (int64_t)LIST_INDEX_MASK) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the neighbour list handles at most %u atoms per GPU", LIST_INDEX_MASK);
     }
@@ -1347,7 +1208,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
     if (capacity > n) capacity = n;
     capacity = (capacity + 7) / 8 * 8;  // whole 16-byte words in both list formats
     const size_t stride = ((size_t)n + 31) / 32 * 32;
-    LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(8));
+    LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(16));
     LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(stride * (size_t)capacity));
     LUMOL_CUDA_CHECK(ctx, ctx->ncount.reserve(stride));
     LUMOL_CUDA_CHECK(ctx, ctx->xref.reserve((size_t)3 * n));
@@ -1402,7 +1263,7 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         ScopedClock clock(ctx, &ctx->clk_neighbor);
         if (!reuse) {
             if (!ctx->flags_initialised) {
-                LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(flags, 0, 8 * sizeof(int), ctx->stream));
+                LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(flags, 0, 16 * sizeof(int), ctx->stream));
                 ctx->flags_initialised = true;
             }
             LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->frame_pos.ptr, 0, 3 * frame_stride * sizeof(double), ctx->stream));
@@ -1642,10 +1503,12 @@ int neighbor_list_status(Context* ctx, int* rebuilds, int* overflow) {
     *rebuilds = 0;
     *overflow = 0;
     if (ctx->nl_flags.ptr == nullptr || !ctx->flags_initialised) return 0;
-    int host[5] = {0, 0, 0, 0, 0};
+    int host[12] = {0};
     LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(host, ctx->nl_flags.ptr, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     *overflow = host[FLAG_NONFINITE] != 0 ? 2 : host[FLAG_OVERFLOW];
+    // pairs_lj2.cu: frame slots of the ghost images, list of the pairs sitting on the cut-off
+    if (ctx->lj2_active && *overflow == 0 && (host[11] != 0 || host[10] > ctx->deferred_capacity)) *overflow = 1;
     if (host[FLAG_NONFINITE] != 0) ctx->list_valid = false;  // the next evaluation rebuilds from scratch
     *rebuilds = host[FLAG_COUNT];
     return 0;

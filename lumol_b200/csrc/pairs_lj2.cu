@@ -1,0 +1,1510 @@
+// Pipelined Lennard-Jones pair path for single-LJ systems on the neighbour-list path (the headline kernel of the
+// benchmark: liquid argon, sys/compute.rs:37-55 + energy.rs:47-59 + compute.rs:202-216 of the reference for one
+// PairInteraction with restriction None).  Second generation of the staged kernel of pairs_cells.cu; what changed and
+// why (profiles/r1m_*, VERDICT round 1: FP64 pipe 65 % busy, 30 % of the warp time outside the pair loop, 1.33 listed
+// entries per pair inside the cut-off):
+//
+//   * GHOST CELLS.  The box-frame position planes carry one layer of periodic ghost cells around the grid
+//     ((nx+2)(ny+2)(nz+2) cells, the refresh kernel writes up to seven images of a boundary atom).  Every row of a
+//     unit's neighbourhood is then ONE contiguous range: one bulk copy per row and plane, no image fix-up pass.
+//   * PERSISTENT, PIPELINED.  One CTA of sixteen warps per SM and two staging buffers: while unit k is evaluated out
+//     of one, the bulk copies (cp.async.bulk -> mbarrier) of unit k + 1 land in the other.  A warp that finishes a unit
+//     goes straight on to the next one; the LAST warp to finish unit k issues the copies of unit k + 2 into the buffer
+//     that has just drained.  No block-wide barrier, no warp set aside as a producer (544 threads would cap the
+//     kernel at 96 registers).
+//   * TWO LANES PER ATOM.  Lanes 2a, 2a+1 share atom a and split every 8-entry list word 4 + 4: sixteen warps work on one
+//     256-atom unit, no imbalance between the halves.
+//   * RADIAL LEVELS.  At build time every list entry gets the level of its distance, r_b in [rc + k d, rc + (k+1) d),
+//     d = skin / 8, and the columns are ordered by level.  A pair can only be inside the cut-off when
+//     r_b < rc + 2 dmax(t), dmax = largest displacement of any atom since the rebuild (the refresh kernel reduces it), so
+//     an evaluation walks only the prefix of the levels below 2 dmax / d: 1.06 listed per in-cut-off pair right after a
+//     rebuild, 1.33 just before the next, no re-pruning pass and no second list.
+//   * EXACT CUT-OFF.  A pair whose r^2 falls in a narrow band around rc^2 (top 32 bits equal +-1) is not evaluated here
+//     but appended to a short list; a fix-up kernel evaluates those few pairs from the original coordinates with the
+//     reference's own arithmetic (minimum image by division and round, r = sqrt(d.d), `r >= rc -> 0`, pairs.rs:186), so
+//     the set of interacting pairs is the reference's bit for bit whatever rounding the box-frame arithmetic did.
+//
+// Every listed pair is evaluated from both sides (full shell): with 17 FP64 instructions per pair, moving a force
+// through shared memory or shuffles (24 bytes each way at 128 B/clk/SM) costs more than recomputing it (17 / 64 clk/SM),
+// see DESIGN.md section 4.1.
+#include "context.hpp"
+#include "neighbor_common.cuh"
+
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <cstring>
+
+namespace lumol {
+
+#ifndef LJ2_THREADS_CONFIG
+#define LJ2_THREADS_CONFIG 512
+#endif
+#ifndef LJ2_BUFFERS_CONFIG
+#define LJ2_BUFFERS_CONFIG 2
+#endif
+constexpr int LJ2_THREADS = LJ2_THREADS_CONFIG;
+#ifndef LJ2_ILP8
+#define LJ2_ILP8 0
+#endif
+#ifndef LJ2_LPA_CONFIG
+#define LJ2_LPA_CONFIG 2
+#endif
+constexpr int LJ2_LPA = LJ2_LPA_CONFIG;                         // lanes per atom: they split every 8-entry list word 4 + 4 (and alternate words when 4)
+constexpr int U_ATOMS = LJ2_THREADS / LJ2_LPA;     // atoms per unit (consecutive in cell order)
+constexpr int LJ2_BUFFERS = LJ2_BUFFERS_CONFIG;
+constexpr int LJ2_WORD_STRIDE = LJ2_LPA / 2;       // a lane walks words word_first, word_first + LJ2_WORD_STRIDE, ...
+constexpr int LJ2_MAX_SEGMENTS = 6;
+constexpr int LJ2_MAX_RUNS = 9 * LJ2_MAX_SEGMENTS;
+constexpr int LJ2_SLOTS = LJ2_BUFFERS == 2 ? 4528 : 3072;  // atoms of one staged copy (dummy slots 0, 1 included)
+constexpr int LJ2_STAGE_BYTES = 3 * LJ2_SLOTS * 8;  // (x, y, z) per slot: 106 KiB, two buffers per CTA
+constexpr int LJ2_LEVELS = 8;
+constexpr int LJ2_NV = 16;
+constexpr unsigned RAW_VALUE_MASK = (1u << 28) - 1u;
+constexpr int FLAG_DISP = 8;       // flags[8], flags[9]: float bits of the largest squared displacement, by epoch parity
+constexpr int FLAG_DEFERRED = 10;  // number of deferred (on-the-cut-off) pairs of the current evaluation
+constexpr int FLAG_FRAME_OVERFLOW = 11;
+constexpr int DEFERRED_PER_ATOM = 4;
+
+__host__ __device__ __forceinline__ int pad2(int count) { return (count + 1) & ~1; }
+
+// ------------------------------------------------------------------------------------------------
+// rebuild phases specific to this path
+// ------------------------------------------------------------------------------------------------
+
+struct ExtGrid {
+    int nx, ny, nz;  // real cells
+    int ex, ey, ez;  // with the ghost layer
+    __host__ __device__ int count() const { return ex * ey * ez; }
+    // real cell seen at extended coordinates (X, Y, Z)
+    __device__ __forceinline__ int source(int X, int Y, int Z) const {
+        const int x = X == 0 ? nx - 1 : (X == ex - 1 ? 0 : X - 1);
+        const int y = Y == 0 ? ny - 1 : (Y == ey - 1 ? 0 : Y - 1);
+        const int z = Z == 0 ? nz - 1 : (Z == ez - 1 ? 0 : Z - 1);
+        return (z * ny + y) * nx + x;
+    }
+    __device__ __forceinline__ int index(int X, int Y, int Z) const { return (Z * ey + Y) * ex + X; }
+};
+
+struct Scatter2Args {
+    int n;
+    GridView g;
+    const double* __restrict__ pos;   // state order
+    const int* __restrict__ state_of_sorted_old;  // unused here (kept for the sorted-resident mode)
+    const int* __restrict__ cell_of;
+    const int* __restrict__ cell_start;
+    const int* __restrict__ grouped;
+    int* __restrict__ order;          // sorted slot -> state index
+    float4* __restrict__ sorted_f32;  // cell-relative FP32 position (list build)
+    int* __restrict__ sorted_cell;
+    double* __restrict__ xref;        // 3 n, sorted order: position at the rebuild
+    int* __restrict__ kshift;         // n: wrap counts floor(x / L) packed 3 x 10 bits + sign offset
+};
+
+// wrap counts in [-512, 511] per axis
+__device__ __forceinline__ int pack_shift(int kx, int ky, int kz) {
+    return ((kx + 512) & 1023) | (((ky + 512) & 1023) << 10) | (((kz + 512) & 1023) << 20);
+}
+__device__ __forceinline__ void unpack_shift(int packed, int& kx, int& ky, int& kz) {
+    kx = (packed & 1023) - 512;
+    ky = ((packed >> 10) & 1023) - 512;
+    kz = ((packed >> 20) & 1023) - 512;
+}
+
+// rank inside the cell = number of cell mates with a smaller state index (deterministic order)
+__device__ __forceinline__ void scatter2_phase(int vb, const Scatter2Args& a, int* __restrict__ flags) {
+    const int s = vb * REBUILD_THREADS + threadIdx.x;
+    if (s >= a.n) return;
+    const int i = a.grouped[s];
+    const int c = a.cell_of[i];
+    const int lo = a.cell_start[c], hi = a.cell_start[c + 1];
+    int rank = 0;
+    for (int t = lo; t < hi; t++) rank += a.grouped[t] < i ? 1 : 0;
+    const int dst = lo + rank;
+    a.order[dst] = i;
+    const int cx = c % a.g.nc[0], cy = (c / a.g.nc[0]) % a.g.nc[1], cz = c / (a.g.nc[0] * a.g.nc[1]);
+    const double px = a.pos[3 * i], py = a.pos[3 * i + 1], pz = a.pos[3 * i + 2];
+    const double kx = floor(px / a.g.length[0]), ky = floor(py / a.g.length[1]), kz = floor(pz / a.g.length[2]);
+    if (fabs(kx) > 500.0 || fabs(ky) > 500.0 || fabs(kz) > 500.0) flags[FLAG_NONFINITE] = 1;  // hundreds of boxes away: refuse
+    const double x = px - kx * a.g.length[0] - ((double)cx + 0.5) * a.g.edge[0];
+    const double y = py - ky * a.g.length[1] - ((double)cy + 0.5) * a.g.edge[1];
+    const double z = pz - kz * a.g.length[2] - ((double)cz + 0.5) * a.g.edge[2];
+    a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, 0.0f);
+    a.sorted_cell[dst] = c;
+    a.xref[3 * dst] = px;
+    a.xref[3 * dst + 1] = py;
+    a.xref[3 * dst + 2] = pz;
+    a.kshift[dst] = pack_shift((int)kx, (int)ky, (int)kz);
+}
+
+// padded atom count of every extended cell (a ghost cell mirrors its source)
+__device__ __forceinline__ void ext_count_phase(const ExtGrid& e, const int* __restrict__ cell_start, int* __restrict__ ext_pad) {
+    const int total = e.count();
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int X = k % e.ex, Y = (k / e.ex) % e.ey, Z = k / (e.ex * e.ey);
+        const int c = e.source(X, Y, Z);
+        ext_pad[k] = pad2(cell_start[c + 1] - cell_start[c]);
+    }
+}
+
+// last pass of the exclusive scan of the padded counts; also writes the grand total behind the last element
+__device__ __forceinline__ void scan_add_total_phase(int vb, int count, const int* __restrict__ in, int* __restrict__ out,
+                                                     const int* __restrict__ block_sums) {
+    const int base = vb * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    const int add = block_sums[vb];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < count) {
+            const int value = out[base + k] + add;
+            out[base + k] = value;
+            if (base + k == count - 1) out[count] = value + in[count - 1];
+        }
+    }
+}
+
+// Frame index of an atom's real copy and of its ghost images; `visit(frame_index, sx, sy, sz)` with the image shift in
+// box lengths.  Extended cells start at ext_start[] + 2 (frame slots 0 and 1 are the far-away dummy).
+template <typename Visit>
+__device__ __forceinline__ void for_each_image(const ExtGrid& e, const int* __restrict__ ext_start, int c, int rank, Visit visit) {
+    const int x = c % e.nx, y = (c / e.nx) % e.ny, z = c / (e.nx * e.ny);
+    // ghost direction per axis: an atom of the first cell is also seen behind the last one (+L) and vice versa
+    const int gx = x == 0 ? 1 : (x == e.nx - 1 ? -1 : 0);
+    const int gy = y == 0 ? 1 : (y == e.ny - 1 ? -1 : 0);
+    const int gz = z == 0 ? 1 : (z == e.nz - 1 ? -1 : 0);
+    for (int m = 0; m < 8; m++) {
+        const int sx = (m & 1) ? gx : 0, sy = (m & 2) ? gy : 0, sz = (m & 4) ? gz : 0;
+        if (((m & 1) && gx == 0) || ((m & 2) && gy == 0) || ((m & 4) && gz == 0)) continue;
+        const int X = sx > 0 ? e.ex - 1 : (sx < 0 ? 0 : x + 1);
+        const int Y = sy > 0 ? e.ey - 1 : (sy < 0 ? 0 : y + 1);
+        const int Z = sz > 0 ? e.ez - 1 : (sz < 0 ? 0 : z + 1);
+        visit(2 + ext_start[e.index(X, Y, Z)] + rank, sx, sy, sz);
+    }
+}
+
+struct Frame2Args {
+    int n;
+    GridView g;
+    ExtGrid e;
+    const int* __restrict__ cell_start;
+    const int* __restrict__ sorted_cell;
+    const int* __restrict__ ext_start;
+    const int* __restrict__ order;
+    const double* __restrict__ xref;
+    const int* __restrict__ kshift;
+    int* __restrict__ fidx;        // n: frame index of the real copy
+    int* __restrict__ frame_atom;  // frame slot -> sorted index (images included)
+    double* __restrict__ frame;    // (x, y, z) per frame slot
+    size_t fstride;                // frame slots allocated
+    double scale;
+};
+
+// frame indices and the frames themselves at the rebuild positions
+__device__ __forceinline__ void frame2_phase(int vb, const Frame2Args& a, int* __restrict__ flags) {
+    const int s = vb * REBUILD_THREADS + threadIdx.x;
+    if (vb == 0 && threadIdx.x < 2) {
+        // the dummy that padding entries of unstaged columns point at
+        for (int p = 0; p < 3; p++) a.frame[3 * threadIdx.x + p] = 1.0e9 * (double)(p + 1);
+        a.frame_atom[threadIdx.x] = -1;
+    }
+    if (s >= a.n) return;
+    const int c = a.sorted_cell[s];
+    const int rank = s - a.cell_start[c];
+    int kx, ky, kz;
+    unpack_shift(a.kshift[s], kx, ky, kz);
+    const double x = a.xref[3 * s] - (double)kx * a.g.length[0];
+    const double y = a.xref[3 * s + 1] - (double)ky * a.g.length[1];
+    const double z = a.xref[3 * s + 2] - (double)kz * a.g.length[2];
+    bool first = true;
+    for_each_image(a.e, a.ext_start, c, rank, [&](int f, int sx, int sy, int sz) {
+        if ((size_t)f + 2 > a.fstride) {
+            flags[FLAG_FRAME_OVERFLOW] = 1;
+            return;
+        }
+        if (first) a.fidx[s] = f;
+        first = false;
+        a.frame_atom[f] = s;
+        a.frame[3 * (size_t)f] = (x + (double)sx * a.g.length[0]) * a.scale;
+        a.frame[3 * (size_t)f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
+        a.frame[3 * (size_t)f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
+    });
+}
+
+// ---- unit tables -------------------------------------------------------------------------------------------------
+//
+// Unit u holds the sorted atoms [256 u, 256 u + 256): home cells [c0, c0 + K) of the x-fastest cell order, i.e. up to a
+// few row segments.  Segment g (cells x in [xa, xa + len) of grid row r0 + g) brings nine runs, one per (dy, dz): the
+// extended cells X in [xa, xa + len + 1] of the extended row (z + dz + 1, y + dy + 1), contiguous in the frame planes.
+// Run index 9 g + 3 (dz + 1) + (dy + 1).
+
+struct UnitRows {
+    int c0, K, nx, r0, xa0, len0, nseg;
+    __host__ __device__ void init(int first_cell, int cells, int cells_x) {
+        c0 = first_cell;
+        K = cells;
+        nx = cells_x;
+        r0 = c0 / nx;
+        xa0 = c0 - r0 * nx;
+        len0 = min(nx - xa0, K);
+        nseg = 1 + (K - len0 + nx - 1) / nx;
+    }
+    __host__ __device__ void segment(int g, int& xa, int& len) const {
+        if (g == 0) {
+            xa = xa0;
+            len = len0;
+        } else {
+            xa = 0;
+            len = min(nx, K - len0 - (g - 1) * nx);
+        }
+    }
+};
+
+struct Table2Args {
+    int n, nunits;
+    ExtGrid e;
+    const int* __restrict__ sorted_cell;
+    const int* __restrict__ ext_start;
+    int4* __restrict__ header;  // c0, K, number of runs (-1: not staged), staged slots
+    int4* __restrict__ runs;    // first frame index, slots, first slot
+    int* __restrict__ flags;
+};
+
+// one warp per unit
+__device__ __forceinline__ void unit_table_phase(int vb, const Table2Args& a) {
+    const int lane = threadIdx.x & 31;
+    const int unit = vb * REBUILD_WARPS + (threadIdx.x >> 5);
+    if (unit >= a.nunits) return;
+    const int s_first = unit * U_ATOMS, s_last = min(a.n, s_first + U_ATOMS) - 1;
+    const int c_first = a.sorted_cell[s_first], c_last = a.sorted_cell[s_last];
+    UnitRows rows;
+    rows.init(c_first, c_last - c_first + 1, a.e.nx);
+    bool staged = rows.nseg <= LJ2_MAX_SEGMENTS;
+    int total = 2;
+    const int nruns = 9 * rows.nseg;
+    if (staged) {
+        for (int base = 0; base < nruns; base += 32) {
+            const int r = base + lane;
+            int f0 = 0, slots = 0;
+            if (r < nruns) {
+                const int g = r / 9, plane = r - 9 * g;
+                int xa, len;
+                rows.segment(g, xa, len);
+                const int row = rows.r0 + g;
+                const int y = row % a.e.ny, z = row / a.e.ny;
+                const int Y = y + (plane % 3), Z = z + (plane / 3);  // dy + 1 + y, dz + 1 + z
+                const int e0 = a.e.index(xa, Y, Z), e1 = e0 + len + 1;
+                f0 = 2 + a.ext_start[e0];
+                slots = 2 + a.ext_start[e1 + 1] - f0;
+            }
+            int scan = slots;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, scan, o);
+                if (lane >= o) scan += t;
+            }
+            if (r < nruns) a.runs[(size_t)unit * LJ2_MAX_RUNS + r] = make_int4(f0, slots, total + scan - slots, 0);
+            total += __shfl_sync(0xffffffffu, scan, 31);
+        }
+        if (total > LJ2_SLOTS) staged = false;
+    }
+    if (!staged && lane == 0) atomicAdd(a.flags + FLAG_UNSTAGED, 1);
+    if (lane == 0) a.header[unit] = make_int4(rows.c0, rows.K, staged ? nruns : -1, total);
+}
+
+// ---- list build -----------------------------------------------------------------------------------------------------
+
+struct Build2Args {
+    GridView g;
+    ExtGrid e;
+    int ncells;
+    int cells_per_warp;
+    int s_lo, s_hi;      // sorted range of the atoms this rank owns (lists are built for those)
+    int capacity;        // entries per atom
+    float radius2;       // (cut-off + skin)^2, enlarged by 1e-4 relative
+    float cutoff, inv_delta;  // level of an entry: floor((r_b - cutoff) / delta), delta = skin / 8
+    const int* __restrict__ cell_start;
+    const int* __restrict__ ext_start;
+    const float4* __restrict__ sorted_f32;
+    const int4* __restrict__ header;
+    const int4* __restrict__ runs;
+    unsigned short* __restrict__ self_slot;
+    unsigned* __restrict__ nlist;  // raw columns: 32-bit entries (level << 28) | slot or frame index
+    int* __restrict__ ncount;
+    unsigned char* __restrict__ cell_needed;
+    int* __restrict__ flags;
+};
+
+constexpr int BUILD2_CHUNKS = 8;
+
+// One warp per 32-atom chunk of a home cell, one lane per atom; the 27 neighbour cells are streamed, eight candidates
+// (uniform addresses) loaded before the first is tested.  Survivors are collected in a per-lane shared-memory buffer and
+// written as whole 16-byte words (four entries).
+__device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, const float (*offset32)[3], unsigned (*pending)[4]) {
+    const int lane = threadIdx.x & 31;
+    const int global_warp = vb * REBUILD_WARPS + (threadIdx.x >> 5);
+    const int item_lo = global_warp * a.cells_per_warp;
+    const int item_hi = min(a.ncells * BUILD2_CHUNKS, item_lo + a.cells_per_warp);
+    unsigned* mine = pending[threadIdx.x];
+
+    for (int item = item_lo; item < item_hi; item++) {
+        const int first_chunk = item / a.ncells, c = item - first_chunk * a.ncells;
+        const int hs = a.cell_start[c], he = a.cell_start[c + 1];
+        if (hs + 32 * first_chunk >= he) continue;
+        const int cx = c % a.g.nc[0];
+        const int cy = (c / a.g.nc[0]) % a.g.nc[1];
+        const int cz = c / (a.g.nc[0] * a.g.nc[1]);
+        for (int base = hs + 32 * first_chunk; base < he; base += 32 * BUILD2_CHUNKS) {
+            const int s_i = base + lane;
+            bool active = s_i < he && s_i >= a.s_lo && s_i < a.s_hi;
+            float xf = 1.0e18f, yf = 0.0f, zf = 0.0f;
+            bool staged = false;
+            const int4* runs = a.runs;
+            int run_base = 0;
+            if (s_i < he) {
+                const int unit = s_i / U_ATOMS;
+                const int4 header = a.header[unit];
+                staged = header.z >= 0;
+                runs += (size_t)unit * LJ2_MAX_RUNS;
+                run_base = 9 * (c / a.g.nc[0] - header.x / a.g.nc[0]);
+                if (staged) {
+                    const int4 run = runs[run_base + 4];  // dy = dz = 0
+                    const int f_self = 2 + a.ext_start[a.e.index(cx + 1, cy + 1, cz + 1)] + (s_i - hs);
+                    a.self_slot[s_i] = (unsigned short)(3 * (run.z + (f_self - run.x)));
+                }
+            }
+            if (active) {
+                const float4 f = a.sorted_f32[s_i];
+                xf = f.x;
+                yf = f.y;
+                zf = f.z;
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (s_i < he) a.ncount[s_i] = 0;
+                continue;
+            }
+            if (lane < 27) {
+                int mx = cx + (lane % 3) - 1, my = cy + ((lane / 3) % 3) - 1, mz = cz + (lane / 9) - 1;
+                mx += mx < 0 ? a.g.nc[0] : (mx >= a.g.nc[0] ? -a.g.nc[0] : 0);
+                my += my < 0 ? a.g.nc[1] : (my >= a.g.nc[1] ? -a.g.nc[1] : 0);
+                mz += mz < 0 ? a.g.nc[2] : (mz >= a.g.nc[2] ? -a.g.nc[2] : 0);
+                a.cell_needed[(mz * a.g.nc[1] + my) * a.g.nc[0] + mx] = 1;
+            }
+            // raw column of atom s: word w (four 32-bit entries) at ((s >> 5) * (capacity / 4) + w) * 32 + (s & 31)
+            uint4* column = reinterpret_cast<uint4*>(a.nlist) + (size_t)(s_i >> 5) * (a.capacity >> 2) * 32 + (s_i & 31);
+            int count = 0;
+            for (int row = 0; row < 9; row++) {
+                const int uy = cy + (row % 3) - 1, uz = cz + (row / 3) - 1;
+                int ny = uy, nz = uz;
+                ny += ny < 0 ? a.g.nc[1] : 0;
+                ny -= ny >= a.g.nc[1] ? a.g.nc[1] : 0;
+                nz += nz < 0 ? a.g.nc[2] : 0;
+                nz -= nz >= a.g.nc[2] ? a.g.nc[2] : 0;
+                const int row_base = (nz * a.g.nc[1] + ny) * a.g.nc[0];
+                int4 run = make_int4(0, 0, 0, 0);
+                if (staged) run = runs[run_base + row];
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const int code = row * 3 + dx;
+                    int nx = cx + dx - 1;
+                    nx += nx < 0 ? a.g.nc[0] : 0;
+                    nx -= nx >= a.g.nc[0] ? a.g.nc[0] : 0;
+                    const int s0 = a.cell_start[row_base + nx], s1 = a.cell_start[row_base + nx + 1];
+                    const float xr = xf - offset32[code][0], yr = yf - offset32[code][1], zr = zf - offset32[code][2];
+                    // value stored for neighbour s_j: its slot in the staged copy times three (the copy holds (x, y, z)
+                    // triples: the offset of its x in doubles), or its frame index
+                    const int frame_first = 2 + a.ext_start[a.e.index(cx + dx, uy + 1, uz + 1)];  // unwrapped: the image seen from here
+                    const int tag = (staged ? run.z + (frame_first - run.x) : frame_first) - s0;
+                    const int factor = staged ? 3 : 1;
+                    for (int first = s0; first < s1; first += 8) {
+                        float4 f[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) f[u] = __ldg(a.sorted_f32 + min(first + u, s1 - 1));
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int s_j = first + u;
+                            const float ddx = xr - f[u].x, ddy = yr - f[u].y, ddz = zr - f[u].z;
+                            const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                            if (r2 < a.radius2 && s_j != s_i && s_j < s1) {
+                                if (count < a.capacity) {
+                                    int level = (int)floorf((sqrtf(r2) - a.cutoff) * a.inv_delta);
+                                    level = max(0, min(LJ2_LEVELS - 1, level));
+                                    mine[count & 3] = ((unsigned)level << 28) | (unsigned)(factor * (tag + s_j));
+                                    if ((count & 3) == 3) column[(count >> 2) * 32] = make_uint4(mine[0], mine[1], mine[2], mine[3]);
+                                }
+                                count++;
+                            }
+                        }
+                    }
+                }
+            }
+            if (active) {
+                if (count > a.capacity) {
+                    a.flags[FLAG_OVERFLOW] = 1;
+                    count = a.capacity;
+                }
+                if ((count & 3) != 0) {
+                    for (int k = count & 3; k < 4; k++) mine[k] = 0u;
+                    column[(count >> 2) * 32] = make_uint4(mine[0], mine[1], mine[2], mine[3]);
+                }
+                a.ncount[s_i] = count;
+            } else if (s_i < he) {
+                a.ncount[s_i] = 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the rebuild as one cooperative kernel
+// ------------------------------------------------------------------------------------------------
+
+struct Rebuild2Args {
+    int n, ncells, scan_blocks, ext_scan_blocks, nunits, epoch;
+    GridView g;
+    ExtGrid e;
+    const double* position;
+    int *cell_of, *slot_of, *cell_count, *cell_start, *scan_scratch, *grouped, *ext_start, *ext_pad;
+    Scatter2Args scatter;
+    Frame2Args frame;
+    Table2Args table;
+    Build2Args build;
+    int* flags;
+};
+
+__global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args r) {
+    if (r.flags[FLAG_REBUILD] != r.epoch) return;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ int scan_shared[33];
+    __shared__ float offset32[27][3];
+    __shared__ unsigned pending[REBUILD_THREADS][4];
+    if (threadIdx.x < 27) {
+        const int t = threadIdx.x;
+        offset32[t][0] = (float)((double)((t % 3) - 1) * r.g.edge[0]);
+        offset32[t][1] = (float)((double)(((t / 3) % 3) - 1) * r.g.edge[1]);
+        offset32[t][2] = (float)((double)((t / 9) - 1) * r.g.edge[2]);
+    }
+    const int atom_blocks = (r.n + REBUILD_THREADS - 1) / REBUILD_THREADS;
+
+    cell_zero_phase(r.ncells + 1, r.cell_count, r.build.cell_needed, r.flags);
+    if (blockIdx.x == 0 && threadIdx.x == 0) r.flags[FLAG_FRAME_OVERFLOW] = 0;
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
+        cell_assign_phase(vb, r.n, r.g, r.position, r.cell_of, r.slot_of, r.cell_count, r.flags);
+    }
+    grid.sync();
+    if (r.flags[FLAG_NONFINITE] != 0) return;
+    for (int vb = blockIdx.x; vb < r.scan_blocks; vb += gridDim.x) {
+        scan_blocks_phase(vb, r.ncells, r.cell_count, r.cell_start, r.scan_scratch, scan_shared);
+    }
+    grid.sync();
+    if (blockIdx.x == 0) scan_sums_phase(r.scan_blocks, r.scan_scratch, scan_shared);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < r.scan_blocks; vb += gridDim.x) {
+        scan_add_phase(vb, r.ncells, r.cell_start, r.scan_scratch, r.n);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
+        cell_group_phase(vb, r.n, r.cell_of, r.slot_of, r.cell_start, r.grouped);
+    }
+    // the extended cells only need cell_start: their padded counts are formed alongside
+    ext_count_phase(r.e, r.cell_start, r.ext_pad);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) scatter2_phase(vb, r.scatter, r.flags);
+    grid.sync();
+    if (r.flags[FLAG_NONFINITE] != 0) return;
+    const int next = r.e.count();
+    for (int vb = blockIdx.x; vb < r.ext_scan_blocks; vb += gridDim.x) {
+        scan_blocks_phase(vb, next, r.ext_pad, r.ext_start, r.scan_scratch, scan_shared);
+    }
+    grid.sync();
+    if (blockIdx.x == 0) scan_sums_phase(r.ext_scan_blocks, r.scan_scratch, scan_shared);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < r.ext_scan_blocks; vb += gridDim.x) {
+        scan_add_total_phase(vb, next, r.ext_pad, r.ext_start, r.scan_scratch);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) frame2_phase(vb, r.frame, r.flags);
+    for (int vb = blockIdx.x; vb * REBUILD_WARPS < r.nunits; vb += gridDim.x) unit_table_phase(vb, r.table);
+    grid.sync();
+    for (int vb = blockIdx.x; vb * REBUILD_WARPS * r.build.cells_per_warp < r.ncells * BUILD2_CHUNKS; vb += gridDim.x) {
+        list_build2_phase(vb, r.build, offset32, pending);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        r.flags[FLAG_COUNT] += 1;
+        // the frames hold the rebuild positions: nothing has moved yet
+        r.flags[FLAG_DISP] = 0;
+        r.flags[FLAG_DISP + 1] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// final order of the columns: by level, bank-aware inside a level, two streams per atom
+// ------------------------------------------------------------------------------------------------
+//
+// A staged copy holds (x, y, z) triples of doubles, so coordinate c of slot s sits in the 8-byte bank pair (3 s + c) mod
+// 16: two lanes of a half warp collide when their slots are different and congruent modulo 16 (3 is invertible mod 16;
+// list entries are 3 s, whose low four bits are the bucket).  Lanes 2a + h of a half warp (eight atoms, two
+// halves) read entry 8 w + 4 h + q of their column at sub-step t = 4 w + q: the entry emitted for that position is
+// taken, while the buckets of the current level last, from residue (2 (a mod 8) + h + t) mod 16, so the sixteen lanes
+// of a half warp touch sixteen different bank pairs.
+
+constexpr int REORDER2_THREADS = 32;
+
+__global__ void __launch_bounds__(REORDER2_THREADS)
+    list_reorder2_kernel(int n, int capacity, const int4* __restrict__ header, const int* __restrict__ ncount,
+                         unsigned* __restrict__ nlist, unsigned short* __restrict__ cum_levels, int epoch,
+                         const int* __restrict__ flags) {
+    if (flags[FLAG_REBUILD] != epoch || flags[FLAG_NONFINITE] != 0) return;
+    extern __shared__ unsigned reorder2_smem[];
+    unsigned* sorted = reorder2_smem;  // entry p of thread t at [p * 32 + t], grouped by (level, residue)
+    __shared__ unsigned short cursor[LJ2_LEVELS * 16][REORDER2_THREADS], last[LJ2_LEVELS * 16][REORDER2_THREADS];
+    const int t = threadIdx.x;
+    for (int slab = blockIdx.x; slab * REORDER2_THREADS < n; slab += gridDim.x) {
+        const int s_i = slab * REORDER2_THREADS + t;
+        if (s_i >= n) continue;
+        const bool staged = header[s_i / U_ATOMS].z >= 0;
+        const int count = ncount[s_i];
+        uint4* words = reinterpret_cast<uint4*>(nlist) + (size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31);
+        const int nwords = (count + 3) >> 2;
+        for (int b = 0; b < LJ2_LEVELS * 16; b++) last[b][t] = 0;
+        for (int w = 0; w < nwords; w++) {
+            const uint4 word = words[w * 32];
+            const unsigned e[4] = {word.x, word.y, word.z, word.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (4 * w + q < count) last[(e[q] >> 28) * 16 + (staged ? (e[q] & 15u) : 0u)][t]++;
+            }
+        }
+        int running = 0;
+        for (int b = 0; b < LJ2_LEVELS * 16; b++) {
+            cursor[b][t] = (unsigned short)running;
+            running += last[b][t];
+            last[b][t] = (unsigned short)running;
+            if ((b & 15) == 15) cum_levels[(size_t)s_i * LJ2_LEVELS + (b >> 4)] = (unsigned short)running;
+        }
+        for (int w = 0; w < nwords; w++) {
+            const uint4 word = words[w * 32];
+            const unsigned e[4] = {word.x, word.y, word.z, word.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (4 * w + q < count) {
+                    const int position = cursor[(e[q] >> 28) * 16 + (staged ? (e[q] & 15u) : 0u)][t]++;
+                    sorted[position * REORDER2_THREADS + t] = e[q] & RAW_VALUE_MASK;
+                }
+            }
+        }
+        // rewind
+        running = 0;
+        for (int b = 0; b < LJ2_LEVELS * 16; b++) {
+            cursor[b][t] = (unsigned short)running;
+            running = last[b][t];
+        }
+        if (!staged) {
+            // frame indices, four per word, in level order; padding points at the dummy frame slot 0
+            for (int w = 0; w < nwords; w++) {
+                unsigned e[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) e[q] = 4 * w + q < count ? sorted[(4 * w + q) * REORDER2_THREADS + t] : 0u;
+                words[w * 32] = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+            continue;
+        }
+        const int lane_base = LJ2_LPA * (s_i & (16 / LJ2_LPA - 1));
+        unsigned packed[4] = {0u, 0u, 0u, 0u};
+        int level = -1, level_end = 0;
+        unsigned nonempty = 0;  // buckets of the current level that still hold entries
+        for (int p = 0; p < count; p++) {
+            while (p >= level_end) {
+                level++;
+                level_end = level == LJ2_LEVELS - 1 ? count : (int)last[level * 16 + 15][t];
+                nonempty = 0;
+                for (int b = 0; b < 16; b++) nonempty |= cursor[level * 16 + b][t] != last[level * 16 + b][t] ? 1u << b : 0u;
+            }
+            // entry p sits in word p >> 3, half (p >> 2) & 1; with four lanes per atom, lanes {0, 1} walk the even words and
+            // {2, 3} the odd ones
+            const int word = p >> 3;
+            const int h = ((word % LJ2_WORD_STRIDE) << 1) | ((p >> 2) & 1), step = ((word / LJ2_WORD_STRIDE) << 2) | (p & 3);
+            const int want = (lane_base + h + step) & 15;
+            // first non-empty bucket at or after `want`, cyclically
+            const unsigned rotated = ((nonempty >> want) | (nonempty << (16 - want))) & 0xffffu;
+            const int b = (want + __ffs(rotated) - 1) & 15;
+            const int position = cursor[level * 16 + b][t]++;
+            if (position + 1 == (int)last[level * 16 + b][t]) nonempty &= ~(1u << b);
+            const unsigned slot = sorted[position * REORDER2_THREADS + t];
+            packed[(p & 7) >> 1] |= slot << (16 * (p & 1));
+            if ((p & 7) == 7) {
+                words[(p >> 3) * 32] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                packed[0] = packed[1] = packed[2] = packed[3] = 0u;
+            }
+        }
+        if ((count & 7) != 0) words[(count >> 3) * 32] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-evaluation refresh of the frames
+// ------------------------------------------------------------------------------------------------
+
+struct Update2Args {
+    int n;
+    int s_lo, s_hi;  // sorted range refreshed by this rank
+    GridView g;
+    ExtGrid e;
+    const int* __restrict__ order;  // sorted slot -> state index (nullptr: the state arrays are in sorted order)
+    const double* __restrict__ pos;
+    const double* __restrict__ xref;
+    const int* __restrict__ kshift;
+    const int* __restrict__ fidx;
+    const int* __restrict__ sorted_cell;
+    const int* __restrict__ cell_start;
+    const int* __restrict__ ext_start;
+    double* __restrict__ frame;  // (x, y, z) per frame slot
+    size_t fstride;
+    double scale;
+    double threshold2;
+    int epoch;
+    int* __restrict__ flags;
+};
+
+// Positions keep the periodic image they had at the rebuild (frame = x - k L with the wrap counts of the rebuild); the
+// largest squared displacement since the rebuild is reduced per block and folded with an integer atomicMax of its float
+// bits (non-negative floats order like their bit patterns).
+__global__ void __launch_bounds__(256) lj2_update_kernel(Update2Args a) {
+    __shared__ float block_max[8];
+    const int s = a.s_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.flags[FLAG_DISP + ((a.epoch + 1) & 1)] = 0;  // the slot of the next evaluation
+        a.flags[FLAG_DEFERRED] = 0;
+    }
+    float d2f = 0.0f;
+    if (s < a.s_hi) {
+        const int i = a.order != nullptr ? a.order[s] : s;
+        const double px = a.pos[3 * i], py = a.pos[3 * i + 1], pz = a.pos[3 * i + 2];
+        const double dx = px - a.xref[3 * s], dy = py - a.xref[3 * s + 1], dz = pz - a.xref[3 * s + 2];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (!(d2 <= a.threshold2)) a.flags[FLAG_REBUILD] = a.epoch;  // also catches NaN
+        d2f = __double2float_ru(d2);
+        if (!(d2f >= 0.0f)) d2f = 3.0e38f;
+        int kx, ky, kz;
+        unpack_shift(a.kshift[s], kx, ky, kz);
+        const double x = px - (double)kx * a.g.length[0];
+        const double y = py - (double)ky * a.g.length[1];
+        const double z = pz - (double)kz * a.g.length[2];
+        const int c = a.sorted_cell[s];
+        const int rank = s - a.cell_start[c];
+        for_each_image(a.e, a.ext_start, c, rank, [&](int f, int sx, int sy, int sz) {
+            a.frame[3 * (size_t)f] = (x + (double)sx * a.g.length[0]) * a.scale;
+            a.frame[3 * (size_t)f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
+            a.frame[3 * (size_t)f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
+        });
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+    if ((threadIdx.x & 31) == 0) block_max[threadIdx.x >> 5] = d2f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = block_max[0];
+        for (int w = 1; w < 8; w++) m = fmaxf(m, block_max[w]);
+        atomicMax(a.flags + FLAG_DISP + (a.epoch & 1), __float_as_int(m));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// force kernel
+// ------------------------------------------------------------------------------------------------
+
+struct Lj2Args {
+    int n;
+    int u_lo, u_hi;  // units of this rank
+    int capacity;
+    const unsigned* __restrict__ nlist;
+    const unsigned short* __restrict__ cum_levels;
+    const unsigned short* __restrict__ self_slot;
+    const int* __restrict__ fidx;
+    const int* __restrict__ order;  // nullptr: state arrays in sorted order
+    const int4* __restrict__ header;
+    const int4* __restrict__ runs;
+    const double* __restrict__ frame;  // (x, y, z) per frame slot
+    size_t fstride;
+    double epsilon24, epsilon48, epsilon4, shift, inv_sigma;
+    int band_lo;           // top 32 bits of (rc / sigma)^2, minus one: below it a pair is inside the cut-off
+    float inv_delta, margin;  // levels needed: floor((2 dmax + margin) * inv_delta) + 1
+    int epoch;
+    int all_levels;  // experiment knob: walk every level whatever the displacement
+    int write_forces;
+    double* __restrict__ force;
+    double* __restrict__ partials;
+    int2* __restrict__ deferred;  // (state index of i, frame index of j)
+    int deferred_capacity;
+    int* __restrict__ flags;
+};
+
+__device__ __forceinline__ unsigned smem_address(const void* pointer) { return (unsigned)__cvta_generic_to_shared(pointer); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* barrier, unsigned arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_address(barrier)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_bytes(unsigned long long* barrier, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_address(barrier)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* barrier) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_address(barrier)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* barrier, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred done;\n"
+        "LJ2_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+        "@done bra LJ2_WAIT_DONE;\n"
+        "bra LJ2_WAIT_LOOP;\n"
+        "LJ2_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_address(barrier)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void async_copy16(void* shared_dst, const void* global_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_address(shared_dst)), "l"(global_src) : "memory");
+}
+__device__ __forceinline__ void bulk_load(double* shared_dst, const double* global_src, unsigned bytes, unsigned long long* barrier) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_address(shared_dst)),
+                 "l"(global_src), "r"(bytes), "r"(smem_address(barrier))
+                 : "memory");
+}
+
+// One listed neighbour: 17 FP64 instructions, no branch.  Lengths are in units of sigma, so 1 / r^2 is s2 directly; the
+// cut-off test compares the top 32 bits of r^2 on the integer pipe (r^2 >= 0: the bit patterns order like the values),
+// a pair outside gets a zero reciprocal seed and contributes exactly zero.  `near` collects the pairs whose r^2 falls
+// in the three-value band around the cut-off: they are evaluated by the fix-up kernel.
+template <int MODE>
+__device__ __forceinline__ void lj2_pair(const Lj2Args& a, double xj, double yj, double zj, double xi, double yi, double zi,
+                                         double& fx, double& fy, double& fz, double (&acc)[LJ2_NV], unsigned& near, unsigned bit) {
+    const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const int top = __double2hiint(r2);
+    const bool inside = top < a.band_lo;
+    near |= (unsigned)(top - a.band_lo) < 3u ? bit : 0u;
+    double seed;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(r2));
+    const double y = __hiloint2double(inside ? __double2hiint(seed) : 0, 0);
+    // one cubically convergent step, y (1 + e + e^2) with e = 1 - r2 y
+    const double e = fma(-r2, y, 1.0);
+    const double s2 = fma(y, fma(e, e, e), y);
+    const double s4 = s2 * s2;
+    const double s6 = s4 * s2;
+    // sigma^2 force(r) / r = -24 eps (s6 - 2 s6^2) s2 (functions.rs:85-88); rescaled by 1 / sigma at the end
+    const double fr = (s4 * s4) * fma(a.epsilon48, s6, -a.epsilon24);
+    fx = fma(fr, dx, fx);
+    fy = fma(fr, dy, fy);
+    fz = fma(fr, dz, fz);
+    if (MODE == 1) {
+        const double energy = a.epsilon4 * fma(s6, s6, -s6) - a.shift;
+        acc[0] += inside ? energy : 0.0;
+        acc[14] += inside ? 1.0 : 0.0;
+        acc[2] += fr * dx * dx;
+        acc[3] += fr * dx * dy;
+        acc[4] += fr * dx * dz;
+        acc[5] += fr * dy * dy;
+        acc[6] += fr * dy * dz;
+        acc[7] += fr * dz * dz;
+    }
+}
+
+// the four neighbours of a half word: positions out of the staged copy, then the four pair evaluations
+struct Staged4 {
+    double x[4], y[4], z[4];
+    __device__ __forceinline__ void load(const double* __restrict__ buffer, const uint2& word) {
+        const unsigned j[4] = {word.x & 0xffffu, word.x >> 16, word.y & 0xffffu, word.y >> 16};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            x[q] = buffer[j[q]];
+            y[q] = buffer[j[q] + 1];
+            z[q] = buffer[j[q] + 2];
+        }
+    }
+    template <int MODE>
+    __device__ __forceinline__ void evaluate(const Lj2Args& a, double xi, double yi, double zi, double& fx, double& fy, double& fz,
+                                             double (&acc)[LJ2_NV], unsigned& near) const {
+#pragma unroll
+        for (int q = 0; q < 4; q++) lj2_pair<MODE>(a, x[q], y[q], z[q], xi, yi, zi, fx, fy, fz, acc, near, 1u << q);
+    }
+};
+
+// rare: remember the pairs of this half word that sit on the cut-off
+__device__ __noinline__ void lj2_defer(const int4* __restrict__ header, const int4* __restrict__ runs, int2* __restrict__ deferred,
+                                       int deferred_capacity, int* __restrict__ flags, int unit, int state_i, unsigned near,
+                                       unsigned lo, unsigned hi, bool staged) {
+    const unsigned entries[2] = {lo, hi};
+    for (int k = 0; k < 4; k++) {
+        if (!(near & (1u << k))) continue;
+        int frame_index;
+        if (staged) {
+            const int slot = (int)((entries[k >> 1] >> (16 * (k & 1))) & 0xffffu) / 3;
+            frame_index = -1;
+            const int nruns = header[unit].z;
+            for (int r = 0; r < nruns; r++) {
+                const int4 run = runs[(size_t)unit * LJ2_MAX_RUNS + r];
+                if (slot >= run.z && slot < run.z + run.y) frame_index = run.x + (slot - run.z);
+            }
+            if (frame_index < 0) continue;  // the dummy
+        } else {
+            if (k >= 2) continue;
+            frame_index = (int)entries[k];
+        }
+        const int position = atomicAdd(flags + FLAG_DEFERRED, 1);
+        if (position < deferred_capacity) deferred[position] = make_int2(state_i, frame_index);
+    }
+}
+
+// This lane's view of the column of sorted atom s: 8-byte halves of the 16-byte words word_first, word_first + 2, ...
+// (uint2 stride 128 between them); word w of atom s sits at ((s >> 5) * slab_words + w * 32 + (s & 31)) in uint4 units.
+__device__ __forceinline__ const uint2* lj2_column(const unsigned* __restrict__ nlist, size_t slab_words, int s, int word_first, int half) {  // uint2 stride between its words: 64 * LJ2_WORD_STRIDE
+    const uint4* base = reinterpret_cast<const uint4*>(nlist) + (size_t)(s >> 5) * slab_words + (size_t)word_first * 32 + (s & 31);
+    return reinterpret_cast<const uint2*>(base) + half;
+}
+
+// Bulk copies of one unit's neighbourhood into a staging buffer, issued by one warp: ONE copy per run (the frames hold
+// (x, y, z) triples; with one plane per coordinate the three times more numerous, three times smaller copies kept the
+// SM's copy engine busy for longer than the pairs took: profiles/r2d_*), completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void lj2_issue_copies(const Lj2Args& a, const int4* __restrict__ table, double* buffer, unsigned long long* barrier, int lane) {
+    // table[0]: header of the unit, table[1 ...]: its runs (global memory, or the copy a warp left in shared memory)
+    const int4 header = table[0];
+    if (header.z < 0) {
+        // not staged: the consumers gather from global memory, the barrier only has to complete its phase
+        if (lane == 0) mbar_arrive(barrier);
+        return;
+    }
+    if (lane == 0) mbar_expect_bytes(barrier, 24u * (unsigned)(header.w - 2));
+    __syncwarp();
+    for (int r = lane; r < header.z; r += 32) {
+        const int4 run = table[1 + r];
+        bulk_load(buffer + 3 * run.z, a.frame + 3 * (size_t)run.x, (unsigned)run.y * 24u, barrier);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(LJ2_THREADS, 1) lj2_force_kernel(Lj2Args a) {
+    extern __shared__ __align__(16) unsigned char lj2_smem[];
+    double* stage = reinterpret_cast<double*>(lj2_smem);  // two buffers of three planes
+    __shared__ __align__(8) unsigned long long full[LJ2_BUFFERS];
+    __shared__ int done[LJ2_BUFFERS];  // warps that have finished with each buffer
+    __shared__ int4 refill_table[LJ2_BUFFERS][1 + LJ2_MAX_RUNS];  // header and runs of the unit that will refill each buffer
+
+    if (a.flags[FLAG_NONFINITE] != 0) return;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    if (tid == 0) {
+        for (int b = 0; b < LJ2_BUFFERS; b++) {
+            mbar_init(&full[b], 1);
+            done[b] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 6 * LJ2_BUFFERS) {
+        // slots 0 and 1 of every buffer: the dummy, far outside any cut-off
+        const int buffer = tid / 6, slot = (tid % 6) / 3, coordinate = tid % 3;
+        stage[(size_t)buffer * 3 * LJ2_SLOTS + 3 * slot + coordinate] = 1.0e9 * (double)(coordinate + 1);
+    }
+    __syncthreads();
+
+    double acc[LJ2_NV];
+#pragma unroll
+    for (int k = 0; k < LJ2_NV; k++) acc[k] = 0.0;
+
+    const int first_unit = a.u_lo + blockIdx.x, stride = gridDim.x;
+    // the first units: copies issued by warp 0; afterwards the LAST warp to finish unit k issues the copies of unit
+    // k + LJ2_BUFFERS into the buffer it has just released, so no warp ever waits for a buffer to drain
+    if (tid < 32) {
+        for (int b = 0; b < LJ2_BUFFERS; b++) {
+            const int unit = first_unit + b * stride;
+            if (unit >= a.u_hi) break;
+            if (lane == 0) refill_table[b][0] = a.header[unit];
+            for (int r = lane; r < LJ2_MAX_RUNS; r += 32) refill_table[b][1 + r] = a.runs[(size_t)unit * LJ2_MAX_RUNS + r];
+            __syncwarp();
+            lj2_issue_copies(a, refill_table[b], stage + (size_t)b * 3 * LJ2_SLOTS, &full[b], lane);
+        }
+    }
+    {
+        // ---- consumers ------------------------------------------------------------------------------------------
+        // the LJ2_LPA lanes of an atom: lanes {0, 1} take the two halves of its words (of the even words with four lanes per atom,
+        // lanes {2, 3} then take the odd ones)
+        const int local = tid / LJ2_LPA, sub = tid % LJ2_LPA;
+        const int word_first = sub >> 1, half = sub & 1;
+        // levels to walk: pairs listed at r_b >= rc + 2 dmax cannot have come inside the cut-off
+        const float dmax = sqrtf(__int_as_float(a.flags[FLAG_DISP + (a.epoch & 1)])) * 1.000001f;
+        int nlevels = (int)((2.0f * dmax + a.margin) * a.inv_delta) + 1;
+        nlevels = max(1, min(LJ2_LEVELS, nlevels));
+        if (a.all_levels == 1) nlevels = LJ2_LEVELS;
+        const size_t slab_words = (size_t)(a.capacity >> 2) * 32;  // uint4 words per slab of 32 columns
+
+        // head of the first unit
+        int s = first_unit * U_ATOMS + local;
+        int count = 0;
+        unsigned self = 0;
+        // the first four words of the lane's walk, loaded one unit ahead (whatever the count: the slab is allocated; what
+        // lies behind the walked prefix is discarded when the unit starts)
+        uint2 h0 = make_uint2(0, 0), h1 = make_uint2(0, 0), h2 = make_uint2(0, 0), h3 = make_uint2(0, 0);
+        if (first_unit < a.u_hi && s < a.n) {
+            count = a.cum_levels[(size_t)s * LJ2_LEVELS + nlevels - 1];
+            self = a.self_slot[s];
+            const uint2* words = lj2_column(a.nlist, slab_words, s, word_first, half);
+            h0 = words[0];
+            h1 = words[64 * LJ2_WORD_STRIDE];
+            h2 = words[2 * 64 * LJ2_WORD_STRIDE];
+            h3 = words[3 * 64 * LJ2_WORD_STRIDE];
+        }
+        int b = 0, phase = 0;  // buffer k mod 3 and the parity of its use number k / 3
+        for (int unit = first_unit; unit < a.u_hi; unit += stride) {
+            const int s_now = s, count_now = a.all_levels == 2 ? 0 : count;  // experiment knob 2: staging only
+            const unsigned self_now = self;
+            uint2 wcur = h0, wnext = h1, w2 = h2, w3 = h3;
+            // head of the next unit: in flight while this one is evaluated
+            const int next_unit = unit + stride;
+            s = next_unit * U_ATOMS + local;
+            count = 0;
+            const uint2* next_words = nullptr;
+            if (next_unit < a.u_hi && s < a.n) {
+                count = a.cum_levels[(size_t)s * LJ2_LEVELS + nlevels - 1];
+                self = a.self_slot[s];
+                next_words = lj2_column(a.nlist, slab_words, s, word_first, half);
+                h0 = next_words[0];
+                h1 = next_words[64 * LJ2_WORD_STRIDE];
+                h2 = next_words[2 * 64 * LJ2_WORD_STRIDE];
+                h3 = next_words[3 * 64 * LJ2_WORD_STRIDE];
+            }
+            const int4 header = a.header[unit];
+            const bool staged = header.z >= 0;
+            const bool present = s_now < a.n;
+            const int state_i = present ? (a.order != nullptr ? a.order[s_now] : s_now) : 0;
+            const uint2* words = lj2_column(a.nlist, slab_words, s_now, word_first, half);
+            double fx = 0.0, fy = 0.0, fz = 0.0;
+            mbar_wait(&full[b], phase);
+            // the table of the unit that will refill this buffer: fetched by warp 0 with asynchronous copies once this unit's
+            // bulk copies have landed (so the table they were issued from is free); it is complete before warp 0 reports this
+            // unit done, and used by whichever warp finishes the unit last
+            if (tid < 32 && unit + LJ2_BUFFERS * stride < a.u_hi) {
+                const int refill = unit + LJ2_BUFFERS * stride;
+                if (lane == 0) async_copy16(&refill_table[b][0], a.header + refill);
+                for (int r = lane; r < LJ2_MAX_RUNS; r += 32) async_copy16(&refill_table[b][1 + r], a.runs + (size_t)refill * LJ2_MAX_RUNS + r);
+            }
+            if (staged) {
+                const double* buffer = stage + (size_t)b * 3 * LJ2_SLOTS;
+                const double xi = buffer[self_now], yi = buffer[self_now + 1], zi = buffer[self_now + 2];
+                // words of this lane: word_first, word_first + LJ2_WORD_STRIDE, ... of the (count + 7) / 8 words of the prefix
+                const int nwords = (((count_now + 7) >> 3) - word_first + LJ2_WORD_STRIDE - 1) / LJ2_WORD_STRIDE;
+                // Software pipeline, unrolled four words deep: the list words of a column come from DRAM (the list is the
+                // only stream of the kernel), so four of them are in flight per thread and the lines further ahead are
+                // pulled into L2; the twelve position loads of the next half word are issued before the current four
+                // pairs are evaluated.
+                // words behind the walked prefix may hold anything: never turned into shared-memory addresses
+                if (0 >= nwords) wcur = make_uint2(0, 0);
+                if (1 >= nwords) wnext = make_uint2(0, 0);
+                if (2 >= nwords) w2 = make_uint2(0, 0);
+                if (3 >= nwords) w3 = make_uint2(0, 0);
+#if LJ2_ILP8
+                // eight independent pair chains per thread: the positions of two half words are loaded, then both are evaluated
+                // in one basic block (the FP64 pipe is latency-bound with four chains per thread and four warps per scheduler)
+                for (int w = 0; w < nwords; w += 4) {
+                    Staged4 pa, pb;
+                    pa.load(buffer, wcur);
+                    pb.load(buffer, wnext);
+                    unsigned near = 0, near_b = 0;
+                    pa.evaluate<MODE>(a, xi, yi, zi, fx, fy, fz, acc, near);
+                    pb.evaluate<MODE>(a, xi, yi, zi, fx, fy, fz, acc, near_b);
+                    if ((near | near_b) != 0) {
+                        if (near != 0) lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, state_i, near, wcur.x, wcur.y, true);
+                        if (near_b != 0) lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, state_i, near_b, wnext.x, wnext.y, true);
+                    }
+                    wcur = make_uint2(0, 0);
+                    wnext = make_uint2(0, 0);
+                    if (w + 4 < nwords) wcur = words[(size_t)(w + 4) * 64 * LJ2_WORD_STRIDE];
+                    if (w + 5 < nwords) wnext = words[(size_t)(w + 5) * 64 * LJ2_WORD_STRIDE];
+                    if (next_words != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(next_words + (size_t)(w + 4) * 64 * LJ2_WORD_STRIDE));
+                    if (w + 2 >= nwords) break;
+                    pa.load(buffer, w2);
+                    pb.load(buffer, w3);
+                    near = 0;
+                    near_b = 0;
+                    pa.evaluate<MODE>(a, xi, yi, zi, fx, fy, fz, acc, near);
+                    pb.evaluate<MODE>(a, xi, yi, zi, fx, fy, fz, acc, near_b);
+                    if ((near | near_b) != 0) {
+                        if (near != 0) lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, state_i, near, w2.x, w2.y, true);
+                        if (near_b != 0) lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, state_i, near_b, w3.x, w3.y, true);
+                    }
+                    w2 = make_uint2(0, 0);
+                    w3 = make_uint2(0, 0);
+                    if (w + 6 < nwords) w2 = words[(size_t)(w + 6) * 64 * LJ2_WORD_STRIDE];
+                    if (w + 7 < nwords) w3 = words[(size_t)(w + 7) * 64 * LJ2_WORD_STRIDE];
+                    if (next_words != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(next_words + (size_t)(w + 6) * 64 * LJ2_WORD_STRIDE));
+                }
+#else
+                Staged4 pa, pb;
+                pa.load(buffer, wcur);
+#define LJ2_STEP(CUR, NEXT_POS, WORD_NOW, WORD_NEXT, AHEAD)                                                              \
+    {                                                                                                                      \
+        NEXT_POS.load(buffer, WORD_NEXT);                                                                                  \
+        unsigned near = 0;                                                                                                 \
+        CUR.evaluate<MODE>(a, xi, yi, zi, fx, fy, fz, acc, near);                                                          \
+        if (near != 0) {                                                                                                   \
+            lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, state_i, near, WORD_NOW.x, WORD_NOW.y, true); \
+        }                                                                                                                  \
+        WORD_NOW = make_uint2(0, 0);                                                                                       \
+        if (w + (AHEAD) < nwords) WORD_NOW = words[(size_t)(w + (AHEAD)) * 64 * LJ2_WORD_STRIDE];                          \
+        if (next_words != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(next_words + (size_t)(w + (AHEAD)) * 64 * LJ2_WORD_STRIDE)); \
+    }
+                for (int w = 0; w < nwords; w += 4) {
+                    LJ2_STEP(pa, pb, wcur, wnext, 4)
+                    if (w + 1 >= nwords) break;
+                    LJ2_STEP(pb, pa, wnext, w2, 5)
+                    if (w + 2 >= nwords) break;
+                    LJ2_STEP(pa, pb, w2, w3, 6)
+                    if (w + 3 >= nwords) break;
+                    LJ2_STEP(pb, pa, w3, wcur, 7)
+                }
+#undef LJ2_STEP
+#endif
+            } else if (present) {
+                // unit whose neighbourhood does not fit in shared memory: 32-bit frame indices, global gathers
+                const int f_self = a.fidx[s_now];
+                const double xi = a.frame[3 * (size_t)f_self], yi = a.frame[3 * (size_t)f_self + 1], zi = a.frame[3 * (size_t)f_self + 2];
+                const int nwords = (((count_now + 3) >> 2) - word_first + LJ2_WORD_STRIDE - 1) / LJ2_WORD_STRIDE;
+                for (int w = 0; w < nwords; w++) {
+                    const uint2 word = words[(size_t)w * 64 * LJ2_WORD_STRIDE];
+                    unsigned near = 0;
+                    const unsigned j0 = word.x, j1 = word.y;
+                    lj2_pair<MODE>(a, a.frame[3 * (size_t)j0], a.frame[3 * (size_t)j0 + 1], a.frame[3 * (size_t)j0 + 2], xi, yi, zi, fx, fy, fz, acc, near, 1u);
+                    lj2_pair<MODE>(a, a.frame[3 * (size_t)j1], a.frame[3 * (size_t)j1 + 1], a.frame[3 * (size_t)j1 + 2], xi, yi, zi, fx, fy, fz, acc, near, 2u);
+                    if (near != 0) lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, state_i, near, word.x, word.y, false);
+                }
+            }
+            // the lanes of an atom
+#pragma unroll
+            for (int o = 1; o < LJ2_LPA; o <<= 1) {
+                fx += __shfl_xor_sync(0xffffffffu, fx, o);
+                fy += __shfl_xor_sync(0xffffffffu, fy, o);
+                fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            }
+            if (present && sub == 0 && a.write_forces) {
+                a.force[3 * state_i] = fx * a.inv_sigma;
+                a.force[3 * state_i + 1] = fy * a.inv_sigma;
+                a.force[3 * state_i + 2] = fz * a.inv_sigma;
+            }
+            // hand the buffer back; the last warp of the block refills it
+            if (tid < 32) asm volatile("cp.async.wait_all;" ::: "memory");
+            __threadfence_block();
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) last = atomicAdd(&done[b], 1) == LJ2_THREADS / 32 - 1 ? 1 : 0;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                if (lane == 0) done[b] = 0;
+                const int refill = unit + LJ2_BUFFERS * stride;
+                if (refill < a.u_hi) lj2_issue_copies(a, refill_table[b], stage + (size_t)b * 3 * LJ2_SLOTS, &full[b], lane);
+            }
+            if (++b == LJ2_BUFFERS) {
+                b = 0;
+                phase ^= 1;
+            }
+        }
+    }
+
+    if (MODE == 1) {
+        // every pair was visited from both sides: half of the energy and virial from each
+#pragma unroll
+        for (int k = 0; k < LJ2_NV; k++) acc[k] *= 0.5;
+        __syncthreads();
+        block_sum<LJ2_NV>(acc, stage);  // the staged copies are dead
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < LJ2_NV; k++) a.partials[(size_t)blockIdx.x * LJ2_NV + k] = acc[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pairs on the cut-off: the reference's own arithmetic on the original coordinates
+// ------------------------------------------------------------------------------------------------
+
+struct Fix2Args {
+    const int2* __restrict__ deferred;
+    int capacity;
+    const int* __restrict__ frame_atom;
+    const int* __restrict__ order;  // nullptr: state arrays in sorted order
+    const double* __restrict__ pos;
+    double length[3];
+    double sigma, epsilon, cutoff, shift;
+    int full;
+    int write_forces;
+    double* __restrict__ force;
+    double* __restrict__ results;
+    int* __restrict__ flags;
+};
+
+__global__ void __launch_bounds__(128) lj2_fixup_kernel(Fix2Args a) {
+    const int count = min(a.flags[FLAG_DEFERRED], a.capacity);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const int2 entry = a.deferred[k];
+        const int i = entry.x;
+        const int s_j = a.frame_atom[entry.y];
+        if (s_j < 0) continue;
+        const int j = a.order != nullptr ? a.order[s_j] : s_j;
+        // nearest_image(i, j) (configuration.rs:399-403, cells.rs:287-291), no contraction: Rust never fuses
+        double d[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double raw = __dadd_rn(a.pos[3 * i + c], -a.pos[3 * j + c]);
+            d[c] = __dadd_rn(raw, -__dmul_rn(round(__ddiv_rn(raw, a.length[c])), a.length[c]));
+        }
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+        const double r = sqrt(r2);
+        if (r >= a.cutoff) continue;  // pairs.rs:186
+        // functions.rs:80-88
+        const double s = a.sigma / r;
+        const double s2 = s * s;
+        const double s6 = s2 * (s2 * s2);
+        const double energy = 4.0 * a.epsilon * (s6 * s6 - s6) - a.shift;
+        const double force = -24.0 * a.epsilon * (s6 - 2.0 * (s6 * s6)) / r;
+        const double fr = force / r;
+        if (a.write_forces) {
+            atomicAdd(a.force + 3 * i, fr * d[0]);
+            atomicAdd(a.force + 3 * i + 1, fr * d[1]);
+            atomicAdd(a.force + 3 * i + 2, fr * d[2]);
+        }
+        if (a.full) {
+            atomicAdd(a.results + RES_E_PAIRS, 0.5 * energy);
+            atomicAdd(a.results + RES_PAIR_COUNT, 0.5);
+            const double w = 0.5 * fr;
+            atomicAdd(a.results + RES_W_PAIRS + 0, w * d[0] * d[0]);
+            atomicAdd(a.results + RES_W_PAIRS + 1, w * d[0] * d[1]);
+            atomicAdd(a.results + RES_W_PAIRS + 2, w * d[0] * d[2]);
+            atomicAdd(a.results + RES_W_PAIRS + 3, w * d[1] * d[1]);
+            atomicAdd(a.results + RES_W_PAIRS + 4, w * d[1] * d[2]);
+            atomicAdd(a.results + RES_W_PAIRS + 5, w * d[2] * d[2]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------------
+
+__global__ void lj2_set_flag_kernel(int* flags, int index, int value) { flags[index] = value; }
+
+static uint64_t mix2(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+bool lj2_enabled(const Context* ctx) {
+    static const char* knob = std::getenv("LUMOL_CUDA_LJ2");
+    if (knob != nullptr && knob[0] == '0') return false;
+    return ctx->nranks == 1;
+}
+
+int launch_pairs_lj2(Context* ctx, const ComputeRequest& req) {
+    const int n = (int)ctx->n;
+    GridView g;
+    for (int d = 0; d < 3; d++) {
+        g.nc[d] = ctx->ncell[d];
+        g.length[d] = ctx->cell.h[4 * d];
+        g.edge[d] = g.length[d] / (double)g.nc[d];
+    }
+    ExtGrid e;
+    e.nx = g.nc[0];
+    e.ny = g.nc[1];
+    e.nz = g.nc[2];
+    e.ex = e.nx + 2;
+    e.ey = e.ny + 2;
+    e.ez = e.nz + 2;
+    const int ncells = g.nc[0] * g.nc[1] * g.nc[2];
+    const int next = e.count();
+    const lumol_cuda_pair& p = ctx->host_pairs[0];
+    const double cutoff = p.cutoff;
+    const double skin = ctx->skin_effective;
+    const double radius = cutoff + skin;
+    const double sigma = p.p[0], epsilon = p.p[1];
+    const double scale = 1.0 / sigma;
+
+    // ---- buffers ---------------------------------------------------------------------------------
+    const double volume = g.length[0] * g.length[1] * g.length[2];
+    const double mean_neighbors = 4.0 / 3.0 * PI * radius * radius * radius * (double)n / volume;
+    int capacity = (int)(2.0 * mean_neighbors) + 64;
+    if (capacity > n) capacity = n;
+    capacity = (capacity + 7) / 8 * 8;
+    const size_t stride = ((size_t)n + 31) / 32 * 32;
+    const int nunits = (n + U_ATOMS - 1) / U_ATOMS;
+    // frame slots: the atoms, their ghost images (a boundary atom has up to seven), one slot of padding per extended cell
+    const double ghost_ratio = (double)next / (double)ncells;
+    size_t fstride = (size_t)((double)n * (ghost_ratio * 1.5 + 0.25)) + 2 * (size_t)next + 64;
+    if (fstride > (size_t)8 * n + 2 * (size_t)next + 64) fstride = (size_t)8 * n + 2 * (size_t)next + 64;
+    fstride = (fstride + 31) / 32 * 32;
+    LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(16));
+    LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(stride * (size_t)capacity));
+    LUMOL_CUDA_CHECK(ctx, ctx->ncount.reserve(stride));
+    LUMOL_CUDA_CHECK(ctx, ctx->xref.reserve((size_t)3 * n));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_of.reserve((size_t)2 * n));  // cell_of + slot_of
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_count.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_needed.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sorted_cell.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(stride));
+    LUMOL_CUDA_CHECK(ctx, ctx->ext_start.reserve(2 * ((size_t)next + 2)));  // offsets, then the padded counts
+    LUMOL_CUDA_CHECK(ctx, ctx->fidx.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->kshift.reserve((size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_atom.reserve(fstride));
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(3 * fstride));
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)nunits));
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)nunits * LJ2_MAX_RUNS));
+    LUMOL_CUDA_CHECK(ctx, ctx->cum_levels.reserve(stride * LJ2_LEVELS));
+    if (fstride >= (size_t)RAW_VALUE_MASK) {
+        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many atoms per GPU for the neighbour list (%d)", n);
+    }
+    const int deferred_capacity = n * DEFERRED_PER_ATOM + 1024;
+    ctx->deferred_capacity = deferred_capacity;
+    LUMOL_CUDA_CHECK(ctx, ctx->deferred.reserve((size_t)deferred_capacity));
+    const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const int ext_scan_blocks = (next + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)(scan_blocks > ext_scan_blocks ? scan_blocks : ext_scan_blocks) + 1));
+    int* flags = ctx->nl_flags.ptr;
+    int* cell_of = ctx->cell_of.ptr;
+    int* slot_of = ctx->cell_of.ptr + n;
+    int* order = ctx->order.ptr;
+    int* grouped = ctx->order.ptr + n;
+
+    // ---- is the current list still describing this system? ------------------------------------------
+    uint64_t signature = mix2(0x4c4a32, (uint64_t)n);
+    signature = mix2(signature, ctx->cell_generation);
+    signature = mix2(signature, ctx->structure_generation);
+    uint64_t bits;
+    std::memcpy(&bits, &radius, sizeof(bits));
+    signature = mix2(signature, bits);
+    signature = mix2(signature, (uint64_t)capacity);
+    signature = mix2(signature, (uint64_t)fstride);
+    const bool reuse = ctx->list_valid && signature == ctx->list_signature;
+    ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
+    const int epoch = ctx->list_epoch;
+    const int* state_order = order;  // state arrays in original order: sorted slot -> original index
+    {
+        ScopedClock clock(ctx, &ctx->clk_neighbor);
+        if (!ctx->flags_initialised) {
+            LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(flags, 0, 16 * sizeof(int), ctx->stream));
+            ctx->flags_initialised = true;
+        }
+        if (!reuse) {
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, epoch);
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_DEFERRED, 0);
+        } else {
+            Update2Args u;
+            u.n = n;
+            u.s_lo = 0;
+            u.s_hi = n;
+            u.g = g;
+            u.e = e;
+            u.order = state_order;
+            u.pos = ctx->position.ptr;
+            u.xref = ctx->xref.ptr;
+            u.kshift = ctx->kshift.ptr;
+            u.fidx = ctx->fidx.ptr;
+            u.sorted_cell = ctx->sorted_cell.ptr;
+            u.cell_start = ctx->cell_start.ptr;
+            u.ext_start = ctx->ext_start.ptr;
+            u.frame = ctx->frame_pos.ptr;
+            u.fstride = fstride;
+            u.scale = scale;
+            u.threshold2 = 0.25 * skin * skin;
+            u.epoch = epoch;
+            u.flags = flags;
+            lj2_update_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(u);
+        }
+        ctx->launches++;
+        ctx->clk_neighbor.launches++;
+
+        Rebuild2Args r;
+        r.n = n;
+        r.ncells = ncells;
+        r.scan_blocks = scan_blocks;
+        r.ext_scan_blocks = ext_scan_blocks;
+        r.nunits = nunits;
+        r.epoch = epoch;
+        r.g = g;
+        r.e = e;
+        r.position = ctx->position.ptr;
+        r.cell_of = cell_of;
+        r.slot_of = slot_of;
+        r.cell_count = ctx->cell_count.ptr;
+        r.cell_start = ctx->cell_start.ptr;
+        r.scan_scratch = ctx->scan_scratch.ptr;
+        r.grouped = grouped;
+        r.ext_start = ctx->ext_start.ptr;
+        r.ext_pad = ctx->ext_start.ptr + next + 2;
+        r.scatter.n = n;
+        r.scatter.g = g;
+        r.scatter.pos = ctx->position.ptr;
+        r.scatter.state_of_sorted_old = nullptr;
+        r.scatter.cell_of = cell_of;
+        r.scatter.cell_start = ctx->cell_start.ptr;
+        r.scatter.grouped = grouped;
+        r.scatter.order = order;
+        r.scatter.sorted_f32 = ctx->sorted_f32.ptr;
+        r.scatter.sorted_cell = ctx->sorted_cell.ptr;
+        r.scatter.xref = ctx->xref.ptr;
+        r.scatter.kshift = ctx->kshift.ptr;
+        r.frame.n = n;
+        r.frame.g = g;
+        r.frame.e = e;
+        r.frame.cell_start = ctx->cell_start.ptr;
+        r.frame.sorted_cell = ctx->sorted_cell.ptr;
+        r.frame.ext_start = ctx->ext_start.ptr;
+        r.frame.order = order;
+        r.frame.xref = ctx->xref.ptr;
+        r.frame.kshift = ctx->kshift.ptr;
+        r.frame.fidx = ctx->fidx.ptr;
+        r.frame.frame_atom = ctx->frame_atom.ptr;
+        r.frame.frame = ctx->frame_pos.ptr;
+        r.frame.fstride = fstride;
+        r.frame.scale = scale;
+        r.table.n = n;
+        r.table.nunits = nunits;
+        r.table.e = e;
+        r.table.sorted_cell = ctx->sorted_cell.ptr;
+        r.table.ext_start = ctx->ext_start.ptr;
+        r.table.header = ctx->blk_header.ptr;
+        r.table.runs = ctx->blk_entries.ptr;
+        r.table.flags = flags;
+        Build2Args& b = r.build;
+        b.g = g;
+        b.e = e;
+        b.ncells = ncells;
+        b.cells_per_warp = ncells * BUILD2_CHUNKS / (ctx->sm_count * 8 * REBUILD_WARPS * 16) + 1;
+        b.s_lo = 0;
+        b.s_hi = n;
+        b.capacity = capacity;
+        b.radius2 = (float)(radius * radius * 1.0001);
+        b.cutoff = (float)cutoff;
+        b.inv_delta = skin > 0.0 ? (float)((double)LJ2_LEVELS / skin) : 0.0f;
+        b.cell_start = ctx->cell_start.ptr;
+        b.ext_start = ctx->ext_start.ptr;
+        b.sorted_f32 = ctx->sorted_f32.ptr;
+        b.header = ctx->blk_header.ptr;
+        b.runs = ctx->blk_entries.ptr;
+        b.self_slot = ctx->self_local.ptr;
+        b.nlist = ctx->nlist.ptr;
+        b.ncount = ctx->ncount.ptr;
+        b.cell_needed = ctx->cell_needed.ptr;
+        b.flags = flags;
+        r.flags = flags;
+        if (ctx->rebuild2_grid == 0) {
+            int per_sm = 0;
+            LUMOL_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rebuild2_kernel, REBUILD_THREADS, 0));
+            if (per_sm < 1) return ctx->fail(LUMOL_CUDA_ERROR_CUDA, "the rebuild kernel does not fit on the device");
+            ctx->rebuild2_grid = per_sm * ctx->sm_count;
+        }
+        {
+            void* params[] = {&r};
+            LUMOL_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)rebuild2_kernel, dim3(ctx->rebuild2_grid),
+                                                              dim3(REBUILD_THREADS), params, 0, ctx->stream));
+        }
+        ctx->launches++;
+        ctx->clk_neighbor.launches++;
+        const size_t reorder_smem = (size_t)capacity * REORDER2_THREADS * sizeof(unsigned);
+        if (reorder_smem > 190 * 1024) {
+            return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list columns of %d entries do not fit the reorder kernel", capacity);
+        }
+        if (reorder_smem > 16 * 1024) {
+            LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)reorder_smem));
+        }
+        const int slabs = (n + REORDER2_THREADS - 1) / REORDER2_THREADS;
+        const int reorder_grid = slabs < ctx->sm_count * 8 ? slabs : ctx->sm_count * 8;
+        list_reorder2_kernel<<<reorder_grid, REORDER2_THREADS, reorder_smem, ctx->stream>>>(
+            n, capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, ctx->cum_levels.ptr, epoch, flags);
+        ctx->launches++;
+        ctx->clk_neighbor.launches++;
+        LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    ctx->list_valid = true;
+    ctx->list_signature = signature;
+
+    // ---- forces ------------------------------------------------------------------------------------------
+    const bool full = req.energy || req.virial;
+    Lj2Args a;
+    a.n = n;
+    a.u_lo = 0;
+    a.u_hi = nunits;
+    a.capacity = capacity;
+    a.nlist = ctx->nlist.ptr;
+    a.cum_levels = ctx->cum_levels.ptr;
+    a.self_slot = ctx->self_local.ptr;
+    a.fidx = ctx->fidx.ptr;
+    a.order = state_order;
+    a.header = ctx->blk_header.ptr;
+    a.runs = ctx->blk_entries.ptr;
+    a.frame = ctx->frame_pos.ptr;
+    a.fstride = fstride;
+    a.epsilon24 = 24.0 * epsilon;
+    a.epsilon48 = 48.0 * epsilon;
+    a.epsilon4 = 4.0 * epsilon;
+    a.shift = p.shift;
+    a.inv_sigma = scale;
+    {
+        const double reduced = cutoff * scale;
+        const double reduced2 = reduced * reduced;
+        uint64_t pattern;
+        std::memcpy(&pattern, &reduced2, sizeof(pattern));
+        a.band_lo = (int)(pattern >> 32) - 1;
+    }
+    a.inv_delta = skin > 0.0 ? (float)((double)LJ2_LEVELS / skin) : 0.0f;
+    a.margin = 2.0e-3f;
+    a.epoch = epoch;
+    static const char* all_levels = std::getenv("LUMOL_CUDA_LJ2_ALL_LEVELS");  // experiments: 1 all levels, 2 no pairs at all
+    a.all_levels = all_levels != nullptr ? std::atoi(all_levels) : 0;
+    a.write_forces = req.forces;
+    a.force = ctx->force.ptr;
+    a.deferred = ctx->deferred.ptr;
+    a.deferred_capacity = deferred_capacity;
+    a.flags = flags;
+    int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+    LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)grid * LJ2_NV));
+    a.partials = ctx->partials.ptr;
+    const void* kernel = full ? (const void*)lj2_force_kernel<1> : (const void*)lj2_force_kernel<0>;
+    const size_t smem = (size_t)LJ2_BUFFERS * LJ2_STAGE_BYTES;
+    LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ScopedClock clock(ctx, &ctx->clk_pair);
+        void* params[] = {&a};
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(LJ2_THREADS), params, smem, ctx->stream));
+        ctx->launches++;
+        ctx->clk_pair.launches++;
+    }
+    if (full) {
+        int status = launch_reduce(ctx, grid, LJ2_NV, RES_E_PAIRS);
+        if (status != 0) return status;
+    }
+    {
+        Fix2Args f;
+        f.deferred = ctx->deferred.ptr;
+        f.capacity = deferred_capacity;
+        f.frame_atom = ctx->frame_atom.ptr;
+        f.order = state_order;
+        f.pos = ctx->position.ptr;
+        for (int d = 0; d < 3; d++) f.length[d] = g.length[d];
+        f.sigma = sigma;
+        f.epsilon = epsilon;
+        f.cutoff = cutoff;
+        f.shift = p.shift;
+        f.full = full ? 1 : 0;
+        f.write_forces = req.forces ? 1 : 0;
+        f.force = ctx->force.ptr;
+        f.results = ctx->results.ptr;
+        f.flags = flags;
+        ScopedClock clock(ctx, &ctx->clk_pair);
+        lj2_fixup_kernel<<<ctx->sm_count, 128, 0, ctx->stream>>>(f);
+        ctx->launches++;
+        LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace lumol
