@@ -1181,6 +1181,37 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
     if (c->integrator < 0) return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_setup was not called");
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
     PositionsChange change(c);
+    if (c->nranks > 1) {
+        // a peer-exchange time-out of an earlier run must not be reported again
+        LUMOL_CUDA_CHECK(c, cudaMemsetAsync(c->results.ptr + RES_FLAGS + 1, 0, sizeof(double), c->stream));
+    }
+    // Single-LJ systems on the neighbour-list path, NVE velocity-Verlet: the state lives in cell order for the duration of the
+    // call, units of atoms are owned by ranks and only halo frames cross NVLink (pairs_lj2.cu)
+    if (nsteps > 0 && sorted_md_applicable(c)) {
+        int status = sync_tables(c);
+        if (status) return status;
+        status = sorted_md_run(c, nsteps);
+        if (status) return status;
+        LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        if (c->nranks > 1) {
+            double timed_out = 0.0;
+            LUMOL_CUDA_CHECK(c, cudaMemcpy(&timed_out, c->results.ptr + RES_FLAGS + 1, sizeof(double), cudaMemcpyDeviceToHost));
+            if (timed_out != 0.0) {
+                c->list_valid = false;
+                return c->fail(LUMOL_CUDA_ERROR_COMM, "the positions of another rank did not arrive (peer exchange timed out)");
+            }
+        }
+        int rebuilds = 0, overflow = 0;
+        status = neighbor_list_status(c, &rebuilds, &overflow);
+        if (status) return status;
+        if (overflow == 2) {
+            return c->fail(LUMOL_CUDA_ERROR_NOT_FINITE, "a particle position is not finite: the neighbour list cannot be built");
+        }
+        if (overflow) {
+            return c->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list capacity exceeded (strongly inhomogeneous density)");
+        }
+        return LUMOL_CUDA_SUCCESS;
+    }
     // Small systems (all-pairs path: every system of the reference's tests and benches) are bound by launch latency:
     // one step in the middle of the run is captured into a CUDA graph and replayed.  The first
     // step runs eagerly (it allocates and settles the path), the last one as well (it ends with the half kick).

@@ -92,6 +92,10 @@ struct Comm {
     int* peer_flags[PEER_MAX_RANKS] = {};
     void* opened[2 * PEER_MAX_RANKS] = {};
     int nopened = 0;
+    // buffers of the sorted-resident engine mapped from the other ranks (comm_map_peer_buffers)
+    std::vector<void*> mapped;
+    std::vector<void*> mapped_local;  // the local pointers the current mapping was made for
+    std::vector<void*> mapped_peers;  // [buffer][rank]
 };
 
 #define NCCL_CHECK(ctx, expr)                                                                               \
@@ -141,7 +145,8 @@ static int peer_setup(Context* ctx) {
     // reaches only ~400 GB/s; LUMOL_CUDA_PEER_PUSH=1 / =0 forces the choice.
     const char* forced = std::getenv("LUMOL_CUDA_PEER_PUSH");
     bool ok = nranks <= PEER_MAX_RANKS && (forced != nullptr ? forced[0] == '1' : nranks == 2);
-    const size_t n3 = (size_t)3 * ctx->n;
+    // the second inbox copy starts at an even number of doubles: the drift kernel stores double2 (16 bytes) into it
+    const size_t n3 = ((size_t)3 * ctx->n + 1) & ~(size_t)1;
     cudaIpcMemHandle_t mine[2];
     std::memset(mine, 0, sizeof(mine));
     if (ok) {
@@ -220,7 +225,7 @@ int comm_peer_push_begin(Context* ctx, PeerPush* push) {
     push->rank = ctx->rank;
     push->epoch = comm->push_epoch;
     for (int p = 0; p < ctx->nranks; p++) {
-        push->inbox[p] = comm->peer_inbox[p] + (size_t)parity * 3 * ctx->n;
+        push->inbox[p] = comm->peer_inbox[p] + (size_t)parity * (((size_t)3 * ctx->n + 1) & ~(size_t)1);
         push->flags[p] = comm->peer_flags[p] + parity * PEER_MAX_RANKS;
     }
     push->counter = comm->inbox_flags.ptr + 2 * PEER_MAX_RANKS;
@@ -275,6 +280,107 @@ int comm_peer_gather(Context* ctx, const PeerPush& push) {
     return 0;
 }
 
+// all-gather of equal blocks of `chunk` doubles, in place: rank r owns [r * chunk, (r + 1) * chunk)
+int comm_allgather_chunks(Context* ctx, double* data, size_t chunk) {
+    if (ctx->nranks <= 1 || chunk == 0) return 0;
+    ScopedClock clock(ctx, &ctx->clk_comm);
+    NCCL_CHECK(ctx, g_nccl.all_gather(data + (size_t)ctx->rank * chunk, data, chunk, NCCL_FLOAT64, ctx->comm->comm, ctx->stream));
+    ctx->clk_comm.launches++;
+    return 0;
+}
+
+static void unmap_peer_buffers(Comm* comm) {
+    for (void* pointer : comm->mapped) cudaIpcCloseMemHandle(pointer);
+    comm->mapped.clear();
+    comm->mapped_local.clear();
+    comm->mapped_peers.clear();
+}
+
+// Collective over the ranks: maps `count` device buffers of every rank into this process through CUDA IPC (NVLink peer
+// access).  peers[b * PEER_MAX_RANKS + p] is rank p's buffer b (the local pointer for p == rank).  The mapping is kept
+// until one of the local pointers changes (every rank calls this at the same points, so they re-map together).
+// *ok = false when some rank could not export or open a handle: every rank then takes its fallback.
+int comm_map_peer_buffers(Context* ctx, int count, void* const* local, void** peers, bool* ok) {
+    *ok = false;
+    if (ctx->nranks <= 1 || ctx->comm == nullptr || ctx->nranks > PEER_MAX_RANKS) return 0;
+    Comm* comm = ctx->comm;
+    const int nranks = ctx->nranks;
+    bool same = (int)comm->mapped_local.size() == count;
+    for (int b = 0; same && b < count; b++) same = comm->mapped_local[(size_t)b] == local[b];
+    // every rank must agree on whether to re-map: a rank whose pointers moved forces all of them
+    double moved = same ? 0.0 : 1.0;
+    LUMOL_CUDA_CHECK(ctx, comm->staging.reserve(8));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(comm->staging.ptr, &moved, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.all_reduce(comm->staging.ptr, comm->staging.ptr, 1, NCCL_FLOAT64, NCCL_SUM, comm->comm, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(&moved, comm->staging.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (moved == 0.0) {
+        for (int k = 0; k < count * PEER_MAX_RANKS; k++) peers[k] = comm->mapped_peers[(size_t)k];
+        *ok = true;
+        return 0;
+    }
+    unmap_peer_buffers(comm);
+    bool fine = true;
+    std::vector<cudaIpcMemHandle_t> mine((size_t)count);
+    for (int b = 0; b < count; b++) fine = fine && cudaIpcGetMemHandle(&mine[(size_t)b], local[b]) == cudaSuccess;
+    cudaGetLastError();
+    const size_t record = 16 + (size_t)count * sizeof(cudaIpcMemHandle_t);
+    std::vector<unsigned char> host(record * (size_t)nranks, 0);
+    LUMOL_CUDA_CHECK(ctx, comm->handle_staging.reserve(record * (size_t)nranks));
+    unsigned char* own = host.data() + record * (size_t)ctx->rank;
+    own[0] = fine ? 1 : 0;
+    std::memcpy(own + 16, mine.data(), (size_t)count * sizeof(cudaIpcMemHandle_t));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(comm->handle_staging.ptr + record * (size_t)ctx->rank, own, record, cudaMemcpyHostToDevice,
+                                          ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.all_gather(comm->handle_staging.ptr + record * (size_t)ctx->rank, comm->handle_staging.ptr, record, NCCL_CHAR,
+                                      comm->comm, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(host.data(), comm->handle_staging.ptr, host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < nranks; p++) fine = fine && host[record * (size_t)p] == 1;
+    std::vector<void*> table((size_t)count * PEER_MAX_RANKS, nullptr);
+    for (int p = 0; p < nranks && fine; p++) {
+        for (int b = 0; b < count && fine; b++) {
+            if (p == ctx->rank) {
+                table[(size_t)b * PEER_MAX_RANKS + p] = local[b];
+                continue;
+            }
+            cudaIpcMemHandle_t theirs;
+            std::memcpy(&theirs, host.data() + record * (size_t)p + 16 + (size_t)b * sizeof(cudaIpcMemHandle_t), sizeof(theirs));
+            void* pointer = nullptr;
+            fine = cudaIpcOpenMemHandle(&pointer, theirs, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (fine) {
+                comm->mapped.push_back(pointer);
+                table[(size_t)b * PEER_MAX_RANKS + p] = pointer;
+            }
+        }
+    }
+    cudaGetLastError();
+    double verdict = fine ? 0.0 : 1.0;
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(comm->staging.ptr, &verdict, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.all_reduce(comm->staging.ptr, comm->staging.ptr, 1, NCCL_FLOAT64, NCCL_SUM, comm->comm, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(&verdict, comm->staging.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (verdict != 0.0) {
+        unmap_peer_buffers(comm);
+        return 0;
+    }
+    comm->mapped_local.assign(local, local + count);
+    comm->mapped_peers = table;
+    for (int k = 0; k < count * PEER_MAX_RANKS; k++) peers[k] = table[(size_t)k];
+    *ok = true;
+    return 0;
+}
+
+// barrier over the ranks on the context stream (host returns when every rank has reached it)
+int comm_barrier(Context* ctx) {
+    if (ctx->nranks <= 1 || ctx->comm == nullptr) return 0;
+    LUMOL_CUDA_CHECK(ctx, ctx->comm->staging.reserve(8));
+    LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->comm->staging.ptr, 0, sizeof(double), ctx->stream));
+    NCCL_CHECK(ctx, g_nccl.all_reduce(ctx->comm->staging.ptr, ctx->comm->staging.ptr, 1, NCCL_FLOAT64, NCCL_SUM, ctx->comm->comm, ctx->stream));
+    LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int comm_allreduce(Context* ctx, double* data, int64_t count) {
     if (ctx->nranks <= 1) return 0;
     ScopedClock clock(ctx, &ctx->clk_comm);
@@ -289,6 +395,7 @@ void comm_destroy(Context* ctx) {
             g_nccl.comm_destroy(ctx->comm->comm);
         }
         peer_close(ctx->comm);
+        unmap_peer_buffers(ctx->comm);
         ctx->comm->staging.release();
         ctx->comm->inbox.release();
         ctx->comm->inbox_flags.release();

@@ -213,6 +213,9 @@ struct Context {
     int deferred_capacity = 0;
     int rebuild2_grid = 0;
     bool lj2_active = false;  // the current neighbour list was built by pairs_lj2.cu
+    // sorted-resident molecular dynamics (pairs_lj2.cu): state in cell order, ownership by units, halo frames pushed to peers
+    DeviceBuffer<double> sre_x, sre_v, sre_f, sre_m, sre_tmp;
+    DeviceBuffer<int> sre_origin, sre_need_mask, sre_sync;
 
     // ---- reductions ------------------------------------------------------------------------------
     DeviceBuffer<double> partials, reduce_scratch;
@@ -333,6 +336,11 @@ int comm_peer_gather(Context* ctx, const PeerPush& push);                       
 int comm_allgather_positions(Context* ctx);                                                      // comm.cu
 int comm_allreduce(Context* ctx, double* data, int64_t count);                                   // comm.cu
 int comm_allgather_blocks(Context* ctx, double* data, int64_t total);                            // comm.cu
+int comm_allgather_chunks(Context* ctx, double* data, size_t chunk);                             // comm.cu
+int comm_map_peer_buffers(Context* ctx, int count, void* const* local, void** peers, bool* ok);  // comm.cu
+int comm_barrier(Context* ctx);                                                                  // comm.cu
+bool sorted_md_applicable(Context* ctx);                                                         // pairs_lj2.cu
+int sorted_md_run(Context* ctx, int64_t nsteps);                                                 // pairs_lj2.cu
 void comm_destroy(Context* ctx);                                                                 // comm.cu
 int launch_move_cost(Context* ctx, int ntrials, int max_size);                                   // mc.cu
 int launch_move_accept(Context* ctx, int trial, int first, int size, int64_t row);               // mc.cu

@@ -32,6 +32,8 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -266,6 +268,10 @@ struct Table2Args {
     int4* __restrict__ header;  // c0, K, number of runs (-1: not staged), staged slots
     int4* __restrict__ runs;    // first frame index, slots, first slot
     int* __restrict__ flags;
+    // sharded runs: need_mask[c] collects the ranks whose units stage cell c (or one of its periodic images), so that the
+    // owner of an atom knows into which GPUs' frames it has to store the atom's new position
+    int* __restrict__ need_mask;
+    int units_per_rank;
 };
 
 // one warp per unit
@@ -303,6 +309,15 @@ __device__ __forceinline__ void unit_table_phase(int vb, const Table2Args& a) {
             }
             if (r < nruns) a.runs[(size_t)unit * LJ2_MAX_RUNS + r] = make_int4(f0, slots, total + scan - slots, 0);
             total += __shfl_sync(0xffffffffu, scan, 31);
+            if (a.need_mask != nullptr && r < nruns) {
+                const int g = r / 9, plane = r - 9 * g;
+                int xa, len;
+                rows.segment(g, xa, len);
+                const int row = rows.r0 + g;
+                const int Y = row % a.e.ny + (plane % 3), Z = row / a.e.ny + (plane / 3);
+                const int bit = 1 << (unit / a.units_per_rank);
+                for (int X = xa; X <= xa + len + 1; X++) atomicOr(a.need_mask + a.e.source(X, Y, Z), bit);
+            }
         }
         if (total > LJ2_SLOTS) staged = false;
     }
@@ -468,11 +483,62 @@ struct Rebuild2Args {
     Table2Args table;
     Build2Args build;
     int* flags;
+    // Sorted-resident molecular dynamics (the state arrays are kept in cell order between rebuilds): `position` is then the
+    // state in the OLD cell order; velocities, masses and the map back to the caller's atom order follow the atoms into the
+    // new order.  Sharded: the positions and velocities of the other ranks' atoms arrive by peer stores first.
+    struct Sorted {
+        int active;
+        double *x, *v, *m, *tmp;     // state; tmp holds 4 doubles per atom
+        int *origin, *tmp_origin;    // sorted slot -> index in the caller's arrays
+        int nranks;
+        const int* gathered;         // sharded: gathered[rank] == epoch once that rank's state has arrived here
+    } sorted;
 };
+
+// velocities, masses and origins of the atoms into scratch, in the new order ...
+__device__ __forceinline__ void sorted_collect_phase(int vb, int n, const int* __restrict__ order, const Rebuild2Args::Sorted& a) {
+    const int s = vb * REBUILD_THREADS + threadIdx.x;
+    if (s >= n) return;
+    const int i = order[s];
+    a.tmp[4 * (size_t)s] = a.v[3 * (size_t)i];
+    a.tmp[4 * (size_t)s + 1] = a.v[3 * (size_t)i + 1];
+    a.tmp[4 * (size_t)s + 2] = a.v[3 * (size_t)i + 2];
+    a.tmp[4 * (size_t)s + 3] = a.m[i];
+    a.tmp_origin[s] = a.origin[i];
+}
+
+// ... and back into the state arrays once every block has read the old order
+__device__ __forceinline__ void sorted_commit_phase(int vb, int n, const double* __restrict__ xref, const Rebuild2Args::Sorted& a) {
+    const int s = vb * REBUILD_THREADS + threadIdx.x;
+    if (s >= n) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        a.v[3 * (size_t)s + c] = a.tmp[4 * (size_t)s + c];
+        a.x[3 * (size_t)s + c] = xref[3 * (size_t)s + c];
+    }
+    a.m[s] = a.tmp[4 * (size_t)s + 3];
+    a.origin[s] = a.tmp_origin[s];
+}
 
 __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args r) {
     if (r.flags[FLAG_REBUILD] != r.epoch) return;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    if (r.sorted.active && r.sorted.nranks > 1) {
+        // every rank takes the rebuild decision from the same number, so every rank is here: wait for their atoms
+        if (blockIdx.x == 0 && threadIdx.x < r.sorted.nranks) {
+            const volatile int* flag = r.sorted.gathered + threadIdx.x;
+            const long long start = clock64();
+            while (*flag != r.epoch) {
+                if (clock64() - start > 40000000000ll) {
+                    r.flags[FLAG_NONFINITE] = 2;  // reported as a communication error by the host
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        grid.sync();
+        if (r.flags[FLAG_NONFINITE] != 0) return;
+    }
     __shared__ int scan_shared[33];
     __shared__ float offset32[27][3];
     __shared__ unsigned pending[REBUILD_THREADS][4];
@@ -486,6 +552,9 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
 
     cell_zero_phase(r.ncells + 1, r.cell_count, r.build.cell_needed, r.flags);
     if (blockIdx.x == 0 && threadIdx.x == 0) r.flags[FLAG_FRAME_OVERFLOW] = 0;
+    if (r.table.need_mask != nullptr) {
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < r.ncells; k += gridDim.x * blockDim.x) r.table.need_mask[k] = 0;
+    }
     grid.sync();
     for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) {
         cell_assign_phase(vb, r.n, r.g, r.position, r.cell_of, r.slot_of, r.cell_count, r.flags);
@@ -524,7 +593,13 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
     grid.sync();
     for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) frame2_phase(vb, r.frame, r.flags);
     for (int vb = blockIdx.x; vb * REBUILD_WARPS < r.nunits; vb += gridDim.x) unit_table_phase(vb, r.table);
+    if (r.sorted.active) {
+        for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) sorted_collect_phase(vb, r.n, r.scatter.order, r.sorted);
+    }
     grid.sync();
+    if (r.sorted.active) {
+        for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) sorted_commit_phase(vb, r.n, r.scatter.xref, r.sorted);
+    }
     for (int vb = blockIdx.x; vb * REBUILD_WARPS * r.build.cells_per_warp < r.ncells * BUILD2_CHUNKS; vb += gridDim.x) {
         list_build2_phase(vb, r.build, offset32, pending);
     }
@@ -550,7 +625,7 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
 constexpr int REORDER2_THREADS = 32;
 
 __global__ void __launch_bounds__(REORDER2_THREADS)
-    list_reorder2_kernel(int n, int capacity, const int4* __restrict__ header, const int* __restrict__ ncount,
+    list_reorder2_kernel(int s_lo, int n, int capacity, const int4* __restrict__ header, const int* __restrict__ ncount,
                          unsigned* __restrict__ nlist, unsigned short* __restrict__ cum_levels, int epoch,
                          const int* __restrict__ flags) {
     if (flags[FLAG_REBUILD] != epoch || flags[FLAG_NONFINITE] != 0) return;
@@ -558,7 +633,8 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
     unsigned* sorted = reorder2_smem;  // entry p of thread t at [p * 32 + t], grouped by (level, residue)
     __shared__ unsigned short cursor[LJ2_LEVELS * 16][REORDER2_THREADS], last[LJ2_LEVELS * 16][REORDER2_THREADS];
     const int t = threadIdx.x;
-    for (int slab = blockIdx.x; slab * REORDER2_THREADS < n; slab += gridDim.x) {
+    // columns [s_lo, n): the atoms of this rank (s_lo is a multiple of the unit size)
+    for (int slab = s_lo / REORDER2_THREADS + blockIdx.x; slab * REORDER2_THREADS < n; slab += gridDim.x) {
         const int s_i = slab * REORDER2_THREADS + t;
         if (s_i >= n) continue;
         const bool staged = header[s_i / U_ATOMS].z >= 0;
@@ -1131,6 +1207,11 @@ struct Fix2Args {
     const int* __restrict__ frame_atom;
     const int* __restrict__ order;  // nullptr: state arrays in sorted order
     const double* __restrict__ pos;
+    // sharded sorted-resident runs: the state arrays hold current positions of the rank's own atoms only; the separation is
+    // then taken from the frames (positions of both atoms times 1 / sigma, same periodic image up to whole boxes)
+    const double* __restrict__ frame;
+    const int* __restrict__ fidx;
+    double sigma_for_frames;
     double length[3];
     double sigma, epsilon, cutoff, shift;
     int full;
@@ -1152,7 +1233,12 @@ __global__ void __launch_bounds__(128) lj2_fixup_kernel(Fix2Args a) {
         double d[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double raw = __dadd_rn(a.pos[3 * i + c], -a.pos[3 * j + c]);
+            double raw;
+            if (a.frame != nullptr) {
+                raw = (a.frame[3 * (size_t)a.fidx[i] + c] - a.frame[3 * (size_t)entry.y + c]) * a.sigma_for_frames;
+            } else {
+                raw = __dadd_rn(a.pos[3 * i + c], -a.pos[3 * j + c]);
+            }
             d[c] = __dadd_rn(raw, -__dmul_rn(round(__ddiv_rn(raw, a.length[c])), a.length[c]));
         }
         const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
@@ -1198,274 +1284,306 @@ static uint64_t mix2(uint64_t h, uint64_t v) {
 bool lj2_enabled(const Context* ctx) {
     static const char* knob = std::getenv("LUMOL_CUDA_LJ2");
     if (knob != nullptr && knob[0] == '0') return false;
+    // evaluations in the caller's atom order are not sharded on this path (the sorted-resident engine below is): with
+    // several ranks they keep the first-generation kernels, whose atom-block ownership the reductions in api.cu expect
     return ctx->nranks == 1;
 }
 
-int launch_pairs_lj2(Context* ctx, const ComputeRequest& req) {
-    const int n = (int)ctx->n;
+// Sizes, ownership and buffers of one evaluation.
+struct Lj2Plan {
+    int n, ncells, next, nunits, capacity, deferred_capacity, scan_blocks, ext_scan_blocks;
+    size_t stride, fstride;
     GridView g;
-    for (int d = 0; d < 3; d++) {
-        g.nc[d] = ctx->ncell[d];
-        g.length[d] = ctx->cell.h[4 * d];
-        g.edge[d] = g.length[d] / (double)g.nc[d];
-    }
     ExtGrid e;
-    e.nx = g.nc[0];
-    e.ny = g.nc[1];
-    e.nz = g.nc[2];
-    e.ex = e.nx + 2;
-    e.ey = e.ny + 2;
-    e.ez = e.nz + 2;
-    const int ncells = g.nc[0] * g.nc[1] * g.nc[2];
-    const int next = e.count();
-    const lumol_cuda_pair& p = ctx->host_pairs[0];
-    const double cutoff = p.cutoff;
-    const double skin = ctx->skin_effective;
-    const double radius = cutoff + skin;
-    const double sigma = p.p[0], epsilon = p.p[1];
-    const double scale = 1.0 / sigma;
+    double cutoff, skin, radius, sigma, epsilon, scale, shift;
+    int units_per_rank, u_lo, u_hi, s_lo, s_hi;  // units / sorted atoms of this rank
+    uint64_t signature;
+};
 
-    // ---- buffers ---------------------------------------------------------------------------------
-    const double volume = g.length[0] * g.length[1] * g.length[2];
-    const double mean_neighbors = 4.0 / 3.0 * PI * radius * radius * radius * (double)n / volume;
+// `sharded`: the sorted-resident engine on several ranks (units split between the ranks); otherwise one rank does all.
+static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
+    const int n = (int)ctx->n;
+    P.n = n;
+    for (int d = 0; d < 3; d++) {
+        P.g.nc[d] = ctx->ncell[d];
+        P.g.length[d] = ctx->cell.h[4 * d];
+        P.g.edge[d] = P.g.length[d] / (double)P.g.nc[d];
+    }
+    P.e.nx = P.g.nc[0];
+    P.e.ny = P.g.nc[1];
+    P.e.nz = P.g.nc[2];
+    P.e.ex = P.e.nx + 2;
+    P.e.ey = P.e.ny + 2;
+    P.e.ez = P.e.nz + 2;
+    P.ncells = P.g.nc[0] * P.g.nc[1] * P.g.nc[2];
+    P.next = P.e.count();
+    const lumol_cuda_pair& p = ctx->host_pairs[0];
+    P.cutoff = p.cutoff;
+    P.skin = ctx->skin_effective;
+    P.radius = P.cutoff + P.skin;
+    P.sigma = p.p[0];
+    P.epsilon = p.p[1];
+    P.scale = 1.0 / P.sigma;
+    P.shift = p.shift;
+
+    const double volume = P.g.length[0] * P.g.length[1] * P.g.length[2];
+    const double mean_neighbors = 4.0 / 3.0 * PI * P.radius * P.radius * P.radius * (double)n / volume;
     int capacity = (int)(2.0 * mean_neighbors) + 64;
     if (capacity > n) capacity = n;
-    capacity = (capacity + 7) / 8 * 8;
-    const size_t stride = ((size_t)n + 31) / 32 * 32;
-    const int nunits = (n + U_ATOMS - 1) / U_ATOMS;
+    P.capacity = (capacity + 7) / 8 * 8;
+    P.stride = ((size_t)n + 31) / 32 * 32;
+    P.nunits = (n + U_ATOMS - 1) / U_ATOMS;
+    const int nranks = sharded ? ctx->nranks : 1;
+    P.units_per_rank = (P.nunits + nranks - 1) / nranks;
+    P.u_lo = sharded ? std::min(P.nunits, P.units_per_rank * ctx->rank) : 0;
+    P.u_hi = sharded ? std::min(P.nunits, P.u_lo + P.units_per_rank) : P.nunits;
+    P.s_lo = std::min(n, P.u_lo * U_ATOMS);
+    P.s_hi = std::min(n, P.u_hi * U_ATOMS);
     // frame slots: the atoms, their ghost images (a boundary atom has up to seven), one slot of padding per extended cell
-    const double ghost_ratio = (double)next / (double)ncells;
-    size_t fstride = (size_t)((double)n * (ghost_ratio * 1.5 + 0.25)) + 2 * (size_t)next + 64;
-    if (fstride > (size_t)8 * n + 2 * (size_t)next + 64) fstride = (size_t)8 * n + 2 * (size_t)next + 64;
-    fstride = (fstride + 31) / 32 * 32;
+    const double ghost_ratio = (double)P.next / (double)P.ncells;
+    size_t fstride = (size_t)((double)n * (ghost_ratio * 1.5 + 0.25)) + 2 * (size_t)P.next + 64;
+    if (fstride > (size_t)8 * n + 2 * (size_t)P.next + 64) fstride = (size_t)8 * n + 2 * (size_t)P.next + 64;
+    P.fstride = (fstride + 31) / 32 * 32;
+    if (P.fstride >= (size_t)RAW_VALUE_MASK) {
+        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many atoms per GPU for the neighbour list (%d)", n);
+    }
     LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(16));
-    LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(stride * (size_t)capacity));
-    LUMOL_CUDA_CHECK(ctx, ctx->ncount.reserve(stride));
+    LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(P.stride * (size_t)P.capacity));
+    LUMOL_CUDA_CHECK(ctx, ctx->ncount.reserve(P.stride));
     LUMOL_CUDA_CHECK(ctx, ctx->xref.reserve((size_t)3 * n));
     LUMOL_CUDA_CHECK(ctx, ctx->cell_of.reserve((size_t)2 * n));  // cell_of + slot_of
-    LUMOL_CUDA_CHECK(ctx, ctx->cell_count.reserve((size_t)ncells + 1));
-    LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)ncells + 1));
-    LUMOL_CUDA_CHECK(ctx, ctx->cell_needed.reserve((size_t)ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_count.reserve((size_t)P.ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_start.reserve((size_t)P.ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->cell_needed.reserve((size_t)P.ncells + 1));
     LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_cell.reserve((size_t)n));
-    LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(stride));
-    LUMOL_CUDA_CHECK(ctx, ctx->ext_start.reserve(2 * ((size_t)next + 2)));  // offsets, then the padded counts
+    LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(P.stride));
+    LUMOL_CUDA_CHECK(ctx, ctx->ext_start.reserve(2 * ((size_t)P.next + 2)));  // offsets, then the padded counts
     LUMOL_CUDA_CHECK(ctx, ctx->fidx.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->kshift.reserve((size_t)n));
-    LUMOL_CUDA_CHECK(ctx, ctx->frame_atom.reserve(fstride));
-    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(3 * fstride));
-    LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)nunits));
-    LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)nunits * LJ2_MAX_RUNS));
-    LUMOL_CUDA_CHECK(ctx, ctx->cum_levels.reserve(stride * LJ2_LEVELS));
-    if (fstride >= (size_t)RAW_VALUE_MASK) {
-        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many atoms per GPU for the neighbour list (%d)", n);
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_atom.reserve(P.fstride));
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(2 * 3 * P.fstride));  // two copies: a sharded run alternates with the step parity
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)P.nunits));
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)P.nunits * LJ2_MAX_RUNS));
+    LUMOL_CUDA_CHECK(ctx, ctx->cum_levels.reserve(P.stride * LJ2_LEVELS));
+    P.deferred_capacity = n * DEFERRED_PER_ATOM + 1024;
+    ctx->deferred_capacity = P.deferred_capacity;
+    LUMOL_CUDA_CHECK(ctx, ctx->deferred.reserve((size_t)P.deferred_capacity));
+    P.scan_blocks = (P.ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    P.ext_scan_blocks = (P.next + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)(P.scan_blocks > P.ext_scan_blocks ? P.scan_blocks : P.ext_scan_blocks) + 1));
+
+    uint64_t signature = mix2(0x4c4a32, (uint64_t)n);
+    signature = mix2(signature, ctx->cell_generation);
+    signature = mix2(signature, ctx->structure_generation);
+    uint64_t bits;
+    std::memcpy(&bits, &P.radius, sizeof(bits));
+    signature = mix2(signature, bits);
+    signature = mix2(signature, (uint64_t)P.capacity);
+    signature = mix2(signature, (uint64_t)P.fstride);
+    signature = mix2(signature, (uint64_t)P.u_lo * 1315423911ull + (uint64_t)P.u_hi);
+    P.signature = signature;
+    if (!ctx->flags_initialised) {
+        LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->nl_flags.ptr, 0, 16 * sizeof(int), ctx->stream));
+        ctx->flags_initialised = true;
     }
-    const int deferred_capacity = n * DEFERRED_PER_ATOM + 1024;
-    ctx->deferred_capacity = deferred_capacity;
-    LUMOL_CUDA_CHECK(ctx, ctx->deferred.reserve((size_t)deferred_capacity));
-    const int scan_blocks = (ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    const int ext_scan_blocks = (next + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)(scan_blocks > ext_scan_blocks ? scan_blocks : ext_scan_blocks) + 1));
+    return 0;
+}
+
+static double* lj2_frame(Context* ctx, const Lj2Plan& P, int parity) { return ctx->frame_pos.ptr + (size_t)parity * 3 * P.fstride; }
+
+// Refresh of the frames from positions in the caller's order (state arrays not in cell order).
+static int lj2_launch_update(Context* ctx, const Lj2Plan& P, int epoch) {
+    Update2Args u;
+    u.n = P.n;
+    u.s_lo = 0;
+    u.s_hi = P.n;
+    u.g = P.g;
+    u.e = P.e;
+    u.order = ctx->order.ptr;
+    u.pos = ctx->position.ptr;
+    u.xref = ctx->xref.ptr;
+    u.kshift = ctx->kshift.ptr;
+    u.fidx = ctx->fidx.ptr;
+    u.sorted_cell = ctx->sorted_cell.ptr;
+    u.cell_start = ctx->cell_start.ptr;
+    u.ext_start = ctx->ext_start.ptr;
+    u.frame = lj2_frame(ctx, P, 0);
+    u.fstride = P.fstride;
+    u.scale = P.scale;
+    u.threshold2 = 0.25 * P.skin * P.skin;
+    u.epoch = epoch;
+    u.flags = ctx->nl_flags.ptr;
+    lj2_update_kernel<<<(P.n + 255) / 256, 256, 0, ctx->stream>>>(u);
+    ctx->launches++;
+    ctx->clk_neighbor.launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// The guarded rebuild (cooperative kernel + final order of the columns): does nothing unless flags[FLAG_REBUILD] holds
+// this epoch.  `state`: positions the atoms are binned from (caller's order, or the old cell order of a sorted-resident run).
+static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const double* state, int parity,
+                              const Rebuild2Args::Sorted& sorted, int* need_mask) {
+    const int n = P.n;
     int* flags = ctx->nl_flags.ptr;
     int* cell_of = ctx->cell_of.ptr;
     int* slot_of = ctx->cell_of.ptr + n;
     int* order = ctx->order.ptr;
     int* grouped = ctx->order.ptr + n;
-
-    // ---- is the current list still describing this system? ------------------------------------------
-    uint64_t signature = mix2(0x4c4a32, (uint64_t)n);
-    signature = mix2(signature, ctx->cell_generation);
-    signature = mix2(signature, ctx->structure_generation);
-    uint64_t bits;
-    std::memcpy(&bits, &radius, sizeof(bits));
-    signature = mix2(signature, bits);
-    signature = mix2(signature, (uint64_t)capacity);
-    signature = mix2(signature, (uint64_t)fstride);
-    const bool reuse = ctx->list_valid && signature == ctx->list_signature;
-    ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
-    const int epoch = ctx->list_epoch;
-    const int* state_order = order;  // state arrays in original order: sorted slot -> original index
-    {
-        ScopedClock clock(ctx, &ctx->clk_neighbor);
-        if (!ctx->flags_initialised) {
-            LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(flags, 0, 16 * sizeof(int), ctx->stream));
-            ctx->flags_initialised = true;
-        }
-        if (!reuse) {
-            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, epoch);
-            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_DEFERRED, 0);
-        } else {
-            Update2Args u;
-            u.n = n;
-            u.s_lo = 0;
-            u.s_hi = n;
-            u.g = g;
-            u.e = e;
-            u.order = state_order;
-            u.pos = ctx->position.ptr;
-            u.xref = ctx->xref.ptr;
-            u.kshift = ctx->kshift.ptr;
-            u.fidx = ctx->fidx.ptr;
-            u.sorted_cell = ctx->sorted_cell.ptr;
-            u.cell_start = ctx->cell_start.ptr;
-            u.ext_start = ctx->ext_start.ptr;
-            u.frame = ctx->frame_pos.ptr;
-            u.fstride = fstride;
-            u.scale = scale;
-            u.threshold2 = 0.25 * skin * skin;
-            u.epoch = epoch;
-            u.flags = flags;
-            lj2_update_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(u);
-        }
-        ctx->launches++;
-        ctx->clk_neighbor.launches++;
-
-        Rebuild2Args r;
-        r.n = n;
-        r.ncells = ncells;
-        r.scan_blocks = scan_blocks;
-        r.ext_scan_blocks = ext_scan_blocks;
-        r.nunits = nunits;
-        r.epoch = epoch;
-        r.g = g;
-        r.e = e;
-        r.position = ctx->position.ptr;
-        r.cell_of = cell_of;
-        r.slot_of = slot_of;
-        r.cell_count = ctx->cell_count.ptr;
-        r.cell_start = ctx->cell_start.ptr;
-        r.scan_scratch = ctx->scan_scratch.ptr;
-        r.grouped = grouped;
-        r.ext_start = ctx->ext_start.ptr;
-        r.ext_pad = ctx->ext_start.ptr + next + 2;
-        r.scatter.n = n;
-        r.scatter.g = g;
-        r.scatter.pos = ctx->position.ptr;
-        r.scatter.state_of_sorted_old = nullptr;
-        r.scatter.cell_of = cell_of;
-        r.scatter.cell_start = ctx->cell_start.ptr;
-        r.scatter.grouped = grouped;
-        r.scatter.order = order;
-        r.scatter.sorted_f32 = ctx->sorted_f32.ptr;
-        r.scatter.sorted_cell = ctx->sorted_cell.ptr;
-        r.scatter.xref = ctx->xref.ptr;
-        r.scatter.kshift = ctx->kshift.ptr;
-        r.frame.n = n;
-        r.frame.g = g;
-        r.frame.e = e;
-        r.frame.cell_start = ctx->cell_start.ptr;
-        r.frame.sorted_cell = ctx->sorted_cell.ptr;
-        r.frame.ext_start = ctx->ext_start.ptr;
-        r.frame.order = order;
-        r.frame.xref = ctx->xref.ptr;
-        r.frame.kshift = ctx->kshift.ptr;
-        r.frame.fidx = ctx->fidx.ptr;
-        r.frame.frame_atom = ctx->frame_atom.ptr;
-        r.frame.frame = ctx->frame_pos.ptr;
-        r.frame.fstride = fstride;
-        r.frame.scale = scale;
-        r.table.n = n;
-        r.table.nunits = nunits;
-        r.table.e = e;
-        r.table.sorted_cell = ctx->sorted_cell.ptr;
-        r.table.ext_start = ctx->ext_start.ptr;
-        r.table.header = ctx->blk_header.ptr;
-        r.table.runs = ctx->blk_entries.ptr;
-        r.table.flags = flags;
-        Build2Args& b = r.build;
-        b.g = g;
-        b.e = e;
-        b.ncells = ncells;
-        b.cells_per_warp = ncells * BUILD2_CHUNKS / (ctx->sm_count * 8 * REBUILD_WARPS * 16) + 1;
-        b.s_lo = 0;
-        b.s_hi = n;
-        b.capacity = capacity;
-        b.radius2 = (float)(radius * radius * 1.0001);
-        b.cutoff = (float)cutoff;
-        b.inv_delta = skin > 0.0 ? (float)((double)LJ2_LEVELS / skin) : 0.0f;
-        b.cell_start = ctx->cell_start.ptr;
-        b.ext_start = ctx->ext_start.ptr;
-        b.sorted_f32 = ctx->sorted_f32.ptr;
-        b.header = ctx->blk_header.ptr;
-        b.runs = ctx->blk_entries.ptr;
-        b.self_slot = ctx->self_local.ptr;
-        b.nlist = ctx->nlist.ptr;
-        b.ncount = ctx->ncount.ptr;
-        b.cell_needed = ctx->cell_needed.ptr;
-        b.flags = flags;
-        r.flags = flags;
-        if (ctx->rebuild2_grid == 0) {
-            int per_sm = 0;
-            LUMOL_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rebuild2_kernel, REBUILD_THREADS, 0));
-            if (per_sm < 1) return ctx->fail(LUMOL_CUDA_ERROR_CUDA, "the rebuild kernel does not fit on the device");
-            ctx->rebuild2_grid = per_sm * ctx->sm_count;
-        }
-        {
-            void* params[] = {&r};
-            LUMOL_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)rebuild2_kernel, dim3(ctx->rebuild2_grid),
-                                                              dim3(REBUILD_THREADS), params, 0, ctx->stream));
-        }
-        ctx->launches++;
-        ctx->clk_neighbor.launches++;
-        const size_t reorder_smem = (size_t)capacity * REORDER2_THREADS * sizeof(unsigned);
-        if (reorder_smem > 190 * 1024) {
-            return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list columns of %d entries do not fit the reorder kernel", capacity);
-        }
-        if (reorder_smem > 16 * 1024) {
-            LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       (int)reorder_smem));
-        }
-        const int slabs = (n + REORDER2_THREADS - 1) / REORDER2_THREADS;
-        const int reorder_grid = slabs < ctx->sm_count * 8 ? slabs : ctx->sm_count * 8;
-        list_reorder2_kernel<<<reorder_grid, REORDER2_THREADS, reorder_smem, ctx->stream>>>(
-            n, capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, ctx->cum_levels.ptr, epoch, flags);
-        ctx->launches++;
-        ctx->clk_neighbor.launches++;
-        LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    Rebuild2Args r;
+    r.n = n;
+    r.ncells = P.ncells;
+    r.scan_blocks = P.scan_blocks;
+    r.ext_scan_blocks = P.ext_scan_blocks;
+    r.nunits = P.nunits;
+    r.epoch = epoch;
+    r.g = P.g;
+    r.e = P.e;
+    r.position = state;
+    r.cell_of = cell_of;
+    r.slot_of = slot_of;
+    r.cell_count = ctx->cell_count.ptr;
+    r.cell_start = ctx->cell_start.ptr;
+    r.scan_scratch = ctx->scan_scratch.ptr;
+    r.grouped = grouped;
+    r.ext_start = ctx->ext_start.ptr;
+    r.ext_pad = ctx->ext_start.ptr + P.next + 2;
+    r.scatter.n = n;
+    r.scatter.g = P.g;
+    r.scatter.pos = state;
+    r.scatter.state_of_sorted_old = nullptr;
+    r.scatter.cell_of = cell_of;
+    r.scatter.cell_start = ctx->cell_start.ptr;
+    r.scatter.grouped = grouped;
+    r.scatter.order = order;
+    r.scatter.sorted_f32 = ctx->sorted_f32.ptr;
+    r.scatter.sorted_cell = ctx->sorted_cell.ptr;
+    r.scatter.xref = ctx->xref.ptr;
+    r.scatter.kshift = ctx->kshift.ptr;
+    r.frame.n = n;
+    r.frame.g = P.g;
+    r.frame.e = P.e;
+    r.frame.cell_start = ctx->cell_start.ptr;
+    r.frame.sorted_cell = ctx->sorted_cell.ptr;
+    r.frame.ext_start = ctx->ext_start.ptr;
+    r.frame.order = order;
+    r.frame.xref = ctx->xref.ptr;
+    r.frame.kshift = ctx->kshift.ptr;
+    r.frame.fidx = ctx->fidx.ptr;
+    r.frame.frame_atom = ctx->frame_atom.ptr;
+    r.frame.frame = lj2_frame(ctx, P, parity);
+    r.frame.fstride = P.fstride;
+    r.frame.scale = P.scale;
+    r.table.n = n;
+    r.table.nunits = P.nunits;
+    r.table.e = P.e;
+    r.table.sorted_cell = ctx->sorted_cell.ptr;
+    r.table.ext_start = ctx->ext_start.ptr;
+    r.table.header = ctx->blk_header.ptr;
+    r.table.runs = ctx->blk_entries.ptr;
+    r.table.flags = flags;
+    r.table.need_mask = need_mask;
+    r.table.units_per_rank = P.units_per_rank;
+    Build2Args& b = r.build;
+    b.g = P.g;
+    b.e = P.e;
+    b.ncells = P.ncells;
+    b.cells_per_warp = P.ncells * BUILD2_CHUNKS / (ctx->sm_count * 8 * REBUILD_WARPS * 16) + 1;
+    b.s_lo = P.s_lo;
+    b.s_hi = P.s_hi;
+    b.capacity = P.capacity;
+    b.radius2 = (float)(P.radius * P.radius * 1.0001);
+    b.cutoff = (float)P.cutoff;
+    b.inv_delta = P.skin > 0.0 ? (float)((double)LJ2_LEVELS / P.skin) : 0.0f;
+    b.cell_start = ctx->cell_start.ptr;
+    b.ext_start = ctx->ext_start.ptr;
+    b.sorted_f32 = ctx->sorted_f32.ptr;
+    b.header = ctx->blk_header.ptr;
+    b.runs = ctx->blk_entries.ptr;
+    b.self_slot = ctx->self_local.ptr;
+    b.nlist = ctx->nlist.ptr;
+    b.ncount = ctx->ncount.ptr;
+    b.cell_needed = ctx->cell_needed.ptr;
+    b.flags = flags;
+    r.flags = flags;
+    r.sorted = sorted;
+    if (ctx->rebuild2_grid == 0) {
+        int per_sm = 0;
+        LUMOL_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rebuild2_kernel, REBUILD_THREADS, 0));
+        if (per_sm < 1) return ctx->fail(LUMOL_CUDA_ERROR_CUDA, "the rebuild kernel does not fit on the device");
+        ctx->rebuild2_grid = per_sm * ctx->sm_count;
     }
-    ctx->list_valid = true;
-    ctx->list_signature = signature;
+    {
+        void* params[] = {&r};
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)rebuild2_kernel, dim3(ctx->rebuild2_grid),
+                                                          dim3(REBUILD_THREADS), params, 0, ctx->stream));
+    }
+    ctx->launches++;
+    ctx->clk_neighbor.launches++;
+    const size_t reorder_smem = (size_t)P.capacity * REORDER2_THREADS * sizeof(unsigned);
+    if (reorder_smem > 190 * 1024) {
+        return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list columns of %d entries do not fit the reorder kernel", P.capacity);
+    }
+    if (reorder_smem > 16 * 1024) {
+        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)reorder_smem));
+    }
+    const int slabs = (P.s_hi - P.s_lo + REORDER2_THREADS - 1) / REORDER2_THREADS;
+    const int reorder_grid = std::max(1, slabs < ctx->sm_count * 8 ? slabs : ctx->sm_count * 8);
+    list_reorder2_kernel<<<reorder_grid, REORDER2_THREADS, reorder_smem, ctx->stream>>>(
+        P.s_lo, P.s_hi, P.capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, ctx->cum_levels.ptr, epoch, flags);
+    ctx->launches++;
+    ctx->clk_neighbor.launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
 
-    // ---- forces ------------------------------------------------------------------------------------------
+// Force kernel, reduction of the scalar sums, fix-up of the pairs on the cut-off.  `order`: sorted slot -> index in the
+// state arrays (nullptr: the state arrays are in cell order).
+static int lj2_launch_force(Context* ctx, const Lj2Plan& P, const ComputeRequest& req, int epoch, int parity, const int* order,
+                            const double* state_position, double* state_force, bool fix_from_frames = false) {
     const bool full = req.energy || req.virial;
+    int* flags = ctx->nl_flags.ptr;
     Lj2Args a;
-    a.n = n;
-    a.u_lo = 0;
-    a.u_hi = nunits;
-    a.capacity = capacity;
+    a.n = P.n;
+    a.u_lo = P.u_lo;
+    a.u_hi = P.u_hi;
+    a.capacity = P.capacity;
     a.nlist = ctx->nlist.ptr;
     a.cum_levels = ctx->cum_levels.ptr;
     a.self_slot = ctx->self_local.ptr;
     a.fidx = ctx->fidx.ptr;
-    a.order = state_order;
+    a.order = order;
     a.header = ctx->blk_header.ptr;
     a.runs = ctx->blk_entries.ptr;
-    a.frame = ctx->frame_pos.ptr;
-    a.fstride = fstride;
-    a.epsilon24 = 24.0 * epsilon;
-    a.epsilon48 = 48.0 * epsilon;
-    a.epsilon4 = 4.0 * epsilon;
-    a.shift = p.shift;
-    a.inv_sigma = scale;
+    a.frame = lj2_frame(ctx, P, parity);
+    a.fstride = P.fstride;
+    a.epsilon24 = 24.0 * P.epsilon;
+    a.epsilon48 = 48.0 * P.epsilon;
+    a.epsilon4 = 4.0 * P.epsilon;
+    a.shift = P.shift;
+    a.inv_sigma = P.scale;
     {
-        const double reduced = cutoff * scale;
+        const double reduced = P.cutoff * P.scale;
         const double reduced2 = reduced * reduced;
         uint64_t pattern;
         std::memcpy(&pattern, &reduced2, sizeof(pattern));
         a.band_lo = (int)(pattern >> 32) - 1;
     }
-    a.inv_delta = skin > 0.0 ? (float)((double)LJ2_LEVELS / skin) : 0.0f;
+    a.inv_delta = P.skin > 0.0 ? (float)((double)LJ2_LEVELS / P.skin) : 0.0f;
     a.margin = 2.0e-3f;
     a.epoch = epoch;
     static const char* all_levels = std::getenv("LUMOL_CUDA_LJ2_ALL_LEVELS");  // experiments: 1 all levels, 2 no pairs at all
     a.all_levels = all_levels != nullptr ? std::atoi(all_levels) : 0;
     a.write_forces = req.forces;
-    a.force = ctx->force.ptr;
+    a.force = state_force;
     a.deferred = ctx->deferred.ptr;
-    a.deferred_capacity = deferred_capacity;
+    a.deferred_capacity = P.deferred_capacity;
     a.flags = flags;
-    int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+    const int units = P.u_hi - P.u_lo;
+    const int grid = std::max(1, units < ctx->sm_count ? units : ctx->sm_count);
     LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)grid * LJ2_NV));
     a.partials = ctx->partials.ptr;
     const void* kernel = full ? (const void*)lj2_force_kernel<1> : (const void*)lj2_force_kernel<0>;
@@ -1482,28 +1600,515 @@ int launch_pairs_lj2(Context* ctx, const ComputeRequest& req) {
         int status = launch_reduce(ctx, grid, LJ2_NV, RES_E_PAIRS);
         if (status != 0) return status;
     }
+    Fix2Args f;
+    f.deferred = ctx->deferred.ptr;
+    f.capacity = P.deferred_capacity;
+    f.frame_atom = ctx->frame_atom.ptr;
+    f.order = order;
+    f.pos = state_position;
+    f.frame = fix_from_frames ? lj2_frame(ctx, P, parity) : nullptr;
+    f.fidx = ctx->fidx.ptr;
+    f.sigma_for_frames = P.sigma;
+    for (int d = 0; d < 3; d++) f.length[d] = P.g.length[d];
+    f.sigma = P.sigma;
+    f.epsilon = P.epsilon;
+    f.cutoff = P.cutoff;
+    f.shift = P.shift;
+    f.full = full ? 1 : 0;
+    f.write_forces = req.forces ? 1 : 0;
+    f.force = state_force;
+    f.results = ctx->results.ptr;
+    f.flags = flags;
+    lj2_fixup_kernel<<<8, 128, 0, ctx->stream>>>(f);
+    ctx->launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// One evaluation with the state arrays in the caller's order (lumol_cuda_compute, and MD outside the sorted-resident engine).
+int launch_pairs_lj2(Context* ctx, const ComputeRequest& req) {
+    Lj2Plan P;
+    int status = lj2_plan(ctx, false, P);
+    if (status != 0) return status;
+    int* flags = ctx->nl_flags.ptr;
+    const bool reuse = ctx->list_valid && P.signature == ctx->list_signature;
+    ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
+    const int epoch = ctx->list_epoch;
     {
-        Fix2Args f;
-        f.deferred = ctx->deferred.ptr;
-        f.capacity = deferred_capacity;
-        f.frame_atom = ctx->frame_atom.ptr;
-        f.order = state_order;
-        f.pos = ctx->position.ptr;
-        for (int d = 0; d < 3; d++) f.length[d] = g.length[d];
-        f.sigma = sigma;
-        f.epsilon = epsilon;
-        f.cutoff = cutoff;
-        f.shift = p.shift;
-        f.full = full ? 1 : 0;
-        f.write_forces = req.forces ? 1 : 0;
-        f.force = ctx->force.ptr;
-        f.results = ctx->results.ptr;
-        f.flags = flags;
-        ScopedClock clock(ctx, &ctx->clk_pair);
-        lj2_fixup_kernel<<<ctx->sm_count, 128, 0, ctx->stream>>>(f);
+        ScopedClock clock(ctx, &ctx->clk_neighbor);
+        if (!reuse) {
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, epoch);
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_DEFERRED, 0);
+            ctx->launches += 2;
+        } else if ((status = lj2_launch_update(ctx, P, epoch)) != 0) {
+            return status;
+        }
+        Rebuild2Args::Sorted none{};
+        if ((status = lj2_launch_rebuild(ctx, P, epoch, ctx->position.ptr, 0, none, nullptr)) != 0) return status;
+    }
+    ctx->list_valid = true;
+    ctx->list_signature = P.signature;
+    return lj2_launch_force(ctx, P, req, epoch, 0, ctx->order.ptr, ctx->position.ptr, ctx->force.ptr);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// sorted-resident molecular dynamics
+// ------------------------------------------------------------------------------------------------
+//
+// lumol_cuda_md_run of a velocity-Verlet NVE run of a single-LJ system on the neighbour-list path
+// (lumol-sim/src/md/molecular_dynamics.rs:66-76 around integrators.rs:39-69).  Between the entry and the exit of the call
+// the state (x, v, f, m) lives in CELL ORDER: the force kernel stores forces with unit stride, the kick + drift kernel
+// refreshes the frames (and the largest displacement) in the same pass over the atoms, and a rebuild moves the state into
+// the new order inside the cooperative kernel.  Per step: kick-drift-refresh, rebuild guard (two launches that return at
+// once), force kernel, fix-up.
+//
+// Several ranks (one process per GPU): a rank owns a contiguous range of units, i.e. a slab of cells, and integrates only
+// its own atoms.  Every rank has the same frame layout (all of them sort all atoms at a rebuild), so the owner of an
+// atom stores its new frame position, ghost images included, straight into the frames of the ranks whose units stage the
+// atom's cell (NVLink peer stores, CUDA IPC mappings; need_mask from the unit tables).  Frames alternate between two
+// copies with the step parity, so a rank one step ahead never overwrites what a neighbour is still reading.  The last
+// block of the kick-drift kernel publishes, on every peer, the rank's largest squared displacement and an arrival stamp;
+// a one-block kernel waits for the stamps of all ranks and takes the rebuild decision from the global maximum, so all
+// ranks rebuild in the same step.  At a rebuild every rank stores the positions and velocities of its atoms into the
+// state arrays of all peers (a device-side all-gather), then all ranks sort identically.  No NCCL call inside the loop.
+
+constexpr int SRE_THREADS = 256;
+constexpr int SYNC_ARRIVED = 0;    // [parity][rank]: epoch of the last kick-drift of that rank that has landed here
+constexpr int SYNC_DISP = 32;      // [parity][rank]: float bits of its largest squared displacement
+constexpr int SYNC_GATHERED = 64;  // [rank]: epoch of the last rebuild gather of that rank that has landed here
+constexpr int SYNC_LOCAL = 96;     // [parity]: this rank's running maximum; +2: ticket counter; +3: gather ticket counter
+constexpr int SYNC_INTS = 128;
+
+struct SreArgs {
+    int n, s_lo, s_hi;
+    GridView g;
+    ExtGrid e;
+    double half_dt, dt;
+    double* __restrict__ x;
+    double* __restrict__ v;
+    const double* __restrict__ f;
+    const double* __restrict__ m;
+    const double* __restrict__ xref;
+    const int* __restrict__ kshift;
+    const int* __restrict__ sorted_cell;
+    const int* __restrict__ cell_start;
+    const int* __restrict__ ext_start;
+    size_t fstride;
+    double scale, threshold2;
+    int epoch, parity;
+    int* __restrict__ flags;
+    // sharding
+    int nranks, rank;
+    const int* __restrict__ need_mask;
+    double* frame[PEER_MAX_RANKS];  // this parity's frame copy on every rank
+    int* sync[PEER_MAX_RANKS];      // the SYNC_* block of every rank
+};
+
+// integrators.rs:47-53 (and :55-68 of the previous step when MERGED): a = f / m; v += (0.5 dt) a; x += v dt, with the
+// reference's roundings; then the frame images of the new position and the displacement since the rebuild.
+// One thread per COMPONENT (three consecutive threads per atom, SRE_ATOMS atoms per block): every access to the packed
+// n x 3 arrays and to the (x, y, z) frames is coalesced.
+constexpr int SRE_ATOMS = SRE_THREADS / 4;  // 64 atoms use 192 threads of a 256-thread block
+
+template <bool MERGED>
+__global__ void __launch_bounds__(SRE_THREADS) sre_kick_drift_kernel(SreArgs a) {
+    __shared__ float square[SRE_THREADS];
+    __shared__ float block_max[SRE_THREADS / 32];
+    __shared__ bool last_block;
+    const int local_atom = threadIdx.x / 3, c = threadIdx.x - 3 * local_atom;
+    const int s = a.s_lo + blockIdx.x * SRE_ATOMS + local_atom;
+    const bool active = local_atom < SRE_ATOMS && s < a.s_hi;
+    int* local = a.sync[a.rank];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.flags[FLAG_DEFERRED] = 0;
+        if (a.nranks == 1) a.flags[FLAG_DISP + (a.parity ^ 1)] = 0;  // the slot of the next evaluation
+    }
+    float d2c = 0.0f;
+    if (active) {
+        const size_t k = 3 * (size_t)s + c;
+        const double kick = __dmul_rn(a.half_dt, __ddiv_rn(a.f[k], a.m[s]));
+        double v = __dadd_rn(a.v[k], kick);
+        if (MERGED) v = __dadd_rn(v, kick);
+        const double p = __dadd_rn(a.x[k], __dmul_rn(v, a.dt));
+        a.v[k] = v;
+        a.x[k] = p;
+        const double d = p - a.xref[k];
+        d2c = __double2float_ru(d * d);
+        if (!(d2c >= 0.0f)) d2c = 3.0e38f;  // NaN
+        int shift[3];
+        unpack_shift(a.kshift[s], shift[0], shift[1], shift[2]);
+        const double length = a.g.length[c];
+        const double wrapped = p - (double)shift[c] * length;
+        const int cell = a.sorted_cell[s];
+        const int rank_in_cell = s - a.cell_start[cell];
+        const unsigned targets = a.nranks == 1 ? 1u : ((unsigned)a.need_mask[cell] | (1u << a.rank));
+        for_each_image(a.e, a.ext_start, cell, rank_in_cell, [&](int f, int sx, int sy, int sz) {
+            const int image = c == 0 ? sx : (c == 1 ? sy : sz);
+            const double value = (wrapped + (double)image * length) * a.scale;
+            for (int r = 0; r < a.nranks; r++) {
+                if (targets & (1u << r)) a.frame[r][3 * (size_t)f + c] = value;
+            }
+        });
+    }
+    square[threadIdx.x] = d2c;
+    __syncthreads();
+    float d2f = 0.0f;
+    if (active && c == 0) {
+        d2f = square[threadIdx.x] + square[threadIdx.x + 1] + square[threadIdx.x + 2];
+        if (a.nranks == 1 && !(d2f <= (float)a.threshold2)) a.flags[FLAG_REBUILD] = a.epoch;  // also catches NaN
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+    if ((threadIdx.x & 31) == 0) block_max[threadIdx.x >> 5] = d2f;
+    __syncthreads();
+    if (a.nranks == 1) {
+        if (threadIdx.x == 0) {
+            float m = block_max[0];
+            for (int w = 1; w < SRE_THREADS / 32; w++) m = fmaxf(m, block_max[w]);
+            atomicMax(a.flags + FLAG_DISP + a.parity, __float_as_int(m));
+        }
+        return;
+    }
+    // sharded: the peer stores of this block are visible before its ticket is taken; the last block publishes
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = block_max[0];
+        for (int w = 1; w < SRE_THREADS / 32; w++) m = fmaxf(m, block_max[w]);
+        atomicMax(local + SYNC_LOCAL + a.parity, __float_as_int(m));
+        __threadfence();
+        last_block = atomicAdd(local + SYNC_LOCAL + 2, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_block && threadIdx.x < a.nranks) {
+        const int mine = *(volatile int*)(local + SYNC_LOCAL + a.parity);
+        int* peer = a.sync[threadIdx.x];
+        *(volatile int*)(peer + SYNC_DISP + a.parity * PEER_MAX_RANKS + a.rank) = mine;
+        __threadfence_system();
+        *(volatile int*)(peer + SYNC_ARRIVED + a.parity * PEER_MAX_RANKS + a.rank) = a.epoch;
+    }
+    if (last_block) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            local[SYNC_LOCAL + 2] = 0;
+            local[SYNC_LOCAL + a.parity] = 0;  // read above; this parity is used again two steps from now
+        }
+    }
+}
+
+// Sharded: waits for the kick-drift of every rank (their halo frames are then in place), takes the rebuild decision from
+// the largest displacement of all atoms of all ranks.  One warp.
+__global__ void sre_sync_kernel(int nranks, int epoch, int parity, float threshold2, const int* __restrict__ sync,
+                                int* __restrict__ flags, double* __restrict__ results) {
+    const int lane = threadIdx.x;
+    int value = 0, ok = 1;
+    if (lane < nranks) {
+        const volatile int* stamp = sync + SYNC_ARRIVED + parity * PEER_MAX_RANKS + lane;
+        const long long start = clock64();
+        while (*stamp != epoch) {
+            if (clock64() - start > 40000000000ll) {
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence_system();
+        value = *(const volatile int*)(sync + SYNC_DISP + parity * PEER_MAX_RANKS + lane);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        value = max(value, __shfl_xor_sync(0xffffffffu, value, o));
+        ok = min(ok, __shfl_xor_sync(0xffffffffu, ok, o));
+    }
+    if (lane == 0) {
+        flags[FLAG_DISP + parity] = value;
+        flags[FLAG_DISP + (parity ^ 1)] = 0;
+        const float d2 = __int_as_float(value);
+        if (!(d2 <= threshold2)) flags[FLAG_REBUILD] = epoch;
+        if (!ok) results[RES_FLAGS + 1] = 1.0;
+    }
+}
+
+// Sharded, at a rebuild: the positions and velocities of this rank's atoms into the state arrays of every other rank.
+struct SreGatherArgs {
+    int epoch, nranks, rank;
+    size_t lo3, hi3;
+    const double* __restrict__ x;
+    const double* __restrict__ v;
+    double* peer_x[PEER_MAX_RANKS];
+    double* peer_v[PEER_MAX_RANKS];
+    int* sync[PEER_MAX_RANKS];
+    const int* __restrict__ flags;
+};
+
+__global__ void __launch_bounds__(SRE_THREADS) sre_gather_kernel(SreGatherArgs a) {
+    if (a.flags[FLAG_REBUILD] != a.epoch) return;
+    __shared__ bool last_block;
+    for (size_t k = a.lo3 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.hi3; k += (size_t)gridDim.x * blockDim.x) {
+        const double x = a.x[k], v = a.v[k];
+        for (int r = 0; r < a.nranks; r++) {
+            if (r == a.rank) continue;
+            a.peer_x[r][k] = x;
+            a.peer_v[r][k] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    int* local = a.sync[a.rank];
+    if (threadIdx.x == 0) last_block = atomicAdd(local + SYNC_LOCAL + 3, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last_block) {
+        if (threadIdx.x < a.nranks) {
+            __threadfence_system();
+            *(volatile int*)(a.sync[threadIdx.x] + SYNC_GATHERED + a.rank) = a.epoch;
+        }
+        if (threadIdx.x == 0) local[SYNC_LOCAL + 3] = 0;
+    }
+}
+
+// state <-> caller's order
+__global__ void __launch_bounds__(SRE_THREADS)
+    sre_enter_kernel(int n, const int* __restrict__ order, const double* __restrict__ position, const double* __restrict__ velocity,
+                     const double* __restrict__ force, const double* __restrict__ mass, double* __restrict__ x, double* __restrict__ v,
+                     double* __restrict__ f, double* __restrict__ m, int* __restrict__ origin) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = order[s];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        x[3 * (size_t)s + c] = position[3 * (size_t)i + c];
+        v[3 * (size_t)s + c] = velocity[3 * (size_t)i + c];
+        f[3 * (size_t)s + c] = force[3 * (size_t)i + c];
+    }
+    m[s] = mass[i];
+    origin[s] = i;
+}
+
+__global__ void __launch_bounds__(SRE_THREADS)
+    sre_leave_kernel(int n, const int* __restrict__ origin, const double* __restrict__ x, const double* __restrict__ v,
+                     const double* __restrict__ f, double* __restrict__ position, double* __restrict__ velocity,
+                     double* __restrict__ force, int* __restrict__ order) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = origin[s];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        position[3 * (size_t)i + c] = x[3 * (size_t)s + c];
+        velocity[3 * (size_t)i + c] = v[3 * (size_t)s + c];
+        force[3 * (size_t)i + c] = f[3 * (size_t)s + c];
+    }
+    order[s] = i;  // the list stays valid for evaluations in the caller's order
+}
+
+// integrators.rs:55-68: the second half kick of the last step
+__global__ void __launch_bounds__(SRE_THREADS)
+    sre_kick_kernel(size_t lo3, size_t hi3, double half_dt, const double* __restrict__ f, const double* __restrict__ m, double* __restrict__ v) {
+    for (size_t k = lo3 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < hi3; k += (size_t)gridDim.x * blockDim.x) {
+        v[k] = __dadd_rn(v[k], __dmul_rn(half_dt, __ddiv_rn(f[k], m[k / 3])));
+    }
+}
+
+bool sorted_md_applicable(Context* ctx) {
+    const char* knob = std::getenv("LUMOL_CUDA_SORTED_MD");  // read at every call: the tests switch it
+    if (knob != nullptr && knob[0] == '0') return false;
+    static const char* lj2 = std::getenv("LUMOL_CUDA_LJ2");
+    if (lj2 != nullptr && lj2[0] == '0') return false;
+    if (ctx->integrator != LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET || ctx->thermostat != LUMOL_CUDA_THERMOSTAT_NONE || ctx->controls != 0) return false;
+    if (!(ctx->any_pair && ctx->single_lj && ctx->coulomb.kind == 0) || ctx->nbonds + ctx->nangles + ctx->ndihedrals != 0) return false;
+    if (ctx->forced_path == 0 || ctx->forced_path == 2 || ctx->nranks > PEER_MAX_RANKS) return false;
+    if (ctx->n >= (int64_t)RAW_VALUE_MASK) return false;
+    return choose_neighbor_path(ctx, ctx->max_pair_cutoff) == 1;
+}
+
+static int sorted_md_run_checked(Context* ctx, int64_t nsteps);
+
+int sorted_md_run(Context* ctx, int64_t nsteps) {
+    const int status = sorted_md_run_checked(ctx, nsteps);
+    if (status != 0) ctx->list_valid = false;  // the order map may describe the state arrays, not the caller's
+    return status;
+}
+
+static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
+    const bool sharded = ctx->nranks > 1;
+    ctx->path = 1;
+    ctx->lj2_active = true;
+    Lj2Plan P;
+    int status = lj2_plan(ctx, sharded, P);
+    if (status != 0) return status;
+    const int n = P.n;
+    int* flags = ctx->nl_flags.ptr;
+    // state arrays padded to whole rank blocks (the exit all-gather moves equal blocks)
+    const size_t padded = (size_t)P.units_per_rank * U_ATOMS * (size_t)(sharded ? ctx->nranks : 1);
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_x.reserve(3 * padded));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_v.reserve(3 * padded));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_f.reserve(3 * padded));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_m.reserve(padded));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_tmp.reserve(4 * (size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_origin.reserve(2 * (size_t)n));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_need_mask.reserve((size_t)P.ncells + 1));
+    const bool fresh_sync = ctx->sre_sync.ptr == nullptr;
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_sync.reserve(SYNC_INTS));
+    if (fresh_sync) LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->sre_sync.ptr, 0, SYNC_INTS * sizeof(int), ctx->stream));
+
+    // ---- peers ------------------------------------------------------------------------------------------
+    void* peers[4 * PEER_MAX_RANKS] = {};
+    if (sharded) {
+        void* local[4] = {ctx->sre_x.ptr, ctx->sre_v.ptr, ctx->frame_pos.ptr, ctx->sre_sync.ptr};
+        bool ok = false;
+        LUMOL_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((status = comm_map_peer_buffers(ctx, 4, local, peers, &ok)) != 0) return status;
+        if (!ok) return ctx->fail(LUMOL_CUDA_ERROR_COMM, "peer memory (CUDA IPC over NVLink) is not available between the ranks");
+    } else {
+        peers[0 * PEER_MAX_RANKS] = ctx->sre_x.ptr;
+        peers[1 * PEER_MAX_RANKS] = ctx->sre_v.ptr;
+        peers[2 * PEER_MAX_RANKS] = ctx->frame_pos.ptr;
+        peers[3 * PEER_MAX_RANKS] = ctx->sre_sync.ptr;
+    }
+
+    // ---- entry: a list valid for the current positions (caller's order), then the state into cell order -----------
+    const bool reuse = ctx->list_valid && P.signature == ctx->list_signature;
+    ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
+    int epoch = ctx->list_epoch;
+    {
+        ScopedClock clock(ctx, &ctx->clk_neighbor);
+        if (!reuse) {
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, epoch);
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_DEFERRED, 0);
+            ctx->launches += 2;
+        } else if ((status = lj2_launch_update(ctx, P, epoch)) != 0) {
+            return status;
+        }
+        Rebuild2Args::Sorted none{};
+        if ((status = lj2_launch_rebuild(ctx, P, epoch, ctx->position.ptr, 0, none, sharded ? ctx->sre_need_mask.ptr : nullptr)) != 0) return status;
+    }
+    ctx->list_valid = true;
+    ctx->list_signature = P.signature;
+    const int blocks_all = (n + SRE_THREADS - 1) / SRE_THREADS;
+    sre_enter_kernel<<<blocks_all, SRE_THREADS, 0, ctx->stream>>>(n, ctx->order.ptr, ctx->position.ptr, ctx->velocity.ptr, ctx->force.ptr,
+                                                                  ctx->mass.ptr, ctx->sre_x.ptr, ctx->sre_v.ptr, ctx->sre_f.ptr, ctx->sre_m.ptr,
+                                                                  ctx->sre_origin.ptr);
+    ctx->launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    if (sharded) {
+        // nobody pushes into a peer whose buffers are not in place yet
+        LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->results.ptr + RES_FLAGS + 1, 0, sizeof(double), ctx->stream));
+        if ((status = comm_barrier(ctx)) != 0) return status;
+    }
+
+    // ---- steps -------------------------------------------------------------------------------------------------
+    const int owned = P.s_hi - P.s_lo;
+    const int blocks_owned = std::max(1, (owned + SRE_ATOMS - 1) / SRE_ATOMS);
+    const int blocks_kick = std::max(1, std::min(ctx->sm_count * 8, (3 * owned + SRE_THREADS - 1) / SRE_THREADS));
+    ComputeRequest req;
+    req.forces = true;
+    req.pairs = true;
+    for (int64_t step = 0; step < nsteps; step++) {
+        ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
+        epoch = ctx->list_epoch;
+        const int parity = epoch & 1;
+        {
+            ScopedClock clock(ctx, &ctx->clk_integrate);
+            SreArgs a;
+            a.n = n;
+            a.s_lo = P.s_lo;
+            a.s_hi = P.s_hi;
+            a.g = P.g;
+            a.e = P.e;
+            a.half_dt = 0.5 * ctx->dt;
+            a.dt = ctx->dt;
+            a.x = ctx->sre_x.ptr;
+            a.v = ctx->sre_v.ptr;
+            a.f = ctx->sre_f.ptr;
+            a.m = ctx->sre_m.ptr;
+            a.xref = ctx->xref.ptr;
+            a.kshift = ctx->kshift.ptr;
+            a.sorted_cell = ctx->sorted_cell.ptr;
+            a.cell_start = ctx->cell_start.ptr;
+            a.ext_start = ctx->ext_start.ptr;
+            a.fstride = P.fstride;
+            a.scale = P.scale;
+            a.threshold2 = 0.25 * P.skin * P.skin;
+            a.epoch = epoch;
+            a.parity = parity;
+            a.flags = flags;
+            a.nranks = sharded ? ctx->nranks : 1;
+            a.rank = sharded ? ctx->rank : 0;
+            a.need_mask = ctx->sre_need_mask.ptr;
+            for (int r = 0; r < a.nranks; r++) {
+                a.frame[r] = (double*)peers[2 * PEER_MAX_RANKS + r] + (size_t)parity * 3 * P.fstride;
+                a.sync[r] = (int*)peers[3 * PEER_MAX_RANKS + r];
+            }
+            if (step == 0) {
+                sre_kick_drift_kernel<false><<<blocks_owned, SRE_THREADS, 0, ctx->stream>>>(a);
+            } else {
+                sre_kick_drift_kernel<true><<<blocks_owned, SRE_THREADS, 0, ctx->stream>>>(a);
+            }
+            ctx->launches++;
+            ctx->clk_integrate.launches++;
+            LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+        }
+        if (sharded) {
+            ScopedClock clock(ctx, &ctx->clk_comm);
+            sre_sync_kernel<<<1, 32, 0, ctx->stream>>>(ctx->nranks, epoch, parity, (float)(0.25 * P.skin * P.skin), ctx->sre_sync.ptr, flags,
+                                                       ctx->results.ptr);
+            SreGatherArgs g;
+            g.epoch = epoch;
+            g.nranks = ctx->nranks;
+            g.rank = ctx->rank;
+            g.lo3 = 3 * (size_t)P.s_lo;
+            g.hi3 = 3 * (size_t)P.s_hi;
+            g.x = ctx->sre_x.ptr;
+            g.v = ctx->sre_v.ptr;
+            for (int r = 0; r < ctx->nranks; r++) {
+                g.peer_x[r] = (double*)peers[0 * PEER_MAX_RANKS + r];
+                g.peer_v[r] = (double*)peers[1 * PEER_MAX_RANKS + r];
+                g.sync[r] = (int*)peers[3 * PEER_MAX_RANKS + r];
+            }
+            g.flags = flags;
+            sre_gather_kernel<<<ctx->sm_count, SRE_THREADS, 0, ctx->stream>>>(g);
+            ctx->launches += 2;
+            ctx->clk_comm.launches += 2;
+            LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+        }
+        {
+            ScopedClock clock(ctx, &ctx->clk_neighbor);
+            Rebuild2Args::Sorted sorted{};
+            sorted.active = 1;
+            sorted.x = ctx->sre_x.ptr;
+            sorted.v = ctx->sre_v.ptr;
+            sorted.m = ctx->sre_m.ptr;
+            sorted.tmp = ctx->sre_tmp.ptr;
+            sorted.origin = ctx->sre_origin.ptr;
+            sorted.tmp_origin = ctx->sre_origin.ptr + n;
+            sorted.nranks = sharded ? ctx->nranks : 1;
+            sorted.gathered = ctx->sre_sync.ptr + SYNC_GATHERED;
+            if ((status = lj2_launch_rebuild(ctx, P, epoch, ctx->sre_x.ptr, parity, sorted, sharded ? ctx->sre_need_mask.ptr : nullptr)) != 0) {
+                return status;
+            }
+        }
+        if ((status = lj2_launch_force(ctx, P, req, epoch, parity, nullptr, ctx->sre_x.ptr, ctx->sre_f.ptr, sharded)) != 0) return status;
+        ctx->md_step++;
+    }
+    if (nsteps > 0) {
+        ScopedClock clock(ctx, &ctx->clk_integrate);
+        sre_kick_kernel<<<blocks_kick, SRE_THREADS, 0, ctx->stream>>>(3 * (size_t)P.s_lo, 3 * (size_t)P.s_hi, 0.5 * ctx->dt, ctx->sre_f.ptr,
+                                                                      ctx->sre_m.ptr, ctx->sre_v.ptr);
         ctx->launches++;
+        ctx->clk_integrate.launches++;
         LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
     }
+
+    // ---- exit: every rank gets every atom back, in the caller's order ---------------------------------------------------
+    if (sharded) {
+        const size_t chunk = 3 * (size_t)P.units_per_rank * U_ATOMS;
+        if ((status = comm_allgather_chunks(ctx, ctx->sre_x.ptr, chunk)) != 0) return status;
+        if ((status = comm_allgather_chunks(ctx, ctx->sre_v.ptr, chunk)) != 0) return status;
+        if ((status = comm_allgather_chunks(ctx, ctx->sre_f.ptr, chunk)) != 0) return status;
+    }
+    sre_leave_kernel<<<blocks_all, SRE_THREADS, 0, ctx->stream>>>(n, ctx->sre_origin.ptr, ctx->sre_x.ptr, ctx->sre_v.ptr, ctx->sre_f.ptr,
+                                                                  ctx->position.ptr, ctx->velocity.ptr, ctx->force.ptr, ctx->order.ptr);
+    ctx->launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
 }
 

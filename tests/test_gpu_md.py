@@ -313,3 +313,40 @@ def test_remove_rotation_and_rewrap():
     weights = water.masses.reshape(-1, 3, 1)
     com = (centers * weights).sum(axis=1) / weights.sum(axis=1)
     assert (com >= -1e-9).all() and (com < water.cell.a() + 1e-9).all()
+
+
+def test_sorted_resident_md_equals_the_step_by_step_path(monkeypatch):
+    """NVE velocity-Verlet of a single-LJ system on the neighbour-list path runs with the state in cell order for the
+    duration of lumol_cuda_md_run (pairs_lj2.cu): same trajectory as the path that keeps the caller's atom order
+    (LUMOL_CUDA_SORTED_MD=0), across neighbour-list rebuilds and across two calls."""
+    import os
+
+    from lumol_b200 import synthetic
+    from lumol_b200.device import DeviceSystem
+
+    results = []
+    for knob in ("0", "1"):
+        monkeypatch.setenv("LUMOL_CUDA_SORTED_MD", knob)
+        system = synthetic.lj_box(32, seed=20240 + 15)
+        synthetic.maxwell_boltzmann(system, 300.0, seed=3)
+        device = DeviceSystem(0)
+        device.sync(system, velocities=True)
+        lib, ctx = device.lib, device.ctx
+        _ffi.check(ctx, lib.lumol_cuda_md_setup(ctx, _ffi.INTEGRATOR_VELOCITY_VERLET, 1.0))
+        for steps in (25, 45):
+            _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, steps))
+        n = system.size()
+        x, v, f = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        _ffi.check(ctx, lib.lumol_cuda_get_positions(ctx, _ffi.as_double_pointer(x)))
+        _ffi.check(ctx, lib.lumol_cuda_get_velocities(ctx, _ffi.as_double_pointer(v)))
+        _ffi.check(ctx, lib.lumol_cuda_get_forces(ctx, _ffi.as_double_pointer(f)))
+        results.append((x, v, f, device.stats().neighbor_rebuilds))
+        # forces of the final state against an evaluation from scratch
+        fresh = device.compute(forces=True).forces
+        assert np.abs(fresh - f).max() < 1e-11 * np.abs(f).max()
+        device.close()
+    (x0, v0, f0, r0), (x1, v1, f1, r1) = results
+    assert r0 >= 2 and r1 >= 2
+    assert np.abs(x1 - x0).max() < 1e-10
+    assert np.abs(v1 - v0).max() < 1e-10 * np.abs(v0).max()
+    assert np.abs(f1 - f0).max() < 1e-9 * np.abs(f0).max()

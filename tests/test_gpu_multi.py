@@ -1,4 +1,4 @@
-"""Sharded (2-rank, NCCL) evaluation against the single-GPU one; needs two devices (``-m gpu``)."""
+"""Sharded (NCCL + NVLink peer memory) evaluation and MD against the single-GPU ones; needs several devices (``-m gpu``)."""
 
 import os
 import subprocess
@@ -10,13 +10,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_ranks_match_one_rank():
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_ranks_match_one_rank(nranks):
+    """tools/multi_gpu_check.py under torchrun: forces / energies / virials of every system family, ten MD steps, and
+    device-resident MD across neighbour-list rebuilds on a 274 625-atom box, N ranks against one."""
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-               "--master-port", "29611", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    result = subprocess.run(command, capture_output=True, text=True, timeout=900)
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
+               "--master-port", str(29611 + nranks), os.path.join(ROOT, "tools", "multi_gpu_check.py")]
+    result = subprocess.run(command, capture_output=True, text=True, timeout=1500)
     assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-4000:]
     assert "multi-GPU check ok" in result.stdout

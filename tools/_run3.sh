@@ -3,7 +3,7 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "lj or sta
 timeout 600 python -m pytest tests/test_gpu_bench_parity.py -q -m gpu -k "lj_bench or cutoff" 2>&1 | tail -3
 timeout 300 python bench.py --no-spce --no-cpu-baseline --no-e2e --steps 300 --warmup 50 > gpurun_out/lj2_a.json 2> gpurun_out/lj2_a.err; tail -3 gpurun_out/lj2_a.err
 LUMOL_CUDA_LJ2_ALL_LEVELS=1 timeout 300 python bench.py --no-spce --no-cpu-baseline --no-e2e --steps 300 --warmup 50 > gpurun_out/lj2_alllevels.json 2> gpurun_out/lj2_b.err
-LUMOL_CUDA_LJ2_ALL_LEVELS=2 timeout 300 python bench.py --no-spce --no-cpu-baseline --no-e2e --steps 100 --warmup 20 > gpurun_out/lj2_nopairs.json 2> gpurun_out/lj2_d.err
+timeout 300 python -m pytest tests/test_gpu_md.py -q -m gpu -x 2>&1 | tail -3
 python - <<'PY'
 import json
 for name in ("lj2_a","lj2_alllevels","lj2_nopairs"):
@@ -14,5 +14,5 @@ for name in ("lj2_a","lj2_alllevels","lj2_nopairs"):
     except Exception as e:
         print(name, "failed", e)
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file gpurun_out/r2e_launches_lj2.csv python tools/profile_step.py --steps 2 2>&1 | tail -1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lj2_force_kernel -s 12 -c 1 -o gpurun_out/r2d_lj2 python tools/profile_step.py --steps 16 2>&1 | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 14 --csv --log-file gpurun_out/r2e_launches_lj2.csv python tools/profile_step.py --steps 3 2>&1 | tail -1
+

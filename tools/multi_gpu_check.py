@@ -63,11 +63,54 @@ def check(name, system, rank, world, local_rank, kspace=None):
     sharded_device.close()
 
 
+def check_long_md(name, system, steps, rank, world, local_rank):
+    """Device-resident velocity-Verlet MD long enough to cross neighbour-list rebuilds: the sharded run (units of atoms
+    owned by ranks, halo frames pushed over NVLink, device-side all-gather at rebuilds) against the single-GPU run."""
+    results = []
+    for sharded in (False, True):
+        device = DeviceSystem(local_rank)
+        if sharded:
+            parallel.init_communicator(device, rank, world)
+        device.sync(system, velocities=True)
+        lib, ctx = device.lib, device.ctx
+        _ffi.check(ctx, lib.lumol_cuda_md_setup(ctx, _ffi.INTEGRATOR_VELOCITY_VERLET, 1.0))
+        for chunk in (steps // 3, steps - steps // 3):  # two calls: the state leaves and re-enters cell order
+            _ffi.check(ctx, lib.lumol_cuda_md_run(ctx, chunk))
+        n = system.size()
+        x, v, f = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        _ffi.check(ctx, lib.lumol_cuda_get_positions(ctx, _ffi.as_double_pointer(x)))
+        _ffi.check(ctx, lib.lumol_cuda_get_velocities(ctx, _ffi.as_double_pointer(v)))
+        _ffi.check(ctx, lib.lumol_cuda_get_forces(ctx, _ffi.as_double_pointer(f)))
+        rebuilds = device.stats().neighbor_rebuilds
+        # the sharded state is usable by the estimators afterwards
+        energy = device.compute(energy=True).energy.pairs
+        results.append((x, v, f, rebuilds, energy))
+        device.close()
+    (x1, v1, f1, r1, e1), (xs, vs, fs, rs, es) = results
+    assert rs >= 2, f"{name}: the run crossed no rebuild ({rs})"
+    assert np.abs(xs - x1).max() < 1e-9, (name, np.abs(xs - x1).max())
+    assert np.abs(vs - v1).max() < 1e-9 * np.abs(v1).max(), (name, np.abs(vs - v1).max())
+    assert np.abs(fs - f1).max() < 1e-8 * np.abs(f1).max(), (name, np.abs(fs - f1).max())
+    assert abs(es - e1) < 1e-10 * abs(e1), (name, es, e1)
+    if rank == 0:
+        print(f"{name}: {world} ranks vs 1 rank after {steps} MD steps ({rs} rebuilds): positions {np.abs(xs - x1).max():.1e} A, "
+              f"forces {np.abs(fs - f1).max() / np.abs(f1).max():.1e}")
+
+
 def main():
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import systems
+
+    # 274 625 atoms (odd count), 26 x 26 x 26 cells: every rank owns whole units; hot enough to rebuild within 70 steps
+    big = synthetic.lj_box(65, seed=11)
+    synthetic.maxwell_boltzmann(big, 300.0, seed=3)
+    check_long_md("lj-274625 (sorted-resident MD, halo exchange)", big, 70, rank, world, local_rank)
+    # fewer units than would fill every rank evenly, odd atom count
+    small_box = synthetic.lj_box((17, 17, 19), seed=12)
+    synthetic.maxwell_boltzmann(small_box, 300.0, seed=4)
+    check_long_md("lj-5491 (sorted-resident MD, few units)", small_box, 60, rank, world, local_rank)
 
     lj = synthetic.lj_box(24, seed=3)  # 13824 atoms, cell list
     synthetic.maxwell_boltzmann(lj, 120.0, seed=1)
@@ -98,6 +141,13 @@ def main():
     large.set_coulomb_potential(ewald)
     synthetic.maxwell_boltzmann(large, 300.0, seed=5)
     check("spce-3000 (tiled k-space kernels, kmax 30)", large, rank, world, local_rank, kspace=1)
+
+    odd = synthetic.spce_box(9, flexible=True)  # 2187 atoms: odd count, peer-push inbox alignment
+    ewald = lumol.SharedEwald(lumol.Ewald(8.5, 6, 0.33))
+    ewald.set_restriction(lumol.PairRestriction.InterMolecular)
+    odd.set_coulomb_potential(ewald)
+    synthetic.maxwell_boltzmann(odd, 300.0, seed=8)
+    check("spce-2187 (odd atom count)", odd, rank, world, local_rank)
 
     nacl = systems.md_nacl("wolf")
     nacl.positions += np.random.Generator(np.random.PCG64(9)).uniform(-0.2, 0.2, nacl.positions.shape)  # perfect lattice: zero forces
