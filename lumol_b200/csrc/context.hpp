@@ -313,6 +313,8 @@ int launch_pairs_allpairs(Context* ctx, const ComputeRequest& req);             
 int launch_pairs_cells(Context* ctx, const ComputeRequest& req);                                 // pairs_cells.cu
 int launch_pairs_lj2(Context* ctx, const ComputeRequest& req);                                   // pairs_lj2.cu
 bool lj2_enabled(const Context* ctx);                                                            // pairs_lj2.cu
+int launch_pairs_cq(Context* ctx, const ComputeRequest& req);                                    // pairs_lj2.cu
+bool cq_applicable(const Context* ctx);                                                          // pairs_lj2.cu
 int choose_neighbor_path(Context* ctx, double cutoff);                                           // pairs_cells.cu
 int neighbor_list_status(Context* ctx, int* rebuilds, int* overflow);                            // pairs_cells.cu
 int launch_coulomb_self(Context* ctx);                                                           // pairs_allpairs.cu

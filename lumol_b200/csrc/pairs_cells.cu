@@ -1181,6 +1181,11 @@ int launch_pairs_cells(Context* ctx, const ComputeRequest& req) {
         ctx->lj2_active = true;
         return launch_pairs_lj2(ctx, req);
     }
+    // water-like charged systems: staged, branch-free Lennard-Jones + Ewald / Wolf kernel of pairs_lj2.cu
+    if (cq_applicable(ctx)) {
+        ctx->lj2_active = true;
+        return launch_pairs_cq(ctx, req);
+    }
     ctx->lj2_active = false;
     if (ctx->n >= (int64_t)LIST_INDEX_MASK) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "the neighbour list handles at most %u atoms per GPU", LIST_INDEX_MASK);

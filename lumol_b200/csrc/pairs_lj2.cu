@@ -33,6 +33,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <climits>
 
 #include <cstdlib>
 #include <cstring>
@@ -70,6 +71,18 @@ constexpr int DEFERRED_PER_ATOM = 4;
 
 __host__ __device__ __forceinline__ int pad2(int count) { return (count + 1) & ~1; }
 
+// What a force kernel expects of the units and lists the rebuild makes for it (two kernels share the rebuild: the
+// Lennard-Jones kernel above and the charged-system kernel at the end of this file).
+struct UnitShape {
+    int atoms;           // atoms per unit
+    int lanes_per_atom;  // lanes sharing a column (2, 4, ...): they take the halves of its words in turn
+    int slots;           // capacity of one staged copy
+    int value_factor;    // staged entries hold slot * value_factor (doubles before the slot's x in an (x, y, z) copy: 3)
+    int width;           // doubles per frame slot: 3 (x, y, z) or 4 (x, y, z, charge)
+    int flags;           // bit 0: entries carry the neighbour's kind (2 bits) and a same-molecule bit above 13 bits of slot;
+                         // bit 1: the force kernel reads the raw 32-bit columns of the build (no level / bank order pass)
+};
+
 // ------------------------------------------------------------------------------------------------
 // rebuild phases specific to this path
 // ------------------------------------------------------------------------------------------------
@@ -101,6 +114,9 @@ struct Scatter2Args {
     int* __restrict__ sorted_cell;
     double* __restrict__ xref;        // 3 n, sorted order: position at the rebuild
     int* __restrict__ kshift;         // n: wrap counts floor(x / L) packed 3 x 10 bits + sign offset
+    // charged systems: (first atom of the molecule << 2) | kind rides in the w component of sorted_f32
+    const unsigned* __restrict__ kind;
+    const int* __restrict__ mol_first;
 };
 
 // wrap counts in [-512, 511] per axis
@@ -131,7 +147,8 @@ __device__ __forceinline__ void scatter2_phase(int vb, const Scatter2Args& a, in
     const double x = px - kx * a.g.length[0] - ((double)cx + 0.5) * a.g.edge[0];
     const double y = py - ky * a.g.length[1] - ((double)cy + 0.5) * a.g.edge[1];
     const double z = pz - kz * a.g.length[2] - ((double)cz + 0.5) * a.g.edge[2];
-    a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, 0.0f);
+    const int tag = a.kind != nullptr ? ((a.mol_first[i] << 2) | (int)(a.kind[i] & 3u)) : 0;
+    a.sorted_f32[dst] = make_float4((float)x, (float)y, (float)z, __int_as_float(tag));
     a.sorted_cell[dst] = c;
     a.xref[3 * dst] = px;
     a.xref[3 * dst + 1] = py;
@@ -195,9 +212,11 @@ struct Frame2Args {
     const int* __restrict__ kshift;
     int* __restrict__ fidx;        // n: frame index of the real copy
     int* __restrict__ frame_atom;  // frame slot -> sorted index (images included)
-    double* __restrict__ frame;    // (x, y, z) per frame slot
+    double* __restrict__ frame;    // (x, y, z) or (x, y, z, charge) per frame slot
     size_t fstride;                // frame slots allocated
     double scale;
+    int width;
+    const double* __restrict__ charge;  // caller's order (width 4)
 };
 
 // frame indices and the frames themselves at the rebuild positions
@@ -205,7 +224,7 @@ __device__ __forceinline__ void frame2_phase(int vb, const Frame2Args& a, int* _
     const int s = vb * REBUILD_THREADS + threadIdx.x;
     if (vb == 0 && threadIdx.x < 2) {
         // the dummy that padding entries of unstaged columns point at
-        for (int p = 0; p < 3; p++) a.frame[3 * threadIdx.x + p] = 1.0e9 * (double)(p + 1);
+        for (int p = 0; p < a.width; p++) a.frame[a.width * threadIdx.x + p] = p < 3 ? 1.0e9 * (double)(p + 1) : 0.0;
         a.frame_atom[threadIdx.x] = -1;
     }
     if (s >= a.n) return;
@@ -225,9 +244,10 @@ __device__ __forceinline__ void frame2_phase(int vb, const Frame2Args& a, int* _
         if (first) a.fidx[s] = f;
         first = false;
         a.frame_atom[f] = s;
-        a.frame[3 * (size_t)f] = (x + (double)sx * a.g.length[0]) * a.scale;
-        a.frame[3 * (size_t)f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
-        a.frame[3 * (size_t)f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
+        a.frame[(size_t)a.width * f] = (x + (double)sx * a.g.length[0]) * a.scale;
+        a.frame[(size_t)a.width * f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
+        a.frame[(size_t)a.width * f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
+        if (a.width == 4) a.frame[(size_t)a.width * f + 3] = a.charge[a.order[s]];
     });
 }
 
@@ -262,6 +282,7 @@ struct UnitRows {
 
 struct Table2Args {
     int n, nunits;
+    UnitShape shape;
     ExtGrid e;
     const int* __restrict__ sorted_cell;
     const int* __restrict__ ext_start;
@@ -279,7 +300,7 @@ __device__ __forceinline__ void unit_table_phase(int vb, const Table2Args& a) {
     const int lane = threadIdx.x & 31;
     const int unit = vb * REBUILD_WARPS + (threadIdx.x >> 5);
     if (unit >= a.nunits) return;
-    const int s_first = unit * U_ATOMS, s_last = min(a.n, s_first + U_ATOMS) - 1;
+    const int s_first = unit * a.shape.atoms, s_last = min(a.n, s_first + a.shape.atoms) - 1;
     const int c_first = a.sorted_cell[s_first], c_last = a.sorted_cell[s_last];
     UnitRows rows;
     rows.init(c_first, c_last - c_first + 1, a.e.nx);
@@ -319,7 +340,7 @@ __device__ __forceinline__ void unit_table_phase(int vb, const Table2Args& a) {
                 for (int X = xa; X <= xa + len + 1; X++) atomicOr(a.need_mask + a.e.source(X, Y, Z), bit);
             }
         }
-        if (total > LJ2_SLOTS) staged = false;
+        if (total > a.shape.slots) staged = false;
     }
     if (!staged && lane == 0) atomicAdd(a.flags + FLAG_UNSTAGED, 1);
     if (lane == 0) a.header[unit] = make_int4(rows.c0, rows.K, staged ? nruns : -1, total);
@@ -330,6 +351,9 @@ __device__ __forceinline__ void unit_table_phase(int vb, const Table2Args& a) {
 struct Build2Args {
     GridView g;
     ExtGrid e;
+    UnitShape shape;
+    const int* __restrict__ order;  // sorted slot -> state index
+    int o_lo, o_hi;                 // state-index range of the atoms this rank owns (first-generation sharding of the charged path)
     int ncells;
     int cells_per_warp;
     int s_lo, s_hi;      // sorted range of the atoms this rank owns (lists are built for those)
@@ -370,12 +394,17 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
         for (int base = hs + 32 * first_chunk; base < he; base += 32 * BUILD2_CHUNKS) {
             const int s_i = base + lane;
             bool active = s_i < he && s_i >= a.s_lo && s_i < a.s_hi;
+            if (active && a.o_hi > a.o_lo) {
+                const int origin = a.order[s_i];
+                active = origin >= a.o_lo && origin < a.o_hi;
+            }
             float xf = 1.0e18f, yf = 0.0f, zf = 0.0f;
+            int tag_i = 0;
             bool staged = false;
             const int4* runs = a.runs;
             int run_base = 0;
             if (s_i < he) {
-                const int unit = s_i / U_ATOMS;
+                const int unit = s_i / a.shape.atoms;
                 const int4 header = a.header[unit];
                 staged = header.z >= 0;
                 runs += (size_t)unit * LJ2_MAX_RUNS;
@@ -383,7 +412,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                 if (staged) {
                     const int4 run = runs[run_base + 4];  // dy = dz = 0
                     const int f_self = 2 + a.ext_start[a.e.index(cx + 1, cy + 1, cz + 1)] + (s_i - hs);
-                    a.self_slot[s_i] = (unsigned short)(3 * (run.z + (f_self - run.x)));
+                    a.self_slot[s_i] = (unsigned short)(a.shape.value_factor * (run.z + (f_self - run.x)));
                 }
             }
             if (active) {
@@ -391,6 +420,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                 xf = f.x;
                 yf = f.y;
                 zf = f.z;
+                tag_i = __float_as_int(f.w);
             }
             if (!__any_sync(0xffffffffu, active)) {
                 if (s_i < he) a.ncount[s_i] = 0;
@@ -428,7 +458,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                     // triples: the offset of its x in doubles), or its frame index
                     const int frame_first = 2 + a.ext_start[a.e.index(cx + dx, uy + 1, uz + 1)];  // unwrapped: the image seen from here
                     const int tag = (staged ? run.z + (frame_first - run.x) : frame_first) - s0;
-                    const int factor = staged ? 3 : 1;
+                    const int factor = staged ? a.shape.value_factor : 1;
                     for (int first = s0; first < s1; first += 8) {
                         float4 f[8];
 #pragma unroll
@@ -442,7 +472,14 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                                 if (count < a.capacity) {
                                     int level = (int)floorf((sqrtf(r2) - a.cutoff) * a.inv_delta);
                                     level = max(0, min(LJ2_LEVELS - 1, level));
-                                    mine[count & 3] = ((unsigned)level << 28) | (unsigned)(factor * (tag + s_j));
+                                    unsigned value = (unsigned)(factor * (tag + s_j));
+                                    if (a.shape.flags & 1) {
+                                        // neighbour's kind and "same molecule" above the slot (13 bits) or the frame index (25 bits)
+                                        const int tag_j = __float_as_int(f[u].w);
+                                        const unsigned bits = (unsigned)(tag_j & 3) | ((tag_j >> 2) == (tag_i >> 2) ? 4u : 0u);
+                                        value |= bits << (staged ? 13 : 25);
+                                    }
+                                    mine[count & 3] = ((unsigned)level << 28) | value;
                                     if ((count & 3) == 3) column[(count >> 2) * 32] = make_uint4(mine[0], mine[1], mine[2], mine[3]);
                                 }
                                 count++;
@@ -625,7 +662,7 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
 constexpr int REORDER2_THREADS = 32;
 
 __global__ void __launch_bounds__(REORDER2_THREADS)
-    list_reorder2_kernel(int s_lo, int n, int capacity, const int4* __restrict__ header, const int* __restrict__ ncount,
+    list_reorder2_kernel(UnitShape shape, int s_lo, int n, int capacity, const int4* __restrict__ header, const int* __restrict__ ncount,
                          unsigned* __restrict__ nlist, unsigned short* __restrict__ cum_levels, int epoch,
                          const int* __restrict__ flags) {
     if (flags[FLAG_REBUILD] != epoch || flags[FLAG_NONFINITE] != 0) return;
@@ -637,8 +674,9 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
     for (int slab = s_lo / REORDER2_THREADS + blockIdx.x; slab * REORDER2_THREADS < n; slab += gridDim.x) {
         const int s_i = slab * REORDER2_THREADS + t;
         if (s_i >= n) continue;
-        const bool staged = header[s_i / U_ATOMS].z >= 0;
+        const bool staged = header[s_i / shape.atoms].z >= 0;
         const int count = ncount[s_i];
+        const int word_stride = shape.lanes_per_atom / 2;
         uint4* words = reinterpret_cast<uint4*>(nlist) + (size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31);
         const int nwords = (count + 3) >> 2;
         for (int b = 0; b < LJ2_LEVELS * 16; b++) last[b][t] = 0;
@@ -684,7 +722,7 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
             }
             continue;
         }
-        const int lane_base = LJ2_LPA * (s_i & (16 / LJ2_LPA - 1));
+        const int lane_base = shape.lanes_per_atom * (s_i & (16 / shape.lanes_per_atom - 1));
         unsigned packed[4] = {0u, 0u, 0u, 0u};
         int level = -1, level_end = 0;
         unsigned nonempty = 0;  // buckets of the current level that still hold entries
@@ -698,7 +736,7 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
             // entry p sits in word p >> 3, half (p >> 2) & 1; with four lanes per atom, lanes {0, 1} walk the even words and
             // {2, 3} the odd ones
             const int word = p >> 3;
-            const int h = ((word % LJ2_WORD_STRIDE) << 1) | ((p >> 2) & 1), step = ((word / LJ2_WORD_STRIDE) << 2) | (p & 3);
+            const int h = ((word % word_stride) << 1) | ((p >> 2) & 1), step = ((word / word_stride) << 2) | (p & 3);
             const int want = (lane_base + h + step) & 15;
             // first non-empty bucket at or after `want`, cyclically
             const unsigned rotated = ((nonempty >> want) | (nonempty << (16 - want))) & 0xffffu;
@@ -733,8 +771,9 @@ struct Update2Args {
     const int* __restrict__ sorted_cell;
     const int* __restrict__ cell_start;
     const int* __restrict__ ext_start;
-    double* __restrict__ frame;  // (x, y, z) per frame slot
+    double* __restrict__ frame;  // (x, y, z) or (x, y, z, charge) per frame slot
     size_t fstride;
+    int width;
     double scale;
     double threshold2;
     int epoch;
@@ -768,9 +807,9 @@ __global__ void __launch_bounds__(256) lj2_update_kernel(Update2Args a) {
         const int c = a.sorted_cell[s];
         const int rank = s - a.cell_start[c];
         for_each_image(a.e, a.ext_start, c, rank, [&](int f, int sx, int sy, int sz) {
-            a.frame[3 * (size_t)f] = (x + (double)sx * a.g.length[0]) * a.scale;
-            a.frame[3 * (size_t)f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
-            a.frame[3 * (size_t)f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
+            a.frame[(size_t)a.width * f] = (x + (double)sx * a.g.length[0]) * a.scale;
+            a.frame[(size_t)a.width * f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
+            a.frame[(size_t)a.width * f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
         });
     }
 #pragma unroll
@@ -1291,6 +1330,7 @@ bool lj2_enabled(const Context* ctx) {
 
 // Sizes, ownership and buffers of one evaluation.
 struct Lj2Plan {
+    UnitShape shape;
     int n, ncells, next, nunits, capacity, deferred_capacity, scan_blocks, ext_scan_blocks;
     size_t stride, fstride;
     GridView g;
@@ -1301,9 +1341,22 @@ struct Lj2Plan {
 };
 
 // `sharded`: the sorted-resident engine on several ranks (units split between the ranks); otherwise one rank does all.
-static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
+static UnitShape lj2_shape() {
+    UnitShape shape;
+    shape.atoms = U_ATOMS;
+    shape.lanes_per_atom = LJ2_LPA;
+    shape.slots = LJ2_SLOTS;
+    shape.value_factor = 3;
+    shape.width = 3;
+    shape.flags = 0;
+    return shape;
+}
+
+// `cutoff`: the list radius is cutoff + skin.  `lj`: the single Lennard-Jones interaction (nullptr on the charged path).
+static int lj2_plan(Context* ctx, bool sharded, const UnitShape& shape, double cutoff, const lumol_cuda_pair* lj, Lj2Plan& P) {
     const int n = (int)ctx->n;
     P.n = n;
+    P.shape = shape;
     for (int d = 0; d < 3; d++) {
         P.g.nc[d] = ctx->ncell[d];
         P.g.length[d] = ctx->cell.h[4 * d];
@@ -1317,14 +1370,13 @@ static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
     P.e.ez = P.e.nz + 2;
     P.ncells = P.g.nc[0] * P.g.nc[1] * P.g.nc[2];
     P.next = P.e.count();
-    const lumol_cuda_pair& p = ctx->host_pairs[0];
-    P.cutoff = p.cutoff;
+    P.cutoff = cutoff;
     P.skin = ctx->skin_effective;
     P.radius = P.cutoff + P.skin;
-    P.sigma = p.p[0];
-    P.epsilon = p.p[1];
+    P.sigma = lj != nullptr ? lj->p[0] : 1.0;
+    P.epsilon = lj != nullptr ? lj->p[1] : 0.0;
     P.scale = 1.0 / P.sigma;
-    P.shift = p.shift;
+    P.shift = lj != nullptr ? lj->shift : 0.0;
 
     const double volume = P.g.length[0] * P.g.length[1] * P.g.length[2];
     const double mean_neighbors = 4.0 / 3.0 * PI * P.radius * P.radius * P.radius * (double)n / volume;
@@ -1332,13 +1384,13 @@ static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
     if (capacity > n) capacity = n;
     P.capacity = (capacity + 7) / 8 * 8;
     P.stride = ((size_t)n + 31) / 32 * 32;
-    P.nunits = (n + U_ATOMS - 1) / U_ATOMS;
+    P.nunits = (n + shape.atoms - 1) / shape.atoms;
     const int nranks = sharded ? ctx->nranks : 1;
     P.units_per_rank = (P.nunits + nranks - 1) / nranks;
     P.u_lo = sharded ? std::min(P.nunits, P.units_per_rank * ctx->rank) : 0;
     P.u_hi = sharded ? std::min(P.nunits, P.u_lo + P.units_per_rank) : P.nunits;
-    P.s_lo = std::min(n, P.u_lo * U_ATOMS);
-    P.s_hi = std::min(n, P.u_hi * U_ATOMS);
+    P.s_lo = std::min(n, P.u_lo * shape.atoms);
+    P.s_hi = std::min(n, P.u_hi * shape.atoms);
     // frame slots: the atoms, their ghost images (a boundary atom has up to seven), one slot of padding per extended cell
     const double ghost_ratio = (double)P.next / (double)P.ncells;
     size_t fstride = (size_t)((double)n * (ghost_ratio * 1.5 + 0.25)) + 2 * (size_t)P.next + 64;
@@ -1363,7 +1415,7 @@ static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
     LUMOL_CUDA_CHECK(ctx, ctx->fidx.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->kshift.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->frame_atom.reserve(P.fstride));
-    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(2 * 3 * P.fstride));  // two copies: a sharded run alternates with the step parity
+    LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(2 * (size_t)shape.width * P.fstride));  // two copies: a sharded run alternates with the step parity
     LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)P.nunits));
     LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)P.nunits * LJ2_MAX_RUNS));
     LUMOL_CUDA_CHECK(ctx, ctx->cum_levels.reserve(P.stride * LJ2_LEVELS));
@@ -1383,6 +1435,8 @@ static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
     signature = mix2(signature, (uint64_t)P.capacity);
     signature = mix2(signature, (uint64_t)P.fstride);
     signature = mix2(signature, (uint64_t)P.u_lo * 1315423911ull + (uint64_t)P.u_hi);
+    signature = mix2(signature, (uint64_t)shape.atoms * 64 + (uint64_t)shape.width * 8 + (uint64_t)shape.flags);
+    if (shape.flags && ctx->nranks > 1) signature = mix2(signature, (uint64_t)ctx->rank * 977 + (uint64_t)ctx->nranks);
     P.signature = signature;
     if (!ctx->flags_initialised) {
         LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->nl_flags.ptr, 0, 16 * sizeof(int), ctx->stream));
@@ -1391,7 +1445,7 @@ static int lj2_plan(Context* ctx, bool sharded, Lj2Plan& P) {
     return 0;
 }
 
-static double* lj2_frame(Context* ctx, const Lj2Plan& P, int parity) { return ctx->frame_pos.ptr + (size_t)parity * 3 * P.fstride; }
+static double* lj2_frame(Context* ctx, const Lj2Plan& P, int parity) { return ctx->frame_pos.ptr + (size_t)parity * P.shape.width * P.fstride; }
 
 // Refresh of the frames from positions in the caller's order (state arrays not in cell order).
 static int lj2_launch_update(Context* ctx, const Lj2Plan& P, int epoch) {
@@ -1411,6 +1465,7 @@ static int lj2_launch_update(Context* ctx, const Lj2Plan& P, int epoch) {
     u.ext_start = ctx->ext_start.ptr;
     u.frame = lj2_frame(ctx, P, 0);
     u.fstride = P.fstride;
+    u.width = P.shape.width;
     u.scale = P.scale;
     u.threshold2 = 0.25 * P.skin * P.skin;
     u.epoch = epoch;
@@ -1425,7 +1480,7 @@ static int lj2_launch_update(Context* ctx, const Lj2Plan& P, int epoch) {
 // The guarded rebuild (cooperative kernel + final order of the columns): does nothing unless flags[FLAG_REBUILD] holds
 // this epoch.  `state`: positions the atoms are binned from (caller's order, or the old cell order of a sorted-resident run).
 static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const double* state, int parity,
-                              const Rebuild2Args::Sorted& sorted, int* need_mask) {
+                              const Rebuild2Args::Sorted& sorted, int* need_mask, int owner_lo = 0, int owner_hi = 0) {
     const int n = P.n;
     int* flags = ctx->nl_flags.ptr;
     int* cell_of = ctx->cell_of.ptr;
@@ -1462,6 +1517,8 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     r.scatter.sorted_cell = ctx->sorted_cell.ptr;
     r.scatter.xref = ctx->xref.ptr;
     r.scatter.kshift = ctx->kshift.ptr;
+    r.scatter.kind = (P.shape.flags & 1) ? ctx->kind.ptr : nullptr;
+    r.scatter.mol_first = ctx->mol_first.ptr;
     r.frame.n = n;
     r.frame.g = P.g;
     r.frame.e = P.e;
@@ -1476,8 +1533,11 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     r.frame.frame = lj2_frame(ctx, P, parity);
     r.frame.fstride = P.fstride;
     r.frame.scale = P.scale;
+    r.frame.width = P.shape.width;
+    r.frame.charge = ctx->charge.ptr;
     r.table.n = n;
     r.table.nunits = P.nunits;
+    r.table.shape = P.shape;
     r.table.e = P.e;
     r.table.sorted_cell = ctx->sorted_cell.ptr;
     r.table.ext_start = ctx->ext_start.ptr;
@@ -1489,6 +1549,10 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     Build2Args& b = r.build;
     b.g = P.g;
     b.e = P.e;
+    b.shape = P.shape;
+    b.order = order;
+    b.o_lo = owner_lo;
+    b.o_hi = owner_hi;
     b.ncells = P.ncells;
     b.cells_per_warp = P.ncells * BUILD2_CHUNKS / (ctx->sm_count * 8 * REBUILD_WARPS * 16) + 1;
     b.s_lo = P.s_lo;
@@ -1522,7 +1586,7 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     }
     ctx->launches++;
     ctx->clk_neighbor.launches++;
-    const size_t reorder_smem = (size_t)P.capacity * REORDER2_THREADS * sizeof(unsigned);
+    const size_t reorder_smem = (P.shape.flags & 2) ? 0 : (size_t)P.capacity * REORDER2_THREADS * sizeof(unsigned);
     if (reorder_smem > 190 * 1024) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list columns of %d entries do not fit the reorder kernel", P.capacity);
     }
@@ -1530,10 +1594,11 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
         LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)reorder_smem));
     }
+    if (P.shape.flags & 2) return 0;  // raw columns
     const int slabs = (P.s_hi - P.s_lo + REORDER2_THREADS - 1) / REORDER2_THREADS;
     const int reorder_grid = std::max(1, slabs < ctx->sm_count * 8 ? slabs : ctx->sm_count * 8);
     list_reorder2_kernel<<<reorder_grid, REORDER2_THREADS, reorder_smem, ctx->stream>>>(
-        P.s_lo, P.s_hi, P.capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, ctx->cum_levels.ptr, epoch, flags);
+        P.shape, P.s_lo, P.s_hi, P.capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, ctx->cum_levels.ptr, epoch, flags);
     ctx->launches++;
     ctx->clk_neighbor.launches++;
     LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1628,7 +1693,7 @@ static int lj2_launch_force(Context* ctx, const Lj2Plan& P, const ComputeRequest
 // One evaluation with the state arrays in the caller's order (lumol_cuda_compute, and MD outside the sorted-resident engine).
 int launch_pairs_lj2(Context* ctx, const ComputeRequest& req) {
     Lj2Plan P;
-    int status = lj2_plan(ctx, false, P);
+    int status = lj2_plan(ctx, false, lj2_shape(), ctx->host_pairs[0].cutoff, &ctx->host_pairs[0], P);
     if (status != 0) return status;
     int* flags = ctx->nl_flags.ptr;
     const bool reuse = ctx->list_valid && P.signature == ctx->list_signature;
@@ -1706,57 +1771,61 @@ struct SreArgs {
 };
 
 // integrators.rs:47-53 (and :55-68 of the previous step when MERGED): a = f / m; v += (0.5 dt) a; x += v dt, with the
-// reference's roundings; then the frame images of the new position and the displacement since the rebuild.
-// One thread per COMPONENT (three consecutive threads per atom, SRE_ATOMS atoms per block): every access to the packed
-// n x 3 arrays and to the (x, y, z) frames is coalesced.
-constexpr int SRE_ATOMS = SRE_THREADS / 4;  // 64 atoms use 192 threads of a 256-thread block
+// reference's roundings; then the frame images of the new position and the displacement since the rebuild.  One thread per
+// atom (a thread-per-component variant with fully coalesced accesses was slower: 0.087 against 0.048 ms for 1M atoms, the
+// cell arithmetic of the ghost images was then done three times).
+constexpr int SRE_ATOMS = SRE_THREADS;
 
 template <bool MERGED>
 __global__ void __launch_bounds__(SRE_THREADS) sre_kick_drift_kernel(SreArgs a) {
-    __shared__ float square[SRE_THREADS];
     __shared__ float block_max[SRE_THREADS / 32];
     __shared__ bool last_block;
-    const int local_atom = threadIdx.x / 3, c = threadIdx.x - 3 * local_atom;
-    const int s = a.s_lo + blockIdx.x * SRE_ATOMS + local_atom;
-    const bool active = local_atom < SRE_ATOMS && s < a.s_hi;
+    const int s = a.s_lo + blockIdx.x * SRE_ATOMS + threadIdx.x;
     int* local = a.sync[a.rank];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.flags[FLAG_DEFERRED] = 0;
         if (a.nranks == 1) a.flags[FLAG_DISP + (a.parity ^ 1)] = 0;  // the slot of the next evaluation
     }
-    float d2c = 0.0f;
-    if (active) {
-        const size_t k = 3 * (size_t)s + c;
-        const double kick = __dmul_rn(a.half_dt, __ddiv_rn(a.f[k], a.m[s]));
-        double v = __dadd_rn(a.v[k], kick);
-        if (MERGED) v = __dadd_rn(v, kick);
-        const double p = __dadd_rn(a.x[k], __dmul_rn(v, a.dt));
-        a.v[k] = v;
-        a.x[k] = p;
-        const double d = p - a.xref[k];
-        d2c = __double2float_ru(d * d);
-        if (!(d2c >= 0.0f)) d2c = 3.0e38f;  // NaN
-        int shift[3];
-        unpack_shift(a.kshift[s], shift[0], shift[1], shift[2]);
-        const double length = a.g.length[c];
-        const double wrapped = p - (double)shift[c] * length;
+    float d2f = 0.0f;
+    if (s < a.s_hi) {
+        const double mass = a.m[s];
+        double p[3];
+        double d2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const size_t k = 3 * (size_t)s + c;
+            const double kick = __dmul_rn(a.half_dt, __ddiv_rn(a.f[k], mass));
+            double v = __dadd_rn(a.v[k], kick);
+            if (MERGED) v = __dadd_rn(v, kick);
+            p[c] = __dadd_rn(a.x[k], __dmul_rn(v, a.dt));
+            a.v[k] = v;
+            a.x[k] = p[c];
+            const double d = p[c] - a.xref[k];
+            d2 += d * d;
+        }
+        if (a.nranks == 1 && !(d2 <= a.threshold2)) a.flags[FLAG_REBUILD] = a.epoch;  // also catches NaN
+        d2f = __double2float_ru(d2);
+        if (!(d2f >= 0.0f)) d2f = 3.0e38f;
+        int kx, ky, kz;
+        unpack_shift(a.kshift[s], kx, ky, kz);
+        const double x = p[0] - (double)kx * a.g.length[0];
+        const double y = p[1] - (double)ky * a.g.length[1];
+        const double z = p[2] - (double)kz * a.g.length[2];
         const int cell = a.sorted_cell[s];
         const int rank_in_cell = s - a.cell_start[cell];
         const unsigned targets = a.nranks == 1 ? 1u : ((unsigned)a.need_mask[cell] | (1u << a.rank));
         for_each_image(a.e, a.ext_start, cell, rank_in_cell, [&](int f, int sx, int sy, int sz) {
-            const int image = c == 0 ? sx : (c == 1 ? sy : sz);
-            const double value = (wrapped + (double)image * length) * a.scale;
+            const double fx = (x + (double)sx * a.g.length[0]) * a.scale;
+            const double fy = (y + (double)sy * a.g.length[1]) * a.scale;
+            const double fz = (z + (double)sz * a.g.length[2]) * a.scale;
             for (int r = 0; r < a.nranks; r++) {
-                if (targets & (1u << r)) a.frame[r][3 * (size_t)f + c] = value;
+                if (!(targets & (1u << r))) continue;
+                double* frame = a.frame[r];
+                frame[3 * (size_t)f] = fx;
+                frame[3 * (size_t)f + 1] = fy;
+                frame[3 * (size_t)f + 2] = fz;
             }
         });
-    }
-    square[threadIdx.x] = d2c;
-    __syncthreads();
-    float d2f = 0.0f;
-    if (active && c == 0) {
-        d2f = square[threadIdx.x] + square[threadIdx.x + 1] + square[threadIdx.x + 2];
-        if (a.nranks == 1 && !(d2f <= (float)a.threshold2)) a.flags[FLAG_REBUILD] = a.epoch;  // also catches NaN
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
@@ -1770,14 +1839,13 @@ __global__ void __launch_bounds__(SRE_THREADS) sre_kick_drift_kernel(SreArgs a) 
         }
         return;
     }
-    // sharded: the peer stores of this block are visible before its ticket is taken; the last block publishes
-    __threadfence_system();
-    __syncthreads();
+    // sharded: the peer stores of the whole block (ordered before thread 0 by the barrier above; the fence is cumulative)
+    // are visible system-wide before the block's ticket is taken; the last block publishes
     if (threadIdx.x == 0) {
         float m = block_max[0];
         for (int w = 1; w < SRE_THREADS / 32; w++) m = fmaxf(m, block_max[w]);
         atomicMax(local + SYNC_LOCAL + a.parity, __float_as_int(m));
-        __threadfence();
+        __threadfence_system();
         last_block = atomicAdd(local + SYNC_LOCAL + 2, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
@@ -1852,10 +1920,12 @@ __global__ void __launch_bounds__(SRE_THREADS) sre_gather_kernel(SreGatherArgs a
             a.peer_v[r][k] = v;
         }
     }
-    __threadfence_system();
     __syncthreads();
     int* local = a.sync[a.rank];
-    if (threadIdx.x == 0) last_block = atomicAdd(local + SYNC_LOCAL + 3, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // cumulative: covers the peer stores of the block, ordered before this thread by the barrier
+        last_block = atomicAdd(local + SYNC_LOCAL + 3, 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
     if (last_block) {
         if (threadIdx.x < a.nranks) {
@@ -1933,7 +2003,7 @@ static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
     ctx->path = 1;
     ctx->lj2_active = true;
     Lj2Plan P;
-    int status = lj2_plan(ctx, sharded, P);
+    int status = lj2_plan(ctx, sharded, lj2_shape(), ctx->host_pairs[0].cutoff, &ctx->host_pairs[0], P);
     if (status != 0) return status;
     const int n = P.n;
     int* flags = ctx->nl_flags.ptr;
@@ -2107,6 +2177,579 @@ static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
     }
     sre_leave_kernel<<<blocks_all, SRE_THREADS, 0, ctx->stream>>>(n, ctx->sre_origin.ptr, ctx->sre_x.ptr, ctx->sre_v.ptr, ctx->sre_f.ptr,
                                                                   ctx->position.ptr, ctx->velocity.ptr, ctx->force.ptr, ctx->order.ptr);
+    ctx->launches++;
+    LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// charged systems: Lennard-Jones (or null) pairs + Ewald real space / Wolf in one branch-free pass
+// ------------------------------------------------------------------------------------------------
+//
+// Replaces, for "water-like" systems on the neighbour-list path, the loops of sys/compute.rs:37-55 + ewald.rs:430-530 /
+// wolf.rs:177-283: every pair entry Lennard-Jones, null or absent with restriction None, at most four particle kinds,
+// coulomb restriction None or InterMolecular, alpha * rc <= 3.4.  Everything else keeps list_force_kernel.
+//
+// The first-generation kernel gathered 48 bytes per neighbour from L1 / L2 and branched on kind, restriction and charge:
+// 18 of 32 lanes active, FP64 pipe 27 % busy (profiles/r1y_list_force_kernel_spce98k_summary.csv).  Here a unit of 256
+// consecutive atoms stages its neighbourhood once, as (x, y, z, charge) quadruples (one bulk copy per row of cells), the
+// 16-bit list entries carry the neighbour's kind and a same-molecule bit next to the slot, and one straight-line body
+// evaluates both terms for every listed pair:
+//   * one reciprocal square root (hardware seed + one cubic step) serves r, 1 / r and 1 / r^2;
+//   * epsilon = 0 (pairs without Lennard-Jones term, or outside their cut-off) and q_i q_j = 0 (zero charge, outside the
+//     coulomb cut-off, excluded Wolf pair) switch the terms off arithmetically;
+//   * ONE exponential exp(-(alpha r)^2) per pair serves the Gaussian term and erfc(alpha r) = exp(-(alpha r)^2) erfcx(alpha r),
+//     erfcx by a degree-14 polynomial in (x - 4) / (x + 4) (tools/fit_erfcx.py: 3.4e-15 relative); an excluded Ewald pair
+//     takes erfc - 1 = -erf (ewald.rs:395-399, 419-425);
+//   * pairs whose r^2 falls in the narrow band around a cut-off are left to the fix-up kernel, which evaluates them with
+//     the reference's own arithmetic (`r >= rc` for the pair potential, pairs.rs:186; `r > rc` for Ewald and Wolf,
+//     ewald.rs:390, wolf.rs:91).
+
+constexpr int CQ_THREADS = 512;
+constexpr int CQ_LPA = 2;
+constexpr int CQ_ATOMS = CQ_THREADS / CQ_LPA;
+constexpr int CQ_SLOTS = 6784;  // quadruples of one staged copy: 212 KiB
+constexpr int CQ_NV = 16;
+constexpr int CQ_MAX_KINDS = 4;
+constexpr double CQ_XMAX = 3.45;
+
+// tools/fit_erfcx.py
+constexpr double CQ_ERFCX_A = 2.1594202898550723, CQ_ERFCX_B = 1.1594202898550725;
+__constant__ double CQ_ERFCX[15] = {
+    0.3773882991430218,     -0.3429947340586216,   0.17661230872576122,    -0.07210396072897172,  0.02349570533116956,
+    -0.00604706965782215,   0.0011867532468606704, -0.00016177461783462791, 1.0614456744267083e-05, 9.443963073478152e-07,
+    -2.7237999019525457e-07, 7.795810757036897e-09, 4.342510292920047e-09,  -3.307242319007307e-10, -6.793336512007265e-11,
+};
+
+struct CqClass {
+    double sigma2, eps24, eps4, shift;
+    int band_lo;  // top 32 bits of rc^2, minus one; INT_MIN when the pair has no Lennard-Jones term
+    int pad;
+};
+
+struct CqArgs {
+    int n, nunits, capacity;
+    const unsigned* __restrict__ nlist;
+    const int* __restrict__ ncount;
+    const unsigned short* __restrict__ self_slot;
+    const int* __restrict__ fidx;
+    const int* __restrict__ order;
+    const float4* __restrict__ tags;  // sorted_f32: w holds (molecule << 2) | kind
+    const int4* __restrict__ header;
+    const int4* __restrict__ runs;
+    const double* __restrict__ frame;  // (x, y, z, charge) per frame slot
+    CqClass classes[CQ_MAX_KINDS * CQ_MAX_KINDS];
+    int coulomb_kind;        // 0 none, 1 Ewald, 2 Wolf
+    int exclude_same;        // the coulomb restriction is InterMolecular
+    int coulomb_band_lo;
+    double alpha, gauss, wolf_energy, wolf_force;  // gauss = alpha 2 / sqrt(pi)
+    int o_lo, o_hi;          // state-index range owned by this rank
+    int write_forces;
+    double* __restrict__ force;
+    double* __restrict__ partials;
+    int2* __restrict__ deferred;
+    int deferred_capacity;
+    int* __restrict__ flags;
+    int* __restrict__ unit_counter;
+};
+
+// exp(a) for a in [-12, 0]: a = k ln2 + r, |r| <= ln2 / 2, Taylor polynomial of degree 12 (1.7e-16), 2^k by exponent arithmetic
+__device__ __forceinline__ double cq_exp(double a) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: the integer lands in the low word
+    const double shifted = fma(a, 1.4426950408889634, magic);
+    const int k = __double2loint(shifted);
+    const double kd = shifted - magic;
+    double r = fma(kd, -6.93147180369123816490e-01, a);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 479001600.0;
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// erfcx(x) = exp(x^2) erfc(x), x in [0, CQ_XMAX]
+__device__ __forceinline__ double cq_erfcx(double x) {
+    const double d = x + 4.0;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    y = fma(y, fma(e, e, e), y);
+    const double zz = fma((x - 4.0) * y, CQ_ERFCX_A, CQ_ERFCX_B);
+    double p = CQ_ERFCX[14];
+#pragma unroll
+    for (int k = 13; k >= 0; k--) p = fma(p, zz, CQ_ERFCX[k]);
+    return p;
+}
+
+struct CqAtom {
+    double x, y, z, q;        // q already divided by 4 pi epsilon_0
+    const CqClass* row;       // classes of this atom's kind, in shared memory
+};
+
+// One listed neighbour.  `entry`: slot (13 bits) | kind of j (2 bits) | same molecule (1 bit).
+template <int MODE>
+__device__ __forceinline__ void cq_pair(const CqArgs& a, const CqAtom& me, double xj, double yj, double zj, double qj, unsigned kind_j,
+                                        bool same, double& fx, double& fy, double& fz, double (&acc)[CQ_NV], unsigned& near, unsigned bit) {
+    const double dx = me.x - xj, dy = me.y - yj, dz = me.z - zj;
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const int top = __double2hiint(r2);
+    const CqClass& c = me.row[kind_j];
+    const bool lj = c.band_lo != INT_MIN;
+    const bool on_cutoff = (lj && (unsigned)(top - c.band_lo) < 3u) || (a.coulomb_kind != 0 && (unsigned)(top - a.coulomb_band_lo) < 3u);
+    near |= on_cutoff ? bit : 0u;
+    const bool inside_pair = lj && top < c.band_lo && !on_cutoff;
+    const bool inside_coulomb = top < a.coulomb_band_lo && !on_cutoff;
+    // 1 / r: hardware seed and one cubic step, y0 (1 + e / 2 + 3 e^2 / 8) with e = 1 - r2 y0^2
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+    const double e = fma(-(r2 * y0), y0, 1.0);
+    const double rinv = fma(y0 * e, fma(e, 0.375, 0.5), y0);
+    const double rinv2 = rinv * rinv;
+    const double r = r2 * rinv;
+    // Lennard-Jones (functions.rs:80-88): force / r = 24 eps (2 s6^2 - s6) / r^2
+    const double s2 = c.sigma2 * rinv2;
+    const double s6 = s2 * s2 * s2;
+    const double eps24 = inside_pair ? c.eps24 : 0.0;
+    double fr = eps24 * (s6 * fma(2.0, s6, -1.0)) * rinv2;
+    // coulomb (ewald.rs:387-428, wolf.rs:90-117)
+    double qq = me.q * qj;
+    const bool wolf_skip = a.coulomb_kind == 2 && same && a.exclude_same;
+    qq = (inside_coulomb && !wolf_skip) ? qq : 0.0;
+    const double excluded = (a.coulomb_kind == 1 && same && a.exclude_same) ? 1.0 : 0.0;
+    const double x = fmin(a.alpha * r, CQ_XMAX);
+    const double t = cq_exp(-(x * x));
+    const double eor = fma(t, cq_erfcx(x), -excluded) * rinv;  // (erfc(alpha r) - excluded) / r
+    fr += qq * fma(rinv2, fma(a.gauss, t, eor), -a.wolf_force * rinv);
+    fx = fma(fr, dx, fx);
+    fy = fma(fr, dy, fy);
+    fz = fma(fr, dz, fz);
+    if (MODE == 1) {
+        const double fl = eps24 * (s6 * fma(2.0, s6, -1.0)) * rinv2;
+        const double fc = fr - fl;
+        acc[0] += inside_pair ? c.eps4 * fma(s6, s6, -s6) - c.shift : 0.0;
+        acc[14] += inside_pair ? 1.0 : 0.0;
+        acc[2] += fl * dx * dx;
+        acc[3] += fl * dx * dy;
+        acc[4] += fl * dx * dz;
+        acc[5] += fl * dy * dy;
+        acc[6] += fl * dy * dz;
+        acc[7] += fl * dz * dz;
+        acc[1] += qq * (eor - a.wolf_energy);
+        acc[15] += qq != 0.0 ? 1.0 : 0.0;
+        acc[8] += fc * dx * dx;
+        acc[9] += fc * dx * dy;
+        acc[10] += fc * dx * dz;
+        acc[11] += fc * dy * dy;
+        acc[12] += fc * dy * dz;
+        acc[13] += fc * dz * dz;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CQ_THREADS, 1) cq_force_kernel(CqArgs a) {
+    extern __shared__ __align__(16) unsigned char cq_smem[];
+    double* stage = reinterpret_cast<double*>(cq_smem);  // (x, y, z, q) per slot
+    __shared__ __align__(8) unsigned long long full;
+    __shared__ CqClass classes[CQ_MAX_KINDS * CQ_MAX_KINDS];
+    __shared__ int next_unit;
+
+    if (a.flags[FLAG_NONFINITE] != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < CQ_MAX_KINDS * CQ_MAX_KINDS) classes[tid] = a.classes[tid];
+    if (tid < 8) stage[tid] = (tid & 3) == 3 ? 0.0 : 1.0e9 * (double)((tid & 3) + 1);  // dummy slots 0, 1: far away, no charge
+    double acc[CQ_NV];
+#pragma unroll
+    for (int k = 0; k < CQ_NV; k++) acc[k] = 0.0;
+    // the columns are the raw ones of the build: 32-bit entries (level << 28 | flags | slot), four per 16-byte word; the
+    // two lanes of an atom take the even and the odd words
+    const size_t slab_words = (size_t)(a.capacity >> 2) * 32;
+    const int local = tid / CQ_LPA, half = tid % CQ_LPA;
+    unsigned phase = 0;
+
+    for (int unit = blockIdx.x;; ) {
+        __syncthreads();  // everybody is done with the previous copy (and, the first time, the barrier is initialised)
+        if (unit >= a.nunits) break;
+        const int4 header = a.header[unit];
+        const bool staged = header.z >= 0;
+        if (tid < 32) {
+            if (staged) {
+                if (lane == 0) mbar_expect_bytes(&full, 32u * (unsigned)(header.w - 2));
+                __syncwarp();
+                for (int r = lane; r < header.z; r += 32) {
+                    const int4 run = a.runs[(size_t)unit * LJ2_MAX_RUNS + r];
+                    bulk_load(stage + 4 * run.z, a.frame + 4 * (size_t)run.x, (unsigned)run.y * 32u, &full);
+                }
+            } else if (lane == 0) {
+                mbar_arrive(&full);
+            }
+            if (lane == 0) next_unit = atomicAdd(a.unit_counter, 1) + (int)gridDim.x;
+        }
+        // the thread's atom, while the copies are in flight
+        const int s = unit * CQ_ATOMS + local;
+        const bool present = s < a.n;
+        int count = 0, origin = -1, tag = 0;
+        unsigned self = 0;
+        if (present) {
+            count = a.ncount[s];
+            self = a.self_slot[s];
+            origin = a.order[s];
+            tag = __float_as_int(a.tags[s].w);
+        }
+        const bool owned = present && origin >= a.o_lo && origin < a.o_hi;
+        const int column = present ? s : 0;
+        const uint4* words = reinterpret_cast<const uint4*>(a.nlist) + (size_t)(column >> 5) * slab_words + (size_t)half * 32 + (column & 31);
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        mbar_wait(&full, phase);
+        phase ^= 1u;
+        CqAtom me;
+        me.row = classes + (tag & 3) * CQ_MAX_KINDS;
+        if (staged) {
+            me.x = stage[4 * self];
+            me.y = stage[4 * self + 1];
+            me.z = stage[4 * self + 2];
+            me.q = stage[4 * self + 3] * INV_FOUR_PI_EPSILON_0;
+            // this lane's words: half, half + 2, ...
+            const int nwords = owned ? (((count + 3) >> 2) - half + 1) >> 1 : 0;
+            uint4 wcur = nwords > 0 ? words[0] : make_uint4(0, 0, 0, 0);
+            uint4 wnext = nwords > 1 ? words[64] : make_uint4(0, 0, 0, 0);
+            for (int w = 0; w < nwords; w++) {
+                uint4 wafter = make_uint4(0, 0, 0, 0);
+                if (w + 2 < nwords) wafter = words[(size_t)(w + 2) * 64];
+                const unsigned entries[4] = {wcur.x & 0xffffu, wcur.y & 0xffffu, wcur.z & 0xffffu, wcur.w & 0xffffu};
+                unsigned near = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double2* pj = reinterpret_cast<const double2*>(stage + 4 * (entries[q] & 0x1fffu));
+                    const double2 xy = pj[0], zq = pj[1];
+                    cq_pair<MODE>(a, me, xy.x, xy.y, zq.x, zq.y, (entries[q] >> 13) & 3u, (entries[q] >> 15) != 0u, fx, fy, fz, acc, near, 1u << q);
+                }
+                if (near != 0) {
+                    // the defer routine recovers the frame index of a neighbour from the unit's runs (entries as slot * 3)
+                    const unsigned lo = (3u * (entries[0] & 0x1fffu)) | ((3u * (entries[1] & 0x1fffu)) << 16);
+                    const unsigned hi = (3u * (entries[2] & 0x1fffu)) | ((3u * (entries[3] & 0x1fffu)) << 16);
+                    lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, origin, near, lo, hi, true);
+                }
+                wcur = wnext;
+                wnext = wafter;
+            }
+        } else if (owned) {
+            const int f_self = a.fidx[s];
+            me.x = a.frame[4 * (size_t)f_self];
+            me.y = a.frame[4 * (size_t)f_self + 1];
+            me.z = a.frame[4 * (size_t)f_self + 2];
+            me.q = a.frame[4 * (size_t)f_self + 3] * INV_FOUR_PI_EPSILON_0;
+            const int nwords = (((count + 3) >> 2) - half + 1) >> 1;
+            for (int w = 0; w < nwords; w++) {
+                const uint4 word = words[(size_t)w * 64];
+                const unsigned entries[4] = {word.x & RAW_VALUE_MASK, word.y & RAW_VALUE_MASK, word.z & RAW_VALUE_MASK, word.w & RAW_VALUE_MASK};
+#pragma unroll
+                for (int q = 0; q < 4; q += 2) {
+                    unsigned near = 0;
+                    for (int t = 0; t < 2; t++) {
+                        const unsigned entry = entries[q + t];
+                        const double* pj = a.frame + 4 * (size_t)(entry & 0x1ffffffu);
+                        cq_pair<MODE>(a, me, pj[0], pj[1], pj[2], pj[3], (entry >> 25) & 3u, ((entry >> 27) & 1u) != 0u, fx, fy, fz, acc, near, 1u << t);
+                    }
+                    if (near != 0) {
+                        lj2_defer(a.header, a.runs, a.deferred, a.deferred_capacity, a.flags, unit, origin, near, entries[q] & 0x1ffffffu,
+                                  entries[q + 1] & 0x1ffffffu, false);
+                    }
+                }
+            }
+        }
+        fx += __shfl_xor_sync(0xffffffffu, fx, 1);
+        fy += __shfl_xor_sync(0xffffffffu, fy, 1);
+        fz += __shfl_xor_sync(0xffffffffu, fz, 1);
+        if (owned && half == 0 && a.write_forces) {
+            a.force[3 * (size_t)origin] = fx;
+            a.force[3 * (size_t)origin + 1] = fy;
+            a.force[3 * (size_t)origin + 2] = fz;
+        }
+        __syncthreads();
+        unit = next_unit;
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < CQ_NV; k++) acc[k] *= 0.5;
+        block_sum<CQ_NV>(acc, stage);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < CQ_NV; k++) a.partials[(size_t)blockIdx.x * CQ_NV + k] = acc[k];
+        }
+    }
+}
+
+// Pairs left out by a list kernel because they sit on a cut-off: evaluated like the all-pairs kernel evaluates them (the
+// reference's arithmetic and cut-off semantics, any pair potential and restriction), one side of the pair per entry.
+struct FixArgs {
+    const int2* __restrict__ deferred;  // (state index of i, frame index of j)
+    int capacity;
+    const int* __restrict__ frame_atom;
+    const int* __restrict__ order;
+    const double* __restrict__ pos;
+    const double* __restrict__ charge;
+    const unsigned* __restrict__ kind;
+    const int* __restrict__ mol_first;
+    const int* __restrict__ bd_row;
+    const unsigned char* __restrict__ bond_dist;
+    int nkinds;
+    const PairParams* __restrict__ pairs;
+    const TableDesc* __restrict__ tables;
+    const double* __restrict__ table_energy;
+    const double* __restrict__ table_force;
+    CellView cell;
+    CoulombView coulomb;
+    int do_pairs, do_coulomb, full, write_forces;
+    double* __restrict__ force;
+    double* __restrict__ results;
+    const int* __restrict__ flags;
+};
+
+__global__ void __launch_bounds__(128) list_fixup_kernel(FixArgs a) {
+    const int count = min(a.flags[FLAG_DEFERRED], a.capacity);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const int2 entry = a.deferred[k];
+        const int i = entry.x;
+        const int s_j = a.frame_atom[entry.y];
+        if (s_j < 0) continue;
+        const int j = a.order[s_j];
+        double dx = __dadd_rn(a.pos[3 * (size_t)i], -a.pos[3 * (size_t)j]);
+        double dy = __dadd_rn(a.pos[3 * (size_t)i + 1], -a.pos[3 * (size_t)j + 1]);
+        double dz = __dadd_rn(a.pos[3 * (size_t)i + 2], -a.pos[3 * (size_t)j + 2]);
+        vector_image_exact(a.cell, dx, dy, dz);
+        const double r = sqrt(dot3_exact(dx, dy, dz, dx, dy, dz));
+        const bool same_molecule = a.mol_first[i] == a.mol_first[j];
+        const unsigned bits = same_molecule ? a.bond_dist[a.bd_row[i] + (j - a.mol_first[j])] : 0u;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        if (a.do_pairs) {
+            const PairParams& pp = a.pairs[a.kind[i] * a.nkinds + a.kind[j]];
+            if (pp.potential > LUMOL_CUDA_POTENTIAL_NULL && r < pp.cutoff) {
+                double scaling;
+                if (!restriction_excluded(pp.restriction, bits, pp.scale14, scaling)) {
+                    double e, f;
+                    pair_eval(pp, a.tables, a.table_energy, a.table_force, r, e, f);
+                    const double fr = scaling * f / r;
+                    fx += fr * dx;
+                    fy += fr * dy;
+                    fz += fr * dz;
+                    if (a.full) {
+                        const double w = 0.5 * fr;
+                        atomicAdd(a.results + RES_E_PAIRS, 0.5 * scaling * e);
+                        atomicAdd(a.results + RES_PAIR_COUNT, 0.5);
+                        atomicAdd(a.results + RES_W_PAIRS + 0, w * dx * dx);
+                        atomicAdd(a.results + RES_W_PAIRS + 1, w * dx * dy);
+                        atomicAdd(a.results + RES_W_PAIRS + 2, w * dx * dz);
+                        atomicAdd(a.results + RES_W_PAIRS + 3, w * dy * dy);
+                        atomicAdd(a.results + RES_W_PAIRS + 4, w * dy * dz);
+                        atomicAdd(a.results + RES_W_PAIRS + 5, w * dz * dz);
+                    }
+                }
+            }
+        }
+        if (a.do_coulomb && a.coulomb.kind != 0 && r <= a.coulomb.rc) {
+            const double qi = a.charge[i], qj = a.charge[j];
+            if (qi != 0.0 && qj != 0.0) {
+                double scaling;
+                const bool excluded = restriction_excluded(a.coulomb.restriction, bits, a.coulomb.scale14, scaling);
+                double e = 0.0, fr = 0.0;
+                bool active = true;
+                if (a.coulomb.kind == 1) {
+                    ewald_real_pair(a.coulomb, excluded, qi * qj, r, e, fr);
+                } else if (!excluded) {
+                    wolf_pair(a.coulomb, qi * qj, r, e, fr);
+                    e *= scaling;
+                    fr *= scaling;
+                } else {
+                    active = false;
+                }
+                if (active) {
+                    fx += fr * dx;
+                    fy += fr * dy;
+                    fz += fr * dz;
+                    if (a.full) {
+                        const double w = 0.5 * fr;
+                        atomicAdd(a.results + RES_E_COULOMB_REAL, 0.5 * e);
+                        atomicAdd(a.results + RES_COULOMB_PAIR_COUNT, 0.5);
+                        atomicAdd(a.results + RES_W_COULOMB_REAL + 0, w * dx * dx);
+                        atomicAdd(a.results + RES_W_COULOMB_REAL + 1, w * dx * dy);
+                        atomicAdd(a.results + RES_W_COULOMB_REAL + 2, w * dx * dz);
+                        atomicAdd(a.results + RES_W_COULOMB_REAL + 3, w * dy * dy);
+                        atomicAdd(a.results + RES_W_COULOMB_REAL + 4, w * dy * dz);
+                        atomicAdd(a.results + RES_W_COULOMB_REAL + 5, w * dz * dz);
+                    }
+                }
+            }
+        }
+        if (a.write_forces) {
+            atomicAdd(a.force + 3 * (size_t)i, fx);
+            atomicAdd(a.force + 3 * (size_t)i + 1, fy);
+            atomicAdd(a.force + 3 * (size_t)i + 2, fz);
+        }
+    }
+}
+
+static int band_below(double cutoff) {
+    const double squared = cutoff * cutoff;
+    uint64_t pattern;
+    std::memcpy(&pattern, &squared, sizeof(pattern));
+    return (int)(pattern >> 32) - 1;
+}
+
+bool cq_applicable(const Context* ctx) {
+    static const char* knob = std::getenv("LUMOL_CUDA_CQ");
+    if (knob != nullptr && knob[0] == '0') return false;
+    if (ctx->coulomb.kind == 0 || ctx->forced_path == 2 || ctx->nkinds < 1 || ctx->nkinds > CQ_MAX_KINDS) return false;
+    if (ctx->coulomb.restriction != LUMOL_CUDA_RESTRICTION_NONE && ctx->coulomb.restriction != LUMOL_CUDA_RESTRICTION_INTER_MOLECULAR) return false;
+    if (!(ctx->coulomb.alpha * ctx->coulomb.rc <= 3.4)) return false;
+    for (const lumol_cuda_pair& p : ctx->host_pairs) {
+        if (p.potential == LUMOL_CUDA_POTENTIAL_ABSENT || p.potential == LUMOL_CUDA_POTENTIAL_NULL) continue;
+        if (p.potential != LUMOL_CUDA_POTENTIAL_LJ || p.restriction != LUMOL_CUDA_RESTRICTION_NONE) return false;
+    }
+    return ctx->n < (1 << 25);
+}
+
+int launch_pairs_cq(Context* ctx, const ComputeRequest& req) {
+    UnitShape shape;
+    shape.atoms = CQ_ATOMS;
+    shape.lanes_per_atom = CQ_LPA;
+    shape.slots = CQ_SLOTS;
+    shape.value_factor = 1;
+    shape.width = 4;
+    shape.flags = 3;
+    double cutoff = ctx->any_pair ? ctx->max_pair_cutoff : 0.0;
+    if (ctx->coulomb.rc > cutoff) cutoff = ctx->coulomb.rc;
+    Lj2Plan P;
+    int status = lj2_plan(ctx, false, shape, cutoff, nullptr, P);
+    if (status != 0) return status;
+    int64_t o_lo, o_hi;
+    ctx->owned_range(ctx->n, o_lo, o_hi);
+    int* flags = ctx->nl_flags.ptr;
+    const bool reuse = ctx->list_valid && P.signature == ctx->list_signature;
+    ctx->list_epoch = ctx->list_epoch % 1000000000 + 1;
+    const int epoch = ctx->list_epoch;
+    {
+        ScopedClock clock(ctx, &ctx->clk_neighbor);
+        if (!reuse) {
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_REBUILD, epoch);
+            lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, FLAG_DEFERRED, 0);
+            ctx->launches += 2;
+        } else if ((status = lj2_launch_update(ctx, P, epoch)) != 0) {
+            return status;
+        }
+        Rebuild2Args::Sorted none{};
+        const bool sharded = ctx->nranks > 1;
+        if ((status = lj2_launch_rebuild(ctx, P, epoch, ctx->position.ptr, 0, none, nullptr, sharded ? (int)o_lo : 0, sharded ? (int)o_hi : 0)) != 0) {
+            return status;
+        }
+    }
+    ctx->list_valid = true;
+    ctx->list_signature = P.signature;
+
+    const bool do_pairs = req.pairs && ctx->any_pair;
+    const bool do_coulomb = req.coulomb;
+    const bool full = req.energy || req.virial;
+    CqArgs a;
+    a.n = P.n;
+    a.nunits = P.nunits;
+    a.capacity = P.capacity;
+    a.nlist = ctx->nlist.ptr;
+    a.ncount = ctx->ncount.ptr;
+    a.self_slot = ctx->self_local.ptr;
+    a.fidx = ctx->fidx.ptr;
+    a.order = ctx->order.ptr;
+    a.tags = ctx->sorted_f32.ptr;
+    a.header = ctx->blk_header.ptr;
+    a.runs = ctx->blk_entries.ptr;
+    a.frame = lj2_frame(ctx, P, 0);
+    for (int ki = 0; ki < CQ_MAX_KINDS; ki++) {
+        for (int kj = 0; kj < CQ_MAX_KINDS; kj++) {
+            CqClass& c = a.classes[ki * CQ_MAX_KINDS + kj];
+            c.sigma2 = c.eps24 = c.eps4 = c.shift = 0.0;
+            c.band_lo = INT_MIN;
+            c.pad = 0;
+            if (ki >= ctx->nkinds || kj >= ctx->nkinds || !do_pairs) continue;
+            const lumol_cuda_pair& p = ctx->host_pairs[(size_t)ki * ctx->nkinds + kj];
+            if (p.potential != LUMOL_CUDA_POTENTIAL_LJ) continue;
+            c.sigma2 = p.p[0] * p.p[0];
+            c.eps24 = 24.0 * p.p[1];
+            c.eps4 = 4.0 * p.p[1];
+            c.shift = p.shift;
+            c.band_lo = band_below(p.cutoff);
+        }
+    }
+    a.coulomb_kind = do_coulomb ? ctx->coulomb.kind : 0;
+    a.exclude_same = ctx->coulomb.restriction == LUMOL_CUDA_RESTRICTION_INTER_MOLECULAR ? 1 : 0;
+    a.coulomb_band_lo = do_coulomb ? band_below(ctx->coulomb.rc) : INT_MIN;
+    a.alpha = ctx->coulomb.alpha;
+    a.gauss = ctx->coulomb.alpha * FRAC_2_SQRT_PI;
+    a.wolf_energy = ctx->coulomb.kind == 2 ? ctx->coulomb.wolf_energy_constant : 0.0;
+    a.wolf_force = ctx->coulomb.kind == 2 ? ctx->coulomb.wolf_force_constant : 0.0;
+    a.o_lo = (int)o_lo;
+    a.o_hi = (int)o_hi;
+    a.write_forces = req.forces;
+    a.force = ctx->force.ptr;
+    a.deferred = ctx->deferred.ptr;
+    a.deferred_capacity = P.deferred_capacity;
+    a.flags = flags;
+    a.unit_counter = flags + 12;
+    const int grid = std::max(1, P.nunits < ctx->sm_count ? P.nunits : ctx->sm_count);
+    LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)grid * CQ_NV));
+    a.partials = ctx->partials.ptr;
+    const void* kernel = full ? (const void*)cq_force_kernel<1> : (const void*)cq_force_kernel<0>;
+    const size_t smem = (size_t)CQ_SLOTS * 32;
+    LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ScopedClock clock(ctx, &ctx->clk_pair);
+        lj2_set_flag_kernel<<<1, 1, 0, ctx->stream>>>(flags, 12, 0);
+        void* params[] = {&a};
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(CQ_THREADS), params, smem, ctx->stream));
+        ctx->launches += 2;
+        ctx->clk_pair.launches++;
+    }
+    if (full) {
+        if ((status = launch_reduce(ctx, grid, CQ_NV, RES_E_PAIRS)) != 0) return status;
+    }
+    FixArgs f;
+    f.deferred = ctx->deferred.ptr;
+    f.capacity = P.deferred_capacity;
+    f.frame_atom = ctx->frame_atom.ptr;
+    f.order = ctx->order.ptr;
+    f.pos = ctx->position.ptr;
+    f.charge = ctx->charge.ptr;
+    f.kind = ctx->kind.ptr;
+    f.mol_first = ctx->mol_first.ptr;
+    f.bd_row = ctx->bd_row.ptr;
+    f.bond_dist = ctx->bond_dist.ptr;
+    f.nkinds = ctx->nkinds;
+    f.pairs = ctx->pairs.ptr;
+    f.tables = ctx->tables.ptr;
+    f.table_energy = ctx->table_energy.ptr;
+    f.table_force = ctx->table_force.ptr;
+    f.cell = ctx->cell;
+    f.coulomb = ctx->coulomb;
+    f.do_pairs = do_pairs ? 1 : 0;
+    f.do_coulomb = do_coulomb ? 1 : 0;
+    f.full = full ? 1 : 0;
+    f.write_forces = req.forces ? 1 : 0;
+    f.force = ctx->force.ptr;
+    f.results = ctx->results.ptr;
+    f.flags = flags;
+    list_fixup_kernel<<<8, 128, 0, ctx->stream>>>(f);
     ctx->launches++;
     LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
