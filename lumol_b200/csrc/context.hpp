@@ -207,7 +207,7 @@ struct Context {
     DeviceBuffer<double> frame_pos;            // x | y | z planes, sorted order, positions in the frame of the box
     DeviceBuffer<unsigned short> self_local;   // staged slot of each atom inside its own block
     // pipelined Lennard-Jones path (pairs_lj2.cu): frames with ghost cells, radial levels, deferred cut-off pairs
-    DeviceBuffer<int> ext_start, fidx, kshift, frame_atom;
+    DeviceBuffer<int> ext_start, fidx, kshift, frame_atom, unit_rows;
     DeviceBuffer<unsigned short> cum_levels;
     DeviceBuffer<int2> deferred;
     int deferred_capacity = 0;

@@ -81,7 +81,17 @@ struct UnitShape {
     int width;           // doubles per frame slot: 3 (x, y, z) or 4 (x, y, z, charge)
     int flags;           // bit 0: entries carry the neighbour's kind (2 bits) and a same-molecule bit above 13 bits of slot;
                          // bit 1: the force kernel reads the raw 32-bit columns of the build (no level / bank order pass)
+                         // bit 2: units never cross a row of cells (variable size, unit_start[]): every unit is one segment
 };
+
+constexpr int FLAG_UNITS = 13;  // number of units when they are row-aligned (known on the device only)
+
+// unit of sorted atom s when units are row-aligned
+__device__ __forceinline__ int unit_of_atom(int s, int cell, int nx, int unit_atoms, const int* __restrict__ cell_start,
+                                            const int* __restrict__ row_units) {
+    const int row = cell / nx;
+    return row_units[row] + (s - cell_start[row * nx]) / unit_atoms;
+}
 
 // ------------------------------------------------------------------------------------------------
 // rebuild phases specific to this path
@@ -283,6 +293,7 @@ struct UnitRows {
 struct Table2Args {
     int n, nunits;
     UnitShape shape;
+    const int* __restrict__ unit_start;  // row-aligned units: first atom of every unit (and n behind the last)
     ExtGrid e;
     const int* __restrict__ sorted_cell;
     const int* __restrict__ ext_start;
@@ -300,7 +311,12 @@ __device__ __forceinline__ void unit_table_phase(int vb, const Table2Args& a) {
     const int lane = threadIdx.x & 31;
     const int unit = vb * REBUILD_WARPS + (threadIdx.x >> 5);
     if (unit >= a.nunits) return;
-    const int s_first = unit * a.shape.atoms, s_last = min(a.n, s_first + a.shape.atoms) - 1;
+    int s_first = unit * a.shape.atoms, s_last = min(a.n, s_first + a.shape.atoms) - 1;
+    if (a.shape.flags & 4) {
+        if (unit >= a.flags[FLAG_UNITS]) return;
+        s_first = a.unit_start[unit];
+        s_last = a.unit_start[unit + 1] - 1;
+    }
     const int c_first = a.sorted_cell[s_first], c_last = a.sorted_cell[s_last];
     UnitRows rows;
     rows.init(c_first, c_last - c_first + 1, a.e.nx);
@@ -352,6 +368,7 @@ struct Build2Args {
     GridView g;
     ExtGrid e;
     UnitShape shape;
+    const int* __restrict__ row_units;  // row-aligned units: first unit of every row of cells
     const int* __restrict__ order;  // sorted slot -> state index
     int o_lo, o_hi;                 // state-index range of the atoms this rank owns (first-generation sharding of the charged path)
     int ncells;
@@ -404,7 +421,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
             const int4* runs = a.runs;
             int run_base = 0;
             if (s_i < he) {
-                const int unit = s_i / a.shape.atoms;
+                const int unit = (a.shape.flags & 4) ? unit_of_atom(s_i, c, a.g.nc[0], a.shape.atoms, a.cell_start, a.row_units) : s_i / a.shape.atoms;
                 const int4 header = a.header[unit];
                 staged = header.z >= 0;
                 runs += (size_t)unit * LJ2_MAX_RUNS;
@@ -515,6 +532,8 @@ struct Rebuild2Args {
     ExtGrid e;
     const double* position;
     int *cell_of, *slot_of, *cell_count, *cell_start, *scan_scratch, *grouped, *ext_start, *ext_pad;
+    int *row_pad, *row_units, *unit_start, *row_scratch;  // row-aligned units
+    int nrows, row_scan_blocks;
     Scatter2Args scatter;
     Frame2Args frame;
     Table2Args table;
@@ -613,6 +632,14 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
     }
     // the extended cells only need cell_start: their padded counts are formed alongside
     ext_count_phase(r.e, r.cell_start, r.ext_pad);
+    const bool aligned = (r.table.shape.flags & 4) != 0;
+    if (aligned) {
+        // units per row of cells
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < r.nrows; row += gridDim.x * blockDim.x) {
+            const int atoms = r.cell_start[(row + 1) * r.g.nc[0]] - r.cell_start[row * r.g.nc[0]];
+            r.row_pad[row] = (atoms + r.table.shape.atoms - 1) / r.table.shape.atoms;
+        }
+    }
     grid.sync();
     for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) scatter2_phase(vb, r.scatter, r.flags);
     grid.sync();
@@ -621,11 +648,33 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
     for (int vb = blockIdx.x; vb < r.ext_scan_blocks; vb += gridDim.x) {
         scan_blocks_phase(vb, next, r.ext_pad, r.ext_start, r.scan_scratch, scan_shared);
     }
+    if (aligned) {
+        for (int vb = blockIdx.x; vb < r.row_scan_blocks; vb += gridDim.x) {
+            scan_blocks_phase(vb, r.nrows, r.row_pad, r.row_units, r.row_scratch, scan_shared);
+        }
+    }
     grid.sync();
     if (blockIdx.x == 0) scan_sums_phase(r.ext_scan_blocks, r.scan_scratch, scan_shared);
+    if (aligned && blockIdx.x == (gridDim.x > 1 ? 1 : 0)) scan_sums_phase(r.row_scan_blocks, r.row_scratch, scan_shared);
     grid.sync();
     for (int vb = blockIdx.x; vb < r.ext_scan_blocks; vb += gridDim.x) {
         scan_add_total_phase(vb, next, r.ext_pad, r.ext_start, r.scan_scratch);
+    }
+    if (aligned) {
+        for (int vb = blockIdx.x; vb < r.row_scan_blocks; vb += gridDim.x) {
+            scan_add_total_phase(vb, r.nrows, r.row_pad, r.row_units, r.row_scratch);
+        }
+        grid.sync();
+        // first atom of every unit
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < r.nrows; row += gridDim.x * blockDim.x) {
+            const int first = r.cell_start[row * r.g.nc[0]];
+            const int u0 = r.row_units[row], u1 = r.row_units[row + 1];
+            for (int u = u0; u < u1; u++) r.unit_start[u] = first + (u - u0) * r.table.shape.atoms;
+            if (row == r.nrows - 1) {
+                r.unit_start[u1] = r.n;
+                r.flags[FLAG_UNITS] = u1;
+            }
+        }
     }
     grid.sync();
     for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) frame2_phase(vb, r.frame, r.flags);
@@ -1337,6 +1386,7 @@ struct Lj2Plan {
     ExtGrid e;
     double cutoff, skin, radius, sigma, epsilon, scale, shift;
     int units_per_rank, u_lo, u_hi, s_lo, s_hi;  // units / sorted atoms of this rank
+    int nrows, row_scan_blocks;
     uint64_t signature;
 };
 
@@ -1385,12 +1435,14 @@ static int lj2_plan(Context* ctx, bool sharded, const UnitShape& shape, double c
     P.capacity = (capacity + 7) / 8 * 8;
     P.stride = ((size_t)n + 31) / 32 * 32;
     P.nunits = (n + shape.atoms - 1) / shape.atoms;
+    P.nrows = P.g.nc[1] * P.g.nc[2];
+    if (shape.flags & 4) P.nunits += P.nrows + 1;  // upper bound: the last unit of every row may be partial
     const int nranks = sharded ? ctx->nranks : 1;
     P.units_per_rank = (P.nunits + nranks - 1) / nranks;
     P.u_lo = sharded ? std::min(P.nunits, P.units_per_rank * ctx->rank) : 0;
     P.u_hi = sharded ? std::min(P.nunits, P.u_lo + P.units_per_rank) : P.nunits;
     P.s_lo = std::min(n, P.u_lo * shape.atoms);
-    P.s_hi = std::min(n, P.u_hi * shape.atoms);
+    P.s_hi = (shape.flags & 4) ? n : std::min(n, P.u_hi * shape.atoms);
     // frame slots: the atoms, their ghost images (a boundary atom has up to seven), one slot of padding per extended cell
     const double ghost_ratio = (double)P.next / (double)P.ncells;
     size_t fstride = (size_t)((double)n * (ghost_ratio * 1.5 + 0.25)) + 2 * (size_t)P.next + 64;
@@ -1422,6 +1474,9 @@ static int lj2_plan(Context* ctx, bool sharded, const UnitShape& shape, double c
     P.deferred_capacity = n * DEFERRED_PER_ATOM + 1024;
     ctx->deferred_capacity = P.deferred_capacity;
     LUMOL_CUDA_CHECK(ctx, ctx->deferred.reserve((size_t)P.deferred_capacity));
+    P.row_scan_blocks = (P.nrows + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    // row-aligned units: padded counts, first unit of every row (+ total), scan scratch, first atom of every unit (+ n)
+    LUMOL_CUDA_CHECK(ctx, ctx->unit_rows.reserve(3 * ((size_t)P.nrows + 2) + (size_t)P.row_scan_blocks + 2 + (size_t)P.nunits + 2));
     P.scan_blocks = (P.ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
     P.ext_scan_blocks = (P.next + SCAN_BLOCK - 1) / SCAN_BLOCK;
     LUMOL_CUDA_CHECK(ctx, ctx->scan_scratch.reserve((size_t)(P.scan_blocks > P.ext_scan_blocks ? P.scan_blocks : P.ext_scan_blocks) + 1));
@@ -1505,6 +1560,12 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     r.grouped = grouped;
     r.ext_start = ctx->ext_start.ptr;
     r.ext_pad = ctx->ext_start.ptr + P.next + 2;
+    r.nrows = P.nrows;
+    r.row_scan_blocks = P.row_scan_blocks;
+    r.row_pad = ctx->unit_rows.ptr;
+    r.row_units = r.row_pad + P.nrows + 2;
+    r.row_scratch = r.row_units + P.nrows + 2;
+    r.unit_start = r.row_scratch + P.row_scan_blocks + 2;
     r.scatter.n = n;
     r.scatter.g = P.g;
     r.scatter.pos = state;
@@ -1538,6 +1599,7 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     r.table.n = n;
     r.table.nunits = P.nunits;
     r.table.shape = P.shape;
+    r.table.unit_start = r.unit_start;
     r.table.e = P.e;
     r.table.sorted_cell = ctx->sorted_cell.ptr;
     r.table.ext_start = ctx->ext_start.ptr;
@@ -1550,6 +1612,7 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     b.g = P.g;
     b.e = P.e;
     b.shape = P.shape;
+    b.row_units = r.row_units;
     b.order = order;
     b.o_lo = owner_lo;
     b.o_hi = owner_hi;
@@ -2229,7 +2292,8 @@ struct CqClass {
 };
 
 struct CqArgs {
-    int n, nunits, capacity;
+    int n, capacity;
+    const int* __restrict__ unit_start;  // first atom of every unit (row-aligned units)
     const unsigned* __restrict__ nlist;
     const int* __restrict__ ncount;
     const unsigned short* __restrict__ self_slot;
@@ -2243,6 +2307,7 @@ struct CqArgs {
     int coulomb_kind;        // 0 none, 1 Ewald, 2 Wolf
     int exclude_same;        // the coulomb restriction is InterMolecular
     int coulomb_band_lo;
+    int top_cap;             // top 32 bits of the largest argument of the erfc / exp approximations
     double alpha, gauss, wolf_energy, wolf_force;  // gauss = alpha 2 / sqrt(pi)
     int o_lo, o_hi;          // state-index range owned by this rank
     int write_forces;
@@ -2262,6 +2327,8 @@ __device__ __forceinline__ double cq_exp(double a) {
     const double kd = shifted - magic;
     double r = fma(kd, -6.93147180369123816490e-01, a);
     r = fma(kd, -1.90821492927058770002e-10, r);
+    // Horner: Estrin's scheme (shorter dependent chains, three more multiplications) was slower, 0.375 against 0.355 ms on the
+    // 98k-atom SPC/E box: the FP64 pipe, not the chain latency, is the limit
     double p = 1.0 / 479001600.0;
     p = fma(p, r, 1.0 / 39916800.0);
     p = fma(p, r, 1.0 / 3628800.0);
@@ -2327,7 +2394,10 @@ __device__ __forceinline__ void cq_pair(const CqArgs& a, const CqAtom& me, doubl
     const bool wolf_skip = a.coulomb_kind == 2 && same && a.exclude_same;
     qq = (inside_coulomb && !wolf_skip) ? qq : 0.0;
     const double excluded = (a.coulomb_kind == 1 && same && a.exclude_same) ? 1.0 : 0.0;
-    const double x = fmin(a.alpha * r, CQ_XMAX);
+    // alpha r capped (integer minimum on the top word) to the range of the erfc / exp approximations: only pairs outside the
+    // coulomb cut-off (qq = 0), e.g. the far-away slot that padding entries point at, are affected
+    const double x_true = a.alpha * r;
+    const double x = __hiloint2double(min(__double2hiint(x_true), a.top_cap), __double2loint(x_true));
     const double t = cq_exp(-(x * x));
     const double eor = fma(t, cq_erfcx(x), -excluded) * rinv;  // (erfc(alpha r) - excluded) / r
     fr += qq * fma(rinv2, fma(a.gauss, t, eor), -a.wolf_force * rinv);
@@ -2381,9 +2451,10 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cq_force_kernel(CqArgs a) {
     const int local = tid / CQ_LPA, half = tid % CQ_LPA;
     unsigned phase = 0;
 
+    const int nunits = a.flags[FLAG_UNITS];
     for (int unit = blockIdx.x;; ) {
         __syncthreads();  // everybody is done with the previous copy (and, the first time, the barrier is initialised)
-        if (unit >= a.nunits) break;
+        if (unit >= nunits) break;
         const int4 header = a.header[unit];
         const bool staged = header.z >= 0;
         if (tid < 32) {
@@ -2400,8 +2471,8 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cq_force_kernel(CqArgs a) {
             if (lane == 0) next_unit = atomicAdd(a.unit_counter, 1) + (int)gridDim.x;
         }
         // the thread's atom, while the copies are in flight
-        const int s = unit * CQ_ATOMS + local;
-        const bool present = s < a.n;
+        const int s = a.unit_start[unit] + local;
+        const bool present = s < a.unit_start[unit + 1];
         int count = 0, origin = -1, tag = 0;
         unsigned self = 0;
         if (present) {
@@ -2430,6 +2501,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cq_force_kernel(CqArgs a) {
             for (int w = 0; w < nwords; w++) {
                 uint4 wafter = make_uint4(0, 0, 0, 0);
                 if (w + 2 < nwords) wafter = words[(size_t)(w + 2) * 64];
+                if (w + 10 < nwords) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + (size_t)(w + 10) * 64));
                 const unsigned entries[4] = {wcur.x & 0xffffu, wcur.y & 0xffffu, wcur.z & 0xffffu, wcur.w & 0xffffu};
                 unsigned near = 0;
 #pragma unroll
@@ -2630,7 +2702,7 @@ int launch_pairs_cq(Context* ctx, const ComputeRequest& req) {
     shape.slots = CQ_SLOTS;
     shape.value_factor = 1;
     shape.width = 4;
-    shape.flags = 3;
+    shape.flags = 7;
     double cutoff = ctx->any_pair ? ctx->max_pair_cutoff : 0.0;
     if (ctx->coulomb.rc > cutoff) cutoff = ctx->coulomb.rc;
     Lj2Plan P;
@@ -2665,8 +2737,8 @@ int launch_pairs_cq(Context* ctx, const ComputeRequest& req) {
     const bool full = req.energy || req.virial;
     CqArgs a;
     a.n = P.n;
-    a.nunits = P.nunits;
     a.capacity = P.capacity;
+    a.unit_start = ctx->unit_rows.ptr + 2 * ((size_t)P.nrows + 2) + (size_t)P.row_scan_blocks + 2;
     a.nlist = ctx->nlist.ptr;
     a.ncount = ctx->ncount.ptr;
     a.self_slot = ctx->self_local.ptr;
@@ -2696,6 +2768,12 @@ int launch_pairs_cq(Context* ctx, const ComputeRequest& req) {
     a.exclude_same = ctx->coulomb.restriction == LUMOL_CUDA_RESTRICTION_INTER_MOLECULAR ? 1 : 0;
     a.coulomb_band_lo = do_coulomb ? band_below(ctx->coulomb.rc) : INT_MIN;
     a.alpha = ctx->coulomb.alpha;
+    {
+        const double cap = 0.9999 * CQ_XMAX;
+        uint64_t pattern;
+        std::memcpy(&pattern, &cap, sizeof(pattern));
+        a.top_cap = (int)(pattern >> 32);
+    }
     a.gauss = ctx->coulomb.alpha * FRAC_2_SQRT_PI;
     a.wolf_energy = ctx->coulomb.kind == 2 ? ctx->coulomb.wolf_energy_constant : 0.0;
     a.wolf_force = ctx->coulomb.kind == 2 ? ctx->coulomb.wolf_force_constant : 0.0;
@@ -2707,7 +2785,7 @@ int launch_pairs_cq(Context* ctx, const ComputeRequest& req) {
     a.deferred_capacity = P.deferred_capacity;
     a.flags = flags;
     a.unit_counter = flags + 12;
-    const int grid = std::max(1, P.nunits < ctx->sm_count ? P.nunits : ctx->sm_count);
+    const int grid = std::max(1, (P.n + CQ_ATOMS - 1) / CQ_ATOMS < ctx->sm_count ? (P.n + CQ_ATOMS - 1) / CQ_ATOMS : ctx->sm_count);
     LUMOL_CUDA_CHECK(ctx, ctx->partials.reserve((size_t)grid * CQ_NV));
     a.partials = ctx->partials.ptr;
     const void* kernel = full ? (const void*)cq_force_kernel<1> : (const void*)cq_force_kernel<0>;

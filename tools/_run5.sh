@@ -1,7 +1,7 @@
 cd $GRAFT_REPO_ROOT
 timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_parity.py tests/test_gpu_md.py tests/test_gpu_mc.py -q -m gpu 2>&1 | tail -15
 timeout 600 python bench.py --workload spce --lattice 32 --no-cpu-baseline --no-e2e --steps 40 --warmup 5 > gpurun_out/spce_cq.json 2> gpurun_out/spce_cq.err; tail -3 gpurun_out/spce_cq.err
-LUMOL_CUDA_CQ=0 timeout 600 python bench.py --workload spce --lattice 32 --no-cpu-baseline --no-e2e --steps 40 --warmup 5 > gpurun_out/spce_v1.json 2> gpurun_out/spce_v1.err
+
 python - <<'PY'
 import json
 for name in ("spce_cq","spce_v1"):
