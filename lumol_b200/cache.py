@@ -77,7 +77,11 @@ class EnergyCache:
         accepts the first one unless ``accept(trial)`` chose another."""
         # structure, cell and coulomb settings are re-checked (and re-uploaded if they changed); the positions
         # resident on the device -- those of ``init`` plus every accepted move -- are kept
-        device = device_for(system, positions=system._device is None)
+        # ... except after move_all_molecules_cost: that call left its TRIAL configuration on the device (the reference
+        # evaluates it on the same, temporarily modified System and swaps back on rejection), so the host positions, which
+        # are the truth whether the trial was accepted or rejected, are uploaded again
+        device = device_for(system, positions=system._device is None or getattr(self, "_trial_resident", False))
+        self._trial_resident = False
         ids = np.ascontiguousarray(molecule_ids, dtype=np.int64)
         for molecule_id, positions in zip(ids, new_positions):
             bonding = system.molecule(int(molecule_id))
@@ -109,6 +113,7 @@ class EnergyCache:
         Everything is re-evaluated, as in the reference ("temporarily, recompute all interactions"); the pair sum
         includes the intra-molecular pairs, which a rigid move leaves unchanged."""
         terms = device_for(system).compute(energy=True, parts=_ffi.PART_PAIRS | _ffi.PART_COULOMB).energy
+        self._trial_resident = True  # the device now holds the trial positions and cell, not necessarily the accepted state
         pairs, pairs_tail = terms.pairs, terms.pairs_tail
         coulomb = terms.coulomb_real + terms.coulomb_self + terms.coulomb_kspace
         cost = (pairs - self.pairs) + (pairs_tail - self.pairs_tail) + (coulomb - self.coulomb)

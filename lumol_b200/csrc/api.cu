@@ -1141,7 +1141,10 @@ int barostat_step(Context* c) {
     }
     // system.pressure() / system.stress() and system.forces() at the new positions: one device pass
     double virial[9];
-    status = lumol_cuda_compute(handle, LUMOL_CUDA_FORCES | LUMOL_CUDA_ATOMIC_VIRIAL, LUMOL_CUDA_PART_PAIRS | LUMOL_CUDA_PART_BONDED | LUMOL_CUDA_PART_COULOMB,
+    // system.pressure() / stress() use `Virial`, which is the molecular virial when the simulated degrees of freedom are
+    // molecules (compute.rs:372-391)
+    const uint32_t which = c->dof_mode == LUMOL_CUDA_DOF_MOLECULES ? LUMOL_CUDA_MOLECULAR_VIRIAL : LUMOL_CUDA_ATOMIC_VIRIAL;
+    status = lumol_cuda_compute(handle, LUMOL_CUDA_FORCES | which, LUMOL_CUDA_PART_PAIRS | LUMOL_CUDA_PART_BONDED | LUMOL_CUDA_PART_COULOMB,
                                 nullptr, nullptr, virial);
     if (status) return status;
     const double volume = volume_of(c->cell);

@@ -211,11 +211,12 @@ struct Context {
     DeviceBuffer<unsigned short> cum_levels;
     DeviceBuffer<int2> deferred;
     int deferred_capacity = 0;
-    int rebuild2_grid = 0;
+    int rebuild2_grid = 0, rebuild2_grid_flags = 0;
     bool lj2_active = false;  // the current neighbour list was built by pairs_lj2.cu
     // sorted-resident molecular dynamics (pairs_lj2.cu): state in cell order, ownership by units, halo frames pushed to peers
     DeviceBuffer<double> sre_x, sre_v, sre_f, sre_m, sre_tmp;
     DeviceBuffer<int> sre_origin, sre_need_mask, sre_sync;
+    DeviceBuffer<int4> sre_halo_items;
 
     // ---- reductions ------------------------------------------------------------------------------
     DeviceBuffer<double> partials, reduce_scratch;

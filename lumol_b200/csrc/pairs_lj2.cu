@@ -85,6 +85,7 @@ struct UnitShape {
 };
 
 constexpr int FLAG_UNITS = 13;  // number of units when they are row-aligned (known on the device only)
+constexpr int FLAG_HALO_ITEMS = 14;  // sharded runs: number of (cell image, peers) runs the halo kernel copies
 
 // unit of sorted atom s when units are row-aligned
 __device__ __forceinline__ int unit_of_atom(int s, int cell, int nx, int unit_atoms, const int* __restrict__ cell_start,
@@ -394,6 +395,7 @@ constexpr int BUILD2_CHUNKS = 8;
 // One warp per 32-atom chunk of a home cell, one lane per atom; the 27 neighbour cells are streamed, eight candidates
 // (uniform addresses) loaded before the first is tested.  Survivors are collected in a per-lane shared-memory buffer and
 // written as whole 16-byte words (four entries).
+template <int FLAGS>
 __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, const float (*offset32)[3], unsigned (*pending)[4]) {
     const int lane = threadIdx.x & 31;
     const int global_warp = vb * REBUILD_WARPS + (threadIdx.x >> 5);
@@ -421,7 +423,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
             const int4* runs = a.runs;
             int run_base = 0;
             if (s_i < he) {
-                const int unit = (a.shape.flags & 4) ? unit_of_atom(s_i, c, a.g.nc[0], a.shape.atoms, a.cell_start, a.row_units) : s_i / a.shape.atoms;
+                const int unit = (FLAGS & 4) ? unit_of_atom(s_i, c, a.g.nc[0], a.shape.atoms, a.cell_start, a.row_units) : s_i / a.shape.atoms;
                 const int4 header = a.header[unit];
                 staged = header.z >= 0;
                 runs += (size_t)unit * LJ2_MAX_RUNS;
@@ -476,6 +478,9 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                     const int frame_first = 2 + a.ext_start[a.e.index(cx + dx, uy + 1, uz + 1)];  // unwrapped: the image seen from here
                     const int tag = (staged ? run.z + (frame_first - run.x) : frame_first) - s0;
                     const int factor = staged ? a.shape.value_factor : 1;
+                    // eight candidates per round, loaded before the first one is tested (uniform addresses: one broadcast each).  A
+                    // variant that tested the eight branch-free into a bit mask and sent only the survivors through the divergent
+                    // part (re-loading them) was slower: 2.72 against 2.23 ms for the 1M-atom box
                     for (int first = s0; first < s1; first += 8) {
                         float4 f[8];
 #pragma unroll
@@ -490,7 +495,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                                     int level = (int)floorf((sqrtf(r2) - a.cutoff) * a.inv_delta);
                                     level = max(0, min(LJ2_LEVELS - 1, level));
                                     unsigned value = (unsigned)(factor * (tag + s_j));
-                                    if (a.shape.flags & 1) {
+                                    if (FLAGS & 1) {
                                         // neighbour's kind and "same molecule" above the slot (13 bits) or the frame index (25 bits)
                                         const int tag_j = __float_as_int(f[u].w);
                                         const unsigned bits = (unsigned)(tag_j & 3) | ((tag_j >> 2) == (tag_i >> 2) ? 4u : 0u);
@@ -549,6 +554,10 @@ struct Rebuild2Args {
         int nranks;
         const int* gathered;         // sharded: gathered[rank] == epoch once that rank's state has arrived here
     } sorted;
+    // sharded runs (need_mask set): this rank, and where to put the (first double, doubles, peers) of every frame run of its
+    // atoms that another rank stages
+    int halo_rank;
+    int4* halo_items;
 };
 
 // velocities, masses and origins of the atoms into scratch, in the new order ...
@@ -576,7 +585,8 @@ __device__ __forceinline__ void sorted_commit_phase(int vb, int n, const double*
     a.origin[s] = a.tmp_origin[s];
 }
 
-__global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args r) {
+template <int FLAGS>
+__global__ void __launch_bounds__(REBUILD_THREADS, 3) rebuild2_kernel(Rebuild2Args r) {
     if (r.flags[FLAG_REBUILD] != r.epoch) return;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     if (r.sorted.active && r.sorted.nranks > 1) {
@@ -607,7 +617,10 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
     const int atom_blocks = (r.n + REBUILD_THREADS - 1) / REBUILD_THREADS;
 
     cell_zero_phase(r.ncells + 1, r.cell_count, r.build.cell_needed, r.flags);
-    if (blockIdx.x == 0 && threadIdx.x == 0) r.flags[FLAG_FRAME_OVERFLOW] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        r.flags[FLAG_FRAME_OVERFLOW] = 0;
+        r.flags[FLAG_HALO_ITEMS] = 0;
+    }
     if (r.table.need_mask != nullptr) {
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < r.ncells; k += gridDim.x * blockDim.x) r.table.need_mask[k] = 0;
     }
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
     }
     // the extended cells only need cell_start: their padded counts are formed alongside
     ext_count_phase(r.e, r.cell_start, r.ext_pad);
-    const bool aligned = (r.table.shape.flags & 4) != 0;
+    const bool aligned = (FLAGS & 4) != 0;
     if (aligned) {
         // units per row of cells
         for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < r.nrows; row += gridDim.x * blockDim.x) {
@@ -686,8 +699,33 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
     if (r.sorted.active) {
         for (int vb = blockIdx.x; vb < atom_blocks; vb += gridDim.x) sorted_commit_phase(vb, r.n, r.scatter.xref, r.sorted);
     }
+    if (r.table.need_mask != nullptr && r.halo_items != nullptr && r.build.s_hi > r.build.s_lo) {
+        // the frame runs of this rank's atoms (every image of every cell they sit in) that other ranks stage: what the halo
+        // kernel copies after every kick-drift
+        const int c_lo = r.scatter.sorted_cell[r.build.s_lo];
+        const int ncells = r.scatter.sorted_cell[r.build.s_hi - 1] - c_lo + 1;
+        for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < 8 * ncells; item += gridDim.x * blockDim.x) {
+            const int cell = c_lo + (item >> 3), m = item & 7;
+            const unsigned targets = (unsigned)r.table.need_mask[cell] & ~(1u << r.halo_rank);
+            if (targets == 0u) continue;
+            const int first = r.cell_start[cell], end = r.cell_start[cell + 1];
+            const int lo = max(first, r.build.s_lo), hi = min(end, r.build.s_hi);
+            if (lo >= hi) continue;
+            const int x = cell % r.e.nx, y = (cell / r.e.nx) % r.e.ny, z = cell / (r.e.nx * r.e.ny);
+            const int gx = x == 0 ? 1 : (x == r.e.nx - 1 ? -1 : 0);
+            const int gy = y == 0 ? 1 : (y == r.e.ny - 1 ? -1 : 0);
+            const int gz = z == 0 ? 1 : (z == r.e.nz - 1 ? -1 : 0);
+            if (((m & 1) && gx == 0) || ((m & 2) && gy == 0) || ((m & 4) && gz == 0)) continue;
+            const int sx = (m & 1) ? gx : 0, sy = (m & 2) ? gy : 0, sz = (m & 4) ? gz : 0;
+            const int X = sx > 0 ? r.e.ex - 1 : (sx < 0 ? 0 : x + 1);
+            const int Y = sy > 0 ? r.e.ey - 1 : (sy < 0 ? 0 : y + 1);
+            const int Z = sz > 0 ? r.e.ez - 1 : (sz < 0 ? 0 : z + 1);
+            const int begin = 3 * (2 + r.ext_start[r.e.index(X, Y, Z)] + (lo - first));
+            r.halo_items[atomicAdd(r.flags + FLAG_HALO_ITEMS, 1)] = make_int4(begin, 3 * (hi - lo), (int)targets, 0);
+        }
+    }
     for (int vb = blockIdx.x; vb * REBUILD_WARPS * r.build.cells_per_warp < r.ncells * BUILD2_CHUNKS; vb += gridDim.x) {
-        list_build2_phase(vb, r.build, offset32, pending);
+        list_build2_phase<FLAGS>(vb, r.build, offset32, pending);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         r.flags[FLAG_COUNT] += 1;
@@ -710,39 +748,59 @@ __global__ void __launch_bounds__(REBUILD_THREADS) rebuild2_kernel(Rebuild2Args 
 
 constexpr int REORDER2_THREADS = 32;
 
+// COUNTER: unsigned char while a column holds at most 255 entries (more resident warps: the kernel is a chain of dependent
+// shared-memory accesses), unsigned short otherwise.  Columns of units that could not be staged keep the order of the
+// build (their 32-bit entries only lose the level bits; every level counts as walked).
+template <typename COUNTER>
 __global__ void __launch_bounds__(REORDER2_THREADS)
     list_reorder2_kernel(UnitShape shape, int s_lo, int n, int capacity, const int4* __restrict__ header, const int* __restrict__ ncount,
                          unsigned* __restrict__ nlist, unsigned short* __restrict__ cum_levels, int epoch,
                          const int* __restrict__ flags) {
     if (flags[FLAG_REBUILD] != epoch || flags[FLAG_NONFINITE] != 0) return;
-    extern __shared__ unsigned reorder2_smem[];
-    unsigned* sorted = reorder2_smem;  // entry p of thread t at [p * 32 + t], grouped by (level, residue)
-    __shared__ unsigned short cursor[LJ2_LEVELS * 16][REORDER2_THREADS], last[LJ2_LEVELS * 16][REORDER2_THREADS];
+    extern __shared__ unsigned short reorder2_smem[];
+    unsigned short* sorted = reorder2_smem;  // entry p of thread t at [p * 32 + t], grouped by (level, residue)
+    // buckets: the sixteen bank residues of level 0 (four fifths of the entries: the only ones walked at every evaluation
+    // get the bank-aware order), then one bucket per further level
+    constexpr int BUCKETS = 16 + LJ2_LEVELS - 1;
+    __shared__ COUNTER cursor[BUCKETS][REORDER2_THREADS], last[BUCKETS][REORDER2_THREADS];
+    auto bucket_of = [](unsigned entry) { return (entry >> 28) == 0u ? (int)(entry & 15u) : 15 + (int)(entry >> 28); };
     const int t = threadIdx.x;
+    const int word_stride = shape.lanes_per_atom / 2;
     // columns [s_lo, n): the atoms of this rank (s_lo is a multiple of the unit size)
     for (int slab = s_lo / REORDER2_THREADS + blockIdx.x; slab * REORDER2_THREADS < n; slab += gridDim.x) {
         const int s_i = slab * REORDER2_THREADS + t;
         if (s_i >= n) continue;
         const bool staged = header[s_i / shape.atoms].z >= 0;
         const int count = ncount[s_i];
-        const int word_stride = shape.lanes_per_atom / 2;
         uint4* words = reinterpret_cast<uint4*>(nlist) + (size_t)(s_i >> 5) * (capacity >> 2) * 32 + (s_i & 31);
         const int nwords = (count + 3) >> 2;
-        for (int b = 0; b < LJ2_LEVELS * 16; b++) last[b][t] = 0;
+        if (!staged) {
+            for (int w = 0; w < nwords; w++) {
+                uint4 word = words[w * 32];
+                word.x &= RAW_VALUE_MASK;
+                word.y &= RAW_VALUE_MASK;
+                word.z &= RAW_VALUE_MASK;
+                word.w &= RAW_VALUE_MASK;
+                words[w * 32] = word;
+            }
+            for (int level = 0; level < LJ2_LEVELS; level++) cum_levels[(size_t)s_i * LJ2_LEVELS + level] = (unsigned short)count;
+            continue;
+        }
+        for (int b = 0; b < BUCKETS; b++) last[b][t] = 0;
         for (int w = 0; w < nwords; w++) {
             const uint4 word = words[w * 32];
             const unsigned e[4] = {word.x, word.y, word.z, word.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if (4 * w + q < count) last[(e[q] >> 28) * 16 + (staged ? (e[q] & 15u) : 0u)][t]++;
+                if (4 * w + q < count) last[bucket_of(e[q])][t]++;
             }
         }
         int running = 0;
-        for (int b = 0; b < LJ2_LEVELS * 16; b++) {
-            cursor[b][t] = (unsigned short)running;
+        for (int b = 0; b < BUCKETS; b++) {
+            cursor[b][t] = (COUNTER)running;
             running += last[b][t];
-            last[b][t] = (unsigned short)running;
-            if ((b & 15) == 15) cum_levels[(size_t)s_i * LJ2_LEVELS + (b >> 4)] = (unsigned short)running;
+            last[b][t] = (COUNTER)running;
+            if (b >= 15) cum_levels[(size_t)s_i * LJ2_LEVELS + (b - 15)] = (unsigned short)running;
         }
         for (int w = 0; w < nwords; w++) {
             const uint4 word = words[w * 32];
@@ -750,48 +808,36 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (4 * w + q < count) {
-                    const int position = cursor[(e[q] >> 28) * 16 + (staged ? (e[q] & 15u) : 0u)][t]++;
-                    sorted[position * REORDER2_THREADS + t] = e[q] & RAW_VALUE_MASK;
+                    const int position = cursor[bucket_of(e[q])][t]++;
+                    sorted[position * REORDER2_THREADS + t] = (unsigned short)(e[q] & 0xffffu);
                 }
             }
         }
-        // rewind
+        // rewind the residue buckets of level 0
         running = 0;
-        for (int b = 0; b < LJ2_LEVELS * 16; b++) {
-            cursor[b][t] = (unsigned short)running;
+        unsigned nonempty = 0;  // residue buckets of level 0 that still hold entries
+        for (int b = 0; b < 16; b++) {
+            cursor[b][t] = (COUNTER)running;
+            nonempty |= running != (int)last[b][t] ? 1u << b : 0u;
             running = last[b][t];
         }
-        if (!staged) {
-            // frame indices, four per word, in level order; padding points at the dummy frame slot 0
-            for (int w = 0; w < nwords; w++) {
-                unsigned e[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) e[q] = 4 * w + q < count ? sorted[(4 * w + q) * REORDER2_THREADS + t] : 0u;
-                words[w * 32] = make_uint4(e[0], e[1], e[2], e[3]);
-            }
-            continue;
-        }
+        const int level0 = running;
         const int lane_base = shape.lanes_per_atom * (s_i & (16 / shape.lanes_per_atom - 1));
         unsigned packed[4] = {0u, 0u, 0u, 0u};
-        int level = -1, level_end = 0;
-        unsigned nonempty = 0;  // buckets of the current level that still hold entries
         for (int p = 0; p < count; p++) {
-            while (p >= level_end) {
-                level++;
-                level_end = level == LJ2_LEVELS - 1 ? count : (int)last[level * 16 + 15][t];
-                nonempty = 0;
-                for (int b = 0; b < 16; b++) nonempty |= cursor[level * 16 + b][t] != last[level * 16 + b][t] ? 1u << b : 0u;
+            int position = p;  // further levels: the order of the counting sort
+            if (p < level0) {
+                // entry p sits in word p >> 3, half (p >> 2) & 1; with four lanes per atom, lanes {0, 1} walk the even words
+                // and {2, 3} the odd ones
+                const int word = p >> 3;
+                const int h = ((word % word_stride) << 1) | ((p >> 2) & 1), step = ((word / word_stride) << 2) | (p & 3);
+                const int want = (lane_base + h + step) & 15;
+                // first non-empty bucket at or after `want`, cyclically
+                const unsigned rotated = ((nonempty >> want) | (nonempty << (16 - want))) & 0xffffu;
+                const int b = (want + __ffs(rotated) - 1) & 15;
+                position = cursor[b][t]++;
+                if (position + 1 == (int)last[b][t]) nonempty &= ~(1u << b);
             }
-            // entry p sits in word p >> 3, half (p >> 2) & 1; with four lanes per atom, lanes {0, 1} walk the even words and
-            // {2, 3} the odd ones
-            const int word = p >> 3;
-            const int h = ((word % word_stride) << 1) | ((p >> 2) & 1), step = ((word / word_stride) << 2) | (p & 3);
-            const int want = (lane_base + h + step) & 15;
-            // first non-empty bucket at or after `want`, cyclically
-            const unsigned rotated = ((nonempty >> want) | (nonempty << (16 - want))) & 0xffffu;
-            const int b = (want + __ffs(rotated) - 1) & 15;
-            const int position = cursor[level * 16 + b][t]++;
-            if (position + 1 == (int)last[level * 16 + b][t]) nonempty &= ~(1u << b);
             const unsigned slot = sorted[position * REORDER2_THREADS + t];
             packed[(p & 7) >> 1] |= slot << (16 * (p & 1));
             if ((p & 7) == 7) {
@@ -1636,32 +1682,46 @@ static int lj2_launch_rebuild(Context* ctx, const Lj2Plan& P, int epoch, const d
     b.flags = flags;
     r.flags = flags;
     r.sorted = sorted;
-    if (ctx->rebuild2_grid == 0) {
+    r.halo_rank = ctx->rank;
+    r.halo_items = need_mask != nullptr ? ctx->sre_halo_items.ptr : nullptr;
+    const void* rebuild = P.shape.flags == 0 ? (const void*)rebuild2_kernel<0> : (const void*)rebuild2_kernel<7>;
+    int& grid = P.shape.flags == 0 ? ctx->rebuild2_grid : ctx->rebuild2_grid_flags;
+    if (grid == 0) {
         int per_sm = 0;
-        LUMOL_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rebuild2_kernel, REBUILD_THREADS, 0));
+        LUMOL_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rebuild, REBUILD_THREADS, 0));
         if (per_sm < 1) return ctx->fail(LUMOL_CUDA_ERROR_CUDA, "the rebuild kernel does not fit on the device");
-        ctx->rebuild2_grid = per_sm * ctx->sm_count;
+        grid = per_sm * ctx->sm_count;
     }
     {
         void* params[] = {&r};
-        LUMOL_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)rebuild2_kernel, dim3(ctx->rebuild2_grid),
-                                                          dim3(REBUILD_THREADS), params, 0, ctx->stream));
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel(rebuild, dim3(grid), dim3(REBUILD_THREADS), params, 0, ctx->stream));
     }
     ctx->launches++;
     ctx->clk_neighbor.launches++;
-    const size_t reorder_smem = (P.shape.flags & 2) ? 0 : (size_t)P.capacity * REORDER2_THREADS * sizeof(unsigned);
-    if (reorder_smem > 190 * 1024) {
+    if (P.shape.flags & 2) return 0;  // raw columns
+    const size_t reorder_smem = (size_t)P.capacity * REORDER2_THREADS * sizeof(unsigned short);
+    if (reorder_smem > 190 * 1024 || P.capacity > 65535) {
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "neighbour list columns of %d entries do not fit the reorder kernel", P.capacity);
     }
+    const bool narrow = P.capacity <= 255;
+    const void* reorder = narrow ? (const void*)list_reorder2_kernel<unsigned char> : (const void*)list_reorder2_kernel<unsigned short>;
     if (reorder_smem > 16 * 1024) {
-        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(list_reorder2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)reorder_smem));
+        LUMOL_CUDA_CHECK(ctx, cudaFuncSetAttribute(reorder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reorder_smem));
     }
-    if (P.shape.flags & 2) return 0;  // raw columns
     const int slabs = (P.s_hi - P.s_lo + REORDER2_THREADS - 1) / REORDER2_THREADS;
-    const int reorder_grid = std::max(1, slabs < ctx->sm_count * 8 ? slabs : ctx->sm_count * 8);
-    list_reorder2_kernel<<<reorder_grid, REORDER2_THREADS, reorder_smem, ctx->stream>>>(
-        P.shape, P.s_lo, P.s_hi, P.capacity, ctx->blk_header.ptr, ctx->ncount.ptr, ctx->nlist.ptr, ctx->cum_levels.ptr, epoch, flags);
+    const int reorder_grid = std::max(1, slabs < ctx->sm_count * 16 ? slabs : ctx->sm_count * 16);
+    {
+        UnitShape shape = P.shape;
+        int s_lo = P.s_lo, s_hi = P.s_hi, capacity = P.capacity;
+        const int4* header = ctx->blk_header.ptr;
+        const int* ncount = ctx->ncount.ptr;
+        unsigned* nlist = ctx->nlist.ptr;
+        unsigned short* cum = ctx->cum_levels.ptr;
+        int epoch_value = epoch;
+        const int* flag_pointer = flags;
+        void* params[] = {&shape, &s_lo, &s_hi, &capacity, &header, &ncount, &nlist, &cum, &epoch_value, &flag_pointer};
+        LUMOL_CUDA_CHECK(ctx, cudaLaunchKernel(reorder, dim3(reorder_grid), dim3(REORDER2_THREADS), params, reorder_smem, ctx->stream));
+    }
     ctx->launches++;
     ctx->clk_neighbor.launches++;
     LUMOL_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1842,7 +1902,6 @@ constexpr int SRE_ATOMS = SRE_THREADS;
 template <bool MERGED>
 __global__ void __launch_bounds__(SRE_THREADS) sre_kick_drift_kernel(SreArgs a) {
     __shared__ float block_max[SRE_THREADS / 32];
-    __shared__ bool last_block;
     const int s = a.s_lo + blockIdx.x * SRE_ATOMS + threadIdx.x;
     int* local = a.sync[a.rank];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1876,18 +1935,12 @@ __global__ void __launch_bounds__(SRE_THREADS) sre_kick_drift_kernel(SreArgs a) 
         const double z = p[2] - (double)kz * a.g.length[2];
         const int cell = a.sorted_cell[s];
         const int rank_in_cell = s - a.cell_start[cell];
-        const unsigned targets = a.nranks == 1 ? 1u : ((unsigned)a.need_mask[cell] | (1u << a.rank));
+        // the frames of this rank; the halo kernel below copies what the other ranks stage
+        double* frame = a.frame[a.rank];
         for_each_image(a.e, a.ext_start, cell, rank_in_cell, [&](int f, int sx, int sy, int sz) {
-            const double fx = (x + (double)sx * a.g.length[0]) * a.scale;
-            const double fy = (y + (double)sy * a.g.length[1]) * a.scale;
-            const double fz = (z + (double)sz * a.g.length[2]) * a.scale;
-            for (int r = 0; r < a.nranks; r++) {
-                if (!(targets & (1u << r))) continue;
-                double* frame = a.frame[r];
-                frame[3 * (size_t)f] = fx;
-                frame[3 * (size_t)f + 1] = fy;
-                frame[3 * (size_t)f + 2] = fz;
-            }
+            frame[3 * (size_t)f] = (x + (double)sx * a.g.length[0]) * a.scale;
+            frame[3 * (size_t)f + 1] = (y + (double)sy * a.g.length[1]) * a.scale;
+            frame[3 * (size_t)f + 2] = (z + (double)sz * a.g.length[2]) * a.scale;
         });
     }
 #pragma unroll
@@ -1902,20 +1955,51 @@ __global__ void __launch_bounds__(SRE_THREADS) sre_kick_drift_kernel(SreArgs a) 
         }
         return;
     }
-    // sharded: the peer stores of the whole block (ordered before thread 0 by the barrier above; the fence is cumulative)
-    // are visible system-wide before the block's ticket is taken; the last block publishes
+    // sharded: this rank's running maximum; the halo kernel publishes it with the frames
     if (threadIdx.x == 0) {
         float m = block_max[0];
         for (int w = 1; w < SRE_THREADS / 32; w++) m = fmaxf(m, block_max[w]);
         atomicMax(local + SYNC_LOCAL + a.parity, __float_as_int(m));
-        __threadfence_system();
+    }
+}
+
+// Sharded: the new frame positions of this rank's atoms (ghost images included) into the frames of the ranks that stage
+// them.  One warp per owned cell and image: a cell's atoms are contiguous in the frames, so the peer stores are runs of
+// consecutive doubles (per-atom stores from the kick-drift kernel took 28 us for 0.5 M atoms on two ranks).  The last
+// block publishes, on every rank, this rank's largest squared displacement and its arrival stamp.
+struct SreHaloArgs {
+    const int4* __restrict__ items;  // (first double, doubles, peers): built at the rebuild
+    const int* __restrict__ flags;
+    int epoch, parity, nranks, rank;
+    double* frame[PEER_MAX_RANKS];
+    int* sync[PEER_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(SRE_THREADS) sre_halo_kernel(SreHaloArgs a) {
+    __shared__ bool last_block;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (SRE_THREADS / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (SRE_THREADS / 32);
+    const double* mine = a.frame[a.rank];
+    const int nitems = a.flags[FLAG_HALO_ITEMS];
+    for (int item = warp; item < nitems; item += nwarps) {
+        const int4 run = a.items[item];
+        for (int r = 0; r < a.nranks; r++) {
+            if (!(run.z & (1 << r))) continue;
+            double* peer = a.frame[r];
+            for (int k = lane; k < run.y; k += 32) peer[(size_t)run.x + k] = mine[(size_t)run.x + k];
+        }
+    }
+    __syncthreads();
+    int* local = a.sync[a.rank];
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // cumulative: covers the peer stores of the block, ordered before this thread by the barrier
         last_block = atomicAdd(local + SYNC_LOCAL + 2, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
     if (last_block && threadIdx.x < a.nranks) {
-        const int mine = *(volatile int*)(local + SYNC_LOCAL + a.parity);
+        const int value = *(volatile int*)(local + SYNC_LOCAL + a.parity);
         int* peer = a.sync[threadIdx.x];
-        *(volatile int*)(peer + SYNC_DISP + a.parity * PEER_MAX_RANKS + a.rank) = mine;
+        *(volatile int*)(peer + SYNC_DISP + a.parity * PEER_MAX_RANKS + a.rank) = value;
         __threadfence_system();
         *(volatile int*)(peer + SYNC_ARRIVED + a.parity * PEER_MAX_RANKS + a.rank) = a.epoch;
     }
@@ -2079,6 +2163,7 @@ static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
     LUMOL_CUDA_CHECK(ctx, ctx->sre_tmp.reserve(4 * (size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sre_origin.reserve(2 * (size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sre_need_mask.reserve((size_t)P.ncells + 1));
+    LUMOL_CUDA_CHECK(ctx, ctx->sre_halo_items.reserve(8 * (size_t)P.ncells + 8));
     const bool fresh_sync = ctx->sre_sync.ptr == nullptr;
     LUMOL_CUDA_CHECK(ctx, ctx->sre_sync.reserve(SYNC_INTS));
     if (fresh_sync) LUMOL_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->sre_sync.ptr, 0, SYNC_INTS * sizeof(int), ctx->stream));
@@ -2182,6 +2267,24 @@ static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
         }
         if (sharded) {
             ScopedClock clock(ctx, &ctx->clk_comm);
+            SreHaloArgs h;
+            h.items = ctx->sre_halo_items.ptr;
+            h.flags = flags;
+            h.epoch = epoch;
+            h.parity = parity;
+            h.nranks = ctx->nranks;
+            h.rank = ctx->rank;
+            for (int r = 0; r < ctx->nranks; r++) {
+                h.frame[r] = (double*)peers[2 * PEER_MAX_RANKS + r] + (size_t)parity * 3 * P.fstride;
+                h.sync[r] = (int*)peers[3 * PEER_MAX_RANKS + r];
+            }
+            {
+                ScopedClock halo_clock(ctx, &ctx->clk_kspace);  // DIAGNOSTIC: halo copies timed apart from the waits
+                sre_halo_kernel<<<ctx->sm_count, SRE_THREADS, 0, ctx->stream>>>(h);
+                ctx->clk_kspace.launches++;
+            }
+            ctx->launches++;
+            ctx->clk_comm.launches++;
             sre_sync_kernel<<<1, 32, 0, ctx->stream>>>(ctx->nranks, epoch, parity, (float)(0.25 * P.skin * P.skin), ctx->sre_sync.ptr, flags,
                                                        ctx->results.ptr);
             SreGatherArgs g;
@@ -2215,6 +2318,7 @@ static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
             sorted.tmp_origin = ctx->sre_origin.ptr + n;
             sorted.nranks = sharded ? ctx->nranks : 1;
             sorted.gathered = ctx->sre_sync.ptr + SYNC_GATHERED;
+
             if ((status = lj2_launch_rebuild(ctx, P, epoch, ctx->sre_x.ptr, parity, sorted, sharded ? ctx->sre_need_mask.ptr : nullptr)) != 0) {
                 return status;
             }

@@ -234,7 +234,9 @@ class MolecularDynamics:
         if self._ready_for != (id(system), system._version):
             device = self.setup(system)
         else:
-            device = system._device
+            # arrays that are not resident on the device (the host edited them, or never ran) are uploaded again: like the
+            # reference's propagate, the step works on the current system arrays
+            device = device_for(system, velocities=True)
         lib, ctx = device.lib, device.ctx
         if isinstance(self.thermostat, CSVRThermostat):
             noise = np.ascontiguousarray(self.thermostat.sum_noises(system.degrees_of_freedom() - 1, nsteps))

@@ -67,24 +67,27 @@ def sampled_rows(n, count, seed):
 
 # ---- Lennard-Jones bench box ---------------------------------------------------------------------------------
 
-def test_lj_bench_box_sampled_atoms_vs_oracle():
-    """bench.py's default workload: 1 048 576 argon atoms.  512 sampled atoms, total force over all other atoms,
-    forces-only and forces + energy + virial kernel instances; then thirty device-resident velocity-Verlet steps
-    (the neighbour list is reused with displaced atoms) and the same comparison at the final positions."""
-    system = synthetic.lj_box((128, 128, 64), seed=20240 + 20)
+@pytest.mark.parametrize("lattice", [(128, 128, 64), (256, 256, 128)])
+def test_lj_bench_box_sampled_atoms_vs_oracle(lattice):
+    """bench.py's workloads: the 8 388 608-atom argon box of the headline line and the 1 048 576-atom box beside it.
+    512 (256 for the large box) sampled atoms, total force over all other atoms, forces-only and forces + energy + virial
+    kernel instances; then thirty device-resident velocity-Verlet steps (sorted-resident engine, the neighbour list is
+    reused with displaced atoms) and the same comparison at the final positions."""
+    system = synthetic.lj_box(lattice, seed=20240 + 20)
     synthetic.maxwell_boltzmann(system, 120.0, seed=7)
     n = system.size()
-    rows = sampled_rows(n, 512, seed=1)
-    assert len(rows) >= 256
+    rows = sampled_rows(n, 512 if n < 2_000_000 else 256, seed=1)
+    assert len(rows) >= 200
+    label = f"lj-{n // 1048576}M"
     device = device_for(system, velocities=True)
     reference = oracle.OracleSystem(system)
     expected = reference.pair_forces_rows(rows)
     forces_only = device.compute(forces=True).forces
     assert device.stats().neighbor_path == 1
     scale = np.abs(forces_only).max()
-    assert_forces("lj-1M forces-only kernel", forces_only[rows], expected, scale)
+    assert_forces(f"{label} forces-only kernel", forces_only[rows], expected, scale)
     full = device.compute(forces=True, energy=True, virial=True)
-    assert_forces("lj-1M forces+energy+virial kernel", full.forces[rows], expected, scale)
+    assert_forces(f"{label} forces+energy+virial kernel", full.forces[rows], expected, scale)
     # Newton's third law over the whole box, and the virial against the force field it was computed with
     assert np.abs(full.forces.sum(axis=0)).max() < 1e-9 * scale * np.sqrt(n)
 
@@ -98,10 +101,10 @@ def test_lj_bench_box_sampled_atoms_vs_oracle():
         forces = np.zeros((n, 3))
         _ffi.check(ctx, lib.lumol_cuda_get_positions(ctx, _ffi.as_double_pointer(positions)))
         _ffi.check(ctx, lib.lumol_cuda_get_forces(ctx, _ffi.as_double_pointer(forces)))
-        moved = synthetic.lj_box((128, 128, 64), seed=20240 + 20)
+        moved = synthetic.lj_box(lattice, seed=20240 + 20)
         moved.positions[:] = positions
         expected = oracle.OracleSystem(moved).pair_forces_rows(rows)
-        assert_forces(f"lj-1M after {steps} more MD steps", forces[rows], expected, np.abs(forces).max())
+        assert_forces(f"{label} after {steps} more MD steps", forces[rows], expected, np.abs(forces).max())
     device.close()
 
 

@@ -2,7 +2,7 @@ cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "lj or staged or cell_list or non_finite or edge" 2>&1 | tail -3
 timeout 600 python -m pytest tests/test_gpu_bench_parity.py -q -m gpu -k "lj_bench or cutoff" 2>&1 | tail -3
 timeout 300 python bench.py --no-spce --no-cpu-baseline --no-e2e --steps 300 --warmup 50 > gpurun_out/lj2_a.json 2> gpurun_out/lj2_a.err; tail -3 gpurun_out/lj2_a.err
-LUMOL_CUDA_LJ2_ALL_LEVELS=1 timeout 300 python bench.py --no-spce --no-cpu-baseline --no-e2e --steps 300 --warmup 50 > gpurun_out/lj2_alllevels.json 2> gpurun_out/lj2_b.err
+
 timeout 300 python -m pytest tests/test_gpu_md.py -q -m gpu -x 2>&1 | tail -3
 python - <<'PY'
 import json
@@ -14,5 +14,7 @@ for name in ("lj2_a","lj2_alllevels","lj2_nopairs"):
     except Exception as e:
         print(name, "failed", e)
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 14 --csv --log-file gpurun_out/r2e_launches_lj2.csv python tools/profile_step.py --steps 3 2>&1 | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 14 --csv --log-file gpurun_out/r2e_launches_lj2.csv python tools/profile_step.py --steps 2 2>&1 | tail -1
 
+LUMOL_CUDA_SORTED_MD=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 9 --csv --log-file gpurun_out/r2e_launches_lj2b.csv python tools/profile_step.py --steps 2 2>&1 | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file gpurun_out/r2e_launches_spce.csv python tools/profile_step.py --workload spce --lattice 32 --steps 2 2>&1 | tail -1
