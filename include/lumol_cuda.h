@@ -126,7 +126,8 @@ enum {
     LUMOL_CUDA_FORCES = 1,          /* Forces::compute, sys/compute.rs:33-107 */
     LUMOL_CUDA_ENERGY = 2,          /* PotentialEnergy::compute, sys/compute.rs:114-127 */
     LUMOL_CUDA_ATOMIC_VIRIAL = 4,   /* AtomicVirial::compute, sys/compute.rs:198-254 */
-    LUMOL_CUDA_MOLECULAR_VIRIAL = 8 /* MolecularVirial::compute, sys/compute.rs:281-363 */
+    LUMOL_CUDA_MOLECULAR_VIRIAL = 8, /* MolecularVirial::compute, sys/compute.rs:281-363 */
+    LUMOL_CUDA_OWNED_FORCES = 16     /* with LUMOL_CUDA_FORCES on a sharded context: only this rank's block of forces (lumol_cuda_owned_range) */
 };
 
 /* Which interaction families take part (bit mask); lets the host implement
@@ -250,6 +251,11 @@ int32_t lumol_cuda_set_coulomb_wolf(lumol_cuda_context* ctx, double cutoff, int3
  * `what` has both virial bits the atomic virial is returned. */
 int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, uint32_t parts, double* forces,
                            lumol_cuda_energy* energy, double virial[9]);
+/* Sharded contexts (lumol_cuda_comm_init): the block of atoms, in the caller's order, whose forces this rank evaluates in
+ * lumol_cuda_compute.  With LUMOL_CUDA_OWNED_FORCES in `what`, `forces` receives only those count x 3 values (no
+ * all-gather between the ranks, count x 24 bytes to the host instead of n x 24): what a host-side integrator that is
+ * itself sharded over processes needs (the reference has no such notion: its Forces::compute fills one Vec, compute.rs:33). */
+int32_t lumol_cuda_owned_range(lumol_cuda_context* ctx, int64_t* first, int64_t* count);
 /* KineticEnergy (compute.rs:134-144), and sum_i m_i v_i (x) v_i for Stress (compute.rs:471-474) */
 int32_t lumol_cuda_kinetic_energy(lumol_cuda_context* ctx, double* kinetic);
 int32_t lumol_cuda_kinetic_tensor(lumol_cuda_context* ctx, double tensor[9]);

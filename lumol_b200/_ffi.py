@@ -18,6 +18,7 @@ RESTRICTION_NONE, RESTRICTION_INTRA_MOLECULAR, RESTRICTION_INTER_MOLECULAR = 0, 
 RESTRICTION_EXCLUDE12, RESTRICTION_EXCLUDE13, RESTRICTION_EXCLUDE14, RESTRICTION_SCALE14 = 3, 4, 5, 6
 CELL_INFINITE, CELL_ORTHORHOMBIC, CELL_TRICLINIC = 0, 1, 2
 FORCES, ENERGY, ATOMIC_VIRIAL, MOLECULAR_VIRIAL = 1, 2, 4, 8
+OWNED_FORCES = 16  # sharded contexts: lumol_cuda_compute returns only this rank's block of forces (lumol_cuda_owned_range)
 PART_PAIRS, PART_BONDED, PART_COULOMB, PART_ALL = 1, 2, 4, 7
 INTEGRATOR_VELOCITY_VERLET, INTEGRATOR_VERLET, INTEGRATOR_LEAP_FROG = 0, 1, 2
 INTEGRATOR_BERENDSEN_BAROSTAT, INTEGRATOR_ANISO_BERENDSEN_BAROSTAT = 3, 4
@@ -119,6 +120,7 @@ SIGNATURES = {
     "lumol_cuda_set_positions": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_set_velocities": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_get_positions": (_c.c_int32, [_ctx, _dp]),
+    "lumol_cuda_owned_range": (_c.c_int32, [_ctx, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "lumol_cuda_get_velocities": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_get_forces": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_set_molecules": (

@@ -676,7 +676,7 @@ int evaluate_forces_device(Context* c, const ComputeRequest& req) {
 extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, uint32_t parts, double* forces,
                                       lumol_cuda_energy* energy, double virial[9]) {
     CTX_OR_FAIL(ctx);
-    if ((what & ~15u) != 0 || (parts & ~7u) != 0) {
+    if ((what & ~31u) != 0 || (parts & ~7u) != 0) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_compute: unknown bits in what/parts");
     }
     ComputeRequest req;
@@ -717,12 +717,22 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
         std::memset(c->host_results, 0, RES_COUNT * sizeof(double));
     }
     if (req.forces && forces != nullptr && c->n > 0) {
-        if (c->nranks > 1) {
-            status = comm_allgather_blocks(c, c->force.ptr, 3 * c->n);
-            if (status) return status;
+        if ((what & LUMOL_CUDA_OWNED_FORCES) != 0 && c->nranks > 1) {
+            // only this rank's block: no all-gather, 1 / nranks of the bytes to the host
+            int64_t lo, hi;
+            c->owned_range(c->n, lo, hi);
+            if (hi > lo) {
+                LUMOL_CUDA_CHECK(c, cudaMemcpyAsync(forces, c->force.ptr + 3 * lo, (size_t)(hi - lo) * 3 * sizeof(double),
+                                                    cudaMemcpyDeviceToHost, c->stream));
+            }
+        } else {
+            if (c->nranks > 1) {
+                status = comm_allgather_blocks(c, c->force.ptr, 3 * c->n);
+                if (status) return status;
+            }
+            LUMOL_CUDA_CHECK(c, cudaMemcpyAsync(forces, c->force.ptr, (size_t)c->n * 3 * sizeof(double),
+                                                cudaMemcpyDeviceToHost, c->stream));
         }
-        LUMOL_CUDA_CHECK(c, cudaMemcpyAsync(forces, c->force.ptr, (size_t)c->n * 3 * sizeof(double),
-                                            cudaMemcpyDeviceToHost, c->stream));
     }
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     if (c->path == 1) {
@@ -818,6 +828,16 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
             virial[8] += tail_virial;
         }
     }
+    return LUMOL_CUDA_SUCCESS;
+}
+
+extern "C" int32_t lumol_cuda_owned_range(lumol_cuda_context* ctx, int64_t* first, int64_t* count) {
+    CTX_OR_FAIL(ctx);
+    if (first == nullptr || count == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
+    int64_t lo, hi;
+    c->owned_range(c->n, lo, hi);
+    *first = lo;
+    *count = hi - lo;
     return LUMOL_CUDA_SUCCESS;
 }
 

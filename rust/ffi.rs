@@ -44,14 +44,65 @@ pub struct lumol_cuda_energy {
     pub coulomb_kspace: f64,
 }
 
+/// Counters of the measurement harness (`lumol_cuda_stats`).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct lumol_cuda_stats {
+    pub natoms: i64,
+    pub kernel_launches: i64,
+    pub neighbor_path: i64,
+    pub ncells: [i64; 3],
+    pub nkvectors: i64,
+    pub pair_launches: i64,
+    pub pair_ms: f64,
+    pub kspace_launches: i64,
+    pub kspace_ms: f64,
+    pub integrate_launches: i64,
+    pub integrate_ms: f64,
+    pub neighbor_launches: i64,
+    pub neighbor_ms: f64,
+    pub comm_launches: i64,
+    pub comm_ms: f64,
+    pub pair_count: f64,
+    pub coulomb_pair_count: f64,
+    pub neighbor_rebuilds: i64,
+    pub neighbor_skin: f64,
+}
+
 pub const LUMOL_CUDA_FORCES: u32 = 1;
 pub const LUMOL_CUDA_ENERGY: u32 = 2;
 pub const LUMOL_CUDA_ATOMIC_VIRIAL: u32 = 4;
 pub const LUMOL_CUDA_MOLECULAR_VIRIAL: u32 = 8;
+pub const LUMOL_CUDA_OWNED_FORCES: u32 = 16;
 pub const LUMOL_CUDA_PART_PAIRS: u32 = 1;
 pub const LUMOL_CUDA_PART_BONDED: u32 = 2;
 pub const LUMOL_CUDA_PART_COULOMB: u32 = 4;
 pub const LUMOL_CUDA_PART_ALL: u32 = 7;
+
+pub const LUMOL_CUDA_POTENTIAL_ABSENT: i32 = -1;
+pub const LUMOL_CUDA_POTENTIAL_NULL: i32 = 0;
+pub const LUMOL_CUDA_POTENTIAL_LJ: i32 = 1;
+pub const LUMOL_CUDA_POTENTIAL_HARMONIC: i32 = 2;
+pub const LUMOL_CUDA_POTENTIAL_BUCKINGHAM: i32 = 3;
+pub const LUMOL_CUDA_POTENTIAL_BMH: i32 = 4;
+pub const LUMOL_CUDA_POTENTIAL_MORSE: i32 = 5;
+pub const LUMOL_CUDA_POTENTIAL_GAUSSIAN: i32 = 6;
+pub const LUMOL_CUDA_POTENTIAL_MIE: i32 = 7;
+pub const LUMOL_CUDA_POTENTIAL_COSINE_HARMONIC: i32 = 8;
+pub const LUMOL_CUDA_POTENTIAL_TORSION: i32 = 9;
+pub const LUMOL_CUDA_POTENTIAL_TABLE: i32 = 10;
+pub const LUMOL_CUDA_RESTRICTION_NONE: i32 = 0;
+pub const LUMOL_CUDA_RESTRICTION_INTRA_MOLECULAR: i32 = 1;
+pub const LUMOL_CUDA_RESTRICTION_INTER_MOLECULAR: i32 = 2;
+pub const LUMOL_CUDA_RESTRICTION_EXCLUDE12: i32 = 3;
+pub const LUMOL_CUDA_RESTRICTION_EXCLUDE13: i32 = 4;
+pub const LUMOL_CUDA_RESTRICTION_EXCLUDE14: i32 = 5;
+pub const LUMOL_CUDA_RESTRICTION_SCALE14: i32 = 6;
+pub const LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET: i32 = 0;
+pub const LUMOL_CUDA_INTEGRATOR_VERLET: i32 = 1;
+pub const LUMOL_CUDA_INTEGRATOR_LEAP_FROG: i32 = 2;
+pub const LUMOL_CUDA_INTEGRATOR_BERENDSEN_BAROSTAT: i32 = 3;
+pub const LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT: i32 = 4;
 
 extern "C" {
     pub fn lumol_cuda_abi_version() -> i32;
@@ -110,9 +161,18 @@ extern "C" {
     pub fn lumol_cuda_get_cell(ctx: *mut lumol_cuda_context, cell: *mut f64) -> i32;
     pub fn lumol_cuda_comm_unique_id(id: *mut u8) -> i32;
     pub fn lumol_cuda_comm_init(ctx: *mut lumol_cuda_context, nranks: i32, rank: i32, id: *const u8) -> i32;
+    pub fn lumol_cuda_owned_range(ctx: *mut lumol_cuda_context, first: *mut i64, count: *mut i64) -> i32;
     pub fn lumol_cuda_set_neighbor_skin(ctx: *mut lumol_cuda_context, skin: f64) -> i32;
     pub fn lumol_cuda_set_neighbor_path(ctx: *mut lumol_cuda_context, path: i32) -> i32;
     pub fn lumol_cuda_set_kspace_algorithm(ctx: *mut lumol_cuda_context, algorithm: i32) -> i32;
+    pub fn lumol_cuda_ewald_kvectors(
+        ctx: *mut lumol_cuda_context, capacity: i64, count: *mut i64, index: *mut i32, energy_factor: *mut f64, rho: *mut f64,
+    ) -> i32;
+    pub fn lumol_cuda_set_profiling(ctx: *mut lumol_cuda_context, enabled: i32) -> i32;
+    pub fn lumol_cuda_get_stats(ctx: *mut lumol_cuda_context, stats: *mut lumol_cuda_stats) -> i32;
+    pub fn lumol_cuda_reset_stats(ctx: *mut lumol_cuda_context) -> i32;
+    pub fn lumol_cuda_measure_fp64_peak(ctx: *mut lumol_cuda_context, tflops: *mut f64) -> i32;
+    pub fn lumol_cuda_measure_copy_bandwidth(ctx: *mut lumol_cuda_context, gbs: *mut f64) -> i32;
     pub fn lumol_cuda_stream(ctx: *mut lumol_cuda_context) -> *mut c_void;
     pub fn lumol_cuda_synchronize(ctx: *mut lumol_cuda_context) -> i32;
 }

@@ -22,6 +22,25 @@ def test_header_and_binding_agree():
     assert declared_symbols() == sorted(_ffi.SIGNATURES)
 
 
+def test_rust_binding_declares_every_symbol_and_constant():
+    """rust/ffi.rs (the binding a lumol maintainer adds) cannot be compiled here: keep it symbol-for-symbol
+    with the header, and its enum constants equal to the header's values."""
+    with open(os.path.join(ROOT, "rust", "ffi.rs")) as fd:
+        binding = fd.read()
+    assert sorted(set(re.findall(r"\bpub fn (lumol_cuda_[a-z0-9_]+)\s*\(", binding))) == declared_symbols()
+    with open(os.path.join(ROOT, "include", "lumol_cuda.h")) as fd:
+        header = fd.read()
+    values = {name: int(value) for name, value in re.findall(r"\b(LUMOL_CUDA_[A-Z0-9_]+)\s*=\s*(-?\d+)", header)}
+    constants = re.findall(r"pub const (LUMOL_CUDA_[A-Z0-9_]+): [iu]32 = (-?\d+);", binding)
+    assert len(constants) > 30
+    for name, value in constants:
+        assert values[name] == int(value), name
+    # the stats mirror has one field per header field
+    stats_header = re.search(r"typedef struct \{([^}]*)\} lumol_cuda_stats;", header).group(1)
+    stats_rust = re.search(r"pub struct lumol_cuda_stats \{([^}]*)\}", binding).group(1)
+    assert re.findall(r"\b([a-z_0-9]+)(?:\[3\])?;", stats_header) == re.findall(r"pub ([a-z_0-9]+):", stats_rust)
+
+
 def test_library_exports_every_symbol():
     lib = ctypes.CDLL(_ffi.LIBRARY_PATH)
     for name in declared_symbols():

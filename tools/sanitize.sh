@@ -9,12 +9,12 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-select="${1:-bench_system or cache_move or wolf_move or ewald_move or integrators_follow}"
+select="${1:-bench_system or cache_move or wolf_move or ewald_move or integrators_follow or lj_box_cell_list or water_box_cell_list or on_the_cutoff or sorted_resident}"
 status=0
 for tool in memcheck racecheck initcheck; do
     log="gpurun_out/sanitize_${tool}.log"
     compute-sanitizer --tool "$tool" --error-exitcode 3 --target-processes all \
-        python -m pytest tests/test_gpu_parity.py tests/test_gpu_mc.py tests/test_gpu_md.py -q -m gpu -x -k "$select" > "$log" 2>&1
+        python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_parity.py tests/test_gpu_mc.py tests/test_gpu_md.py -q -m gpu -x -k "$select" > "$log" 2>&1
     code=$?
     tail -3 "$log"
     if [ "$code" -ne 0 ]; then
