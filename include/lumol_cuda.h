@@ -194,6 +194,14 @@ typedef struct {
 int32_t lumol_cuda_abi_version(void);
 /* device: CUDA ordinal.  Fails (no fallback) when there is no usable device. */
 int32_t lumol_cuda_create(int32_t device, lumol_cuda_context** ctx);
+/* One context over several devices of THIS process (a single lumol process drives all the GPUs of the node; SURVEY
+ * section 8b: lumol has one `System` and one thread of control).  The library keeps one sharded context and one host
+ * thread per device and connects them with NCCL and NVLink peer memory, exactly as lumol_cuda_comm_init does between
+ * processes; every other entry point accepts the returned context unchanged, takes whole-system arrays and returns
+ * whole-system results (forces are downloaded block by block from the device that owns them).  Not available on such a
+ * context: lumol_cuda_comm_init, the barostats and the molecular virial (as for any sharded context).
+ * ndevices == 1 is lumol_cuda_create(devices[0]). */
+int32_t lumol_cuda_create_multi(const int32_t* devices, int32_t ndevices, lumol_cuda_context** ctx);
 int32_t lumol_cuda_destroy(lumol_cuda_context* ctx);
 /* Message of the last error on this context (or of the last failed create when ctx is NULL). */
 const char* lumol_cuda_last_error(const lumol_cuda_context* ctx);

@@ -113,6 +113,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 SIGNATURES = {
     "lumol_cuda_abi_version": (_c.c_int32, []),
     "lumol_cuda_create": (_c.c_int32, [_c.c_int32, _c.POINTER(_ctx)]),
+    "lumol_cuda_create_multi": (_c.c_int32, [_c.POINTER(_c.c_int32), _c.c_int32, _c.POINTER(_ctx)]),
     "lumol_cuda_destroy": (_c.c_int32, [_ctx]),
     "lumol_cuda_last_error": (_c.c_char_p, [_ctx]),
     "lumol_cuda_set_cell": (_c.c_int32, [_ctx, _dp, _c.c_int32]),

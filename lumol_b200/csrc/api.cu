@@ -11,6 +11,15 @@ using namespace lumol;
 
 static std::string g_create_error;
 
+void lumol::set_create_error(const char* message) { g_create_error = message; }
+
+// A context made by lumol_cuda_create_multi hands the call to one host thread per device (multi.cu); `child` and `rank`
+// name the per-device context inside `call`.
+#define MULTI_FAN(ctx, call)                                                                                      \
+    if ((ctx) != nullptr && (ctx)->multi != nullptr) {                                                            \
+        return lumol::multi_run((ctx), [=](lumol_cuda_context* child, int rank) -> int32_t { (void)rank; return (call); }); \
+    }
+
 #define CTX_OR_FAIL(ctx)                                  \
     if ((ctx) == nullptr) {                               \
         return LUMOL_CUDA_ERROR_INVALID_ARGUMENT;         \
@@ -87,6 +96,11 @@ extern "C" int32_t lumol_cuda_create(int32_t device, lumol_cuda_context** out) {
 
 extern "C" int32_t lumol_cuda_destroy(lumol_cuda_context* ctx) {
     if (ctx == nullptr) return LUMOL_CUDA_SUCCESS;
+    if (ctx->multi != nullptr) {
+        multi_destroy(ctx);
+        delete ctx;
+        return LUMOL_CUDA_SUCCESS;
+    }
     Context* c = &ctx->impl;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -140,6 +154,7 @@ static void invert3(const double m[9], double r[9]) {
 }
 
 extern "C" int32_t lumol_cuda_set_cell(lumol_cuda_context* ctx, const double cell[9], int32_t shape) {
+    MULTI_FAN(ctx, lumol_cuda_set_cell(child, cell, shape));
     CTX_OR_FAIL(ctx);
     if (shape < 0 || shape > 2 || (shape != LUMOL_CUDA_CELL_INFINITE && cell == nullptr)) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_set_cell: bad shape or null matrix");
@@ -203,6 +218,7 @@ static int reset_molecules(Context* c) {
 extern "C" int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, const double* position,
                                             const double* velocity, const double* mass, const double* charge,
                                             const uint32_t* kind) {
+    MULTI_FAN(ctx, lumol_cuda_set_particles(child, n, position, velocity, mass, charge, kind));
     CTX_OR_FAIL(ctx);
     if (n < 0 || n > 400000000 || (n > 0 && (position == nullptr || mass == nullptr || charge == nullptr || kind == nullptr))) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_set_particles: bad size or null array");
@@ -245,6 +261,7 @@ extern "C" int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, 
 }
 
 extern "C" int32_t lumol_cuda_set_positions(lumol_cuda_context* ctx, const double* position) {
+    MULTI_FAN(ctx, lumol_cuda_set_positions(child, position));
     CTX_OR_FAIL(ctx);
     if (position == nullptr && c->n > 0) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null positions");
     PositionsChange change(c);
@@ -257,6 +274,7 @@ extern "C" int32_t lumol_cuda_set_positions(lumol_cuda_context* ctx, const doubl
 }
 
 extern "C" int32_t lumol_cuda_set_velocities(lumol_cuda_context* ctx, const double* velocity) {
+    MULTI_FAN(ctx, lumol_cuda_set_velocities(child, velocity));
     CTX_OR_FAIL(ctx);
     if (velocity == nullptr && c->n > 0) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null velocities");
     if (c->n > 0) {
@@ -274,22 +292,29 @@ static int download3(Context* c, double* dst, DeviceBuffer<double>& src, bool ga
         int status = comm_allgather_blocks(c, src.ptr, 3 * c->n);
         if (status) return status;
     }
+    if (c->discard_downloads) {  // the first child of a multi-device context fills the caller's array
+        LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     LUMOL_CUDA_CHECK(c, cudaMemcpyAsync(dst, src.ptr, (size_t)c->n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 extern "C" int32_t lumol_cuda_get_positions(lumol_cuda_context* ctx, double* position) {
+    MULTI_FAN(ctx, lumol_cuda_get_positions(child, position));
     CTX_OR_FAIL(ctx);
     return download3(c, position, c->position, false);  // positions are all-gathered after every drift
 }
 
 extern "C" int32_t lumol_cuda_get_velocities(lumol_cuda_context* ctx, double* velocity) {
+    MULTI_FAN(ctx, lumol_cuda_get_velocities(child, velocity));
     CTX_OR_FAIL(ctx);
     return download3(c, velocity, c->velocity, true);
 }
 
 extern "C" int32_t lumol_cuda_get_forces(lumol_cuda_context* ctx, double* forces) {
+    MULTI_FAN(ctx, lumol_cuda_get_forces(child, forces));
     CTX_OR_FAIL(ctx);
     return download3(c, forces, c->force, true);
 }
@@ -297,6 +322,7 @@ extern "C" int32_t lumol_cuda_get_forces(lumol_cuda_context* ctx, double* forces
 extern "C" int32_t lumol_cuda_set_molecules(lumol_cuda_context* ctx, int64_t nmol, const uint64_t* start,
                                             const uint64_t* bond_distances_offset, const uint8_t* bond_distances,
                                             uint64_t bond_distances_size) {
+    MULTI_FAN(ctx, lumol_cuda_set_molecules(child, nmol, start, bond_distances_offset, bond_distances, bond_distances_size));
     CTX_OR_FAIL(ctx);
     if (nmol == 0) {
         return reset_molecules(c);
@@ -359,6 +385,7 @@ extern "C" int32_t lumol_cuda_set_molecules(lumol_cuda_context* ctx, int64_t nmo
 static bool valid_restriction(int r) { return r >= LUMOL_CUDA_RESTRICTION_NONE && r <= LUMOL_CUDA_RESTRICTION_SCALE14; }
 
 extern "C" int32_t lumol_cuda_set_pairs(lumol_cuda_context* ctx, int32_t nkinds, const lumol_cuda_pair* pairs) {
+    MULTI_FAN(ctx, lumol_cuda_set_pairs(child, nkinds, pairs));
     CTX_OR_FAIL(ctx);
     if (nkinds < 0 || (nkinds > 0 && pairs == nullptr)) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_set_pairs: bad table");
@@ -420,6 +447,7 @@ extern "C" int32_t lumol_cuda_set_pairs(lumol_cuda_context* ctx, int32_t nkinds,
 
 extern "C" int32_t lumol_cuda_add_table(lumol_cuda_context* ctx, int32_t size, double max, const double* energy,
                                         const double* force) {
+    MULTI_FAN(ctx, lumol_cuda_add_table(child, size, max, energy, force));
     CTX_OR_FAIL(ctx);
     if (size < 2 || !(max > 0.0) || energy == nullptr || force == nullptr) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_add_table: need size >= 2, max > 0 and both tables");
@@ -436,6 +464,7 @@ extern "C" int32_t lumol_cuda_add_table(lumol_cuda_context* ctx, int32_t size, d
 }
 
 extern "C" int32_t lumol_cuda_clear_tables(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_clear_tables(child));
     CTX_OR_FAIL(ctx);
     c->host_tables.clear();
     c->host_table_energy.clear();
@@ -463,6 +492,7 @@ static int sync_tables(Context* c) {
 
 extern "C" int32_t lumol_cuda_set_bonded_potentials(lumol_cuda_context* ctx, int32_t npotentials,
                                                     const lumol_cuda_potential* potentials) {
+    MULTI_FAN(ctx, lumol_cuda_set_bonded_potentials(child, npotentials, potentials));
     CTX_OR_FAIL(ctx);
     if (npotentials < 0 || (npotentials > 0 && potentials == nullptr)) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_set_bonded_potentials: bad table");
@@ -516,21 +546,25 @@ static int set_terms(Context* c, int arity, int64_t count, const int64_t* atoms,
 }
 
 extern "C" int32_t lumol_cuda_set_bonds(lumol_cuda_context* ctx, int64_t n, const int64_t* atoms, const int32_t* potential) {
+    MULTI_FAN(ctx, lumol_cuda_set_bonds(child, n, atoms, potential));
     CTX_OR_FAIL(ctx);
     return set_terms(c, 2, n, atoms, potential, c->bonds, c->nbonds);
 }
 
 extern "C" int32_t lumol_cuda_set_angles(lumol_cuda_context* ctx, int64_t n, const int64_t* atoms, const int32_t* potential) {
+    MULTI_FAN(ctx, lumol_cuda_set_angles(child, n, atoms, potential));
     CTX_OR_FAIL(ctx);
     return set_terms(c, 3, n, atoms, potential, c->angles, c->nangles);
 }
 
 extern "C" int32_t lumol_cuda_set_dihedrals(lumol_cuda_context* ctx, int64_t n, const int64_t* atoms, const int32_t* potential) {
+    MULTI_FAN(ctx, lumol_cuda_set_dihedrals(child, n, atoms, potential));
     CTX_OR_FAIL(ctx);
     return set_terms(c, 4, n, atoms, potential, c->dihedrals, c->ndihedrals);
 }
 
 extern "C" int32_t lumol_cuda_set_coulomb_none(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_set_coulomb_none(child));
     CTX_OR_FAIL(ctx);
     if (c->coulomb.kind != 0) c->structure_generation++;
     c->coulomb = CoulombView{};
@@ -540,6 +574,7 @@ extern "C" int32_t lumol_cuda_set_coulomb_none(lumol_cuda_context* ctx) {
 
 extern "C" int32_t lumol_cuda_set_coulomb_ewald(lumol_cuda_context* ctx, double cutoff, double alpha, int32_t kmax,
                                                 int32_t restriction) {
+    MULTI_FAN(ctx, lumol_cuda_set_coulomb_ewald(child, cutoff, alpha, kmax, restriction));
     CTX_OR_FAIL(ctx);
     // Ewald::new panics (ewald.rs:280-286)
     if (cutoff < 0.0) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "the cutoff can not be negative in Ewald");
@@ -565,6 +600,7 @@ extern "C" int32_t lumol_cuda_set_coulomb_ewald(lumol_cuda_context* ctx, double 
 }
 
 extern "C" int32_t lumol_cuda_set_coulomb_wolf(lumol_cuda_context* ctx, double cutoff, int32_t restriction, double scale14) {
+    MULTI_FAN(ctx, lumol_cuda_set_coulomb_wolf(child, cutoff, restriction, scale14));
     CTX_OR_FAIL(ctx);
     if (!(cutoff > 0.0)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "Got a negative cutoff in Wolf summation");  // wolf.rs:69
     if (!valid_restriction(restriction)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown restriction %d", restriction);
@@ -675,6 +711,19 @@ int evaluate_forces_device(Context* c, const ComputeRequest& req) {
 
 extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, uint32_t parts, double* forces,
                                       lumol_cuda_energy* energy, double virial[9]) {
+    if (ctx != nullptr && ctx->multi != nullptr) {
+        // every device downloads the block of forces it owns straight into the caller's array; sums come from the first
+        return multi_run(ctx, [=](lumol_cuda_context* child, int rank) -> int32_t {
+            lumol_cuda_energy unused_energy;
+            double unused_virial[9];
+            int64_t lo = 0, hi = 0;
+            child->impl.owned_range(child->impl.n, lo, hi);
+            const bool download = forces != nullptr && (what & LUMOL_CUDA_FORCES) != 0 && (what & ~31u) == 0;
+            return lumol_cuda_compute(child, download ? (what | LUMOL_CUDA_OWNED_FORCES) : what, parts, download ? forces + 3 * lo : forces,
+                                      rank == 0 || energy == nullptr ? energy : &unused_energy,
+                                      rank == 0 || virial == nullptr ? virial : unused_virial);
+        });
+    }
     CTX_OR_FAIL(ctx);
     if ((what & ~31u) != 0 || (parts & ~7u) != 0) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_compute: unknown bits in what/parts");
@@ -832,6 +881,12 @@ extern "C" int32_t lumol_cuda_compute(lumol_cuda_context* ctx, uint32_t what, ui
 }
 
 extern "C" int32_t lumol_cuda_owned_range(lumol_cuda_context* ctx, int64_t* first, int64_t* count) {
+    if (ctx != nullptr && ctx->multi != nullptr) {  // the devices of a multi-device context own everything between them
+        if (first == nullptr || count == nullptr) return LUMOL_CUDA_ERROR_INVALID_ARGUMENT;
+        *first = 0;
+        *count = multi_child(ctx, 0)->impl.n;
+        return LUMOL_CUDA_SUCCESS;
+    }
     CTX_OR_FAIL(ctx);
     if (first == nullptr || count == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
     int64_t lo, hi;
@@ -842,6 +897,13 @@ extern "C" int32_t lumol_cuda_owned_range(lumol_cuda_context* ctx, int64_t* firs
 }
 
 extern "C" int32_t lumol_cuda_kinetic_energy(lumol_cuda_context* ctx, double* kinetic) {
+    if (ctx != nullptr && ctx->multi != nullptr) {
+        if (kinetic == nullptr) return LUMOL_CUDA_ERROR_INVALID_ARGUMENT;
+        return multi_run(ctx, [=](lumol_cuda_context* child, int rank) -> int32_t {
+            double unused = 0.0;
+            return lumol_cuda_kinetic_energy(child, rank == 0 ? kinetic : &unused);
+        });
+    }
     CTX_OR_FAIL(ctx);
     if (kinetic == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
     *kinetic = 0.0;
@@ -857,6 +919,13 @@ extern "C" int32_t lumol_cuda_kinetic_energy(lumol_cuda_context* ctx, double* ki
 }
 
 extern "C" int32_t lumol_cuda_kinetic_tensor(lumol_cuda_context* ctx, double tensor[9]) {
+    if (ctx != nullptr && ctx->multi != nullptr) {
+        if (tensor == nullptr) return LUMOL_CUDA_ERROR_INVALID_ARGUMENT;
+        return multi_run(ctx, [=](lumol_cuda_context* child, int rank) -> int32_t {
+            double unused[9];
+            return lumol_cuda_kinetic_tensor(child, rank == 0 ? tensor : unused);
+        });
+    }
     CTX_OR_FAIL(ctx);
     if (tensor == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
     for (int k = 0; k < 9; k++) tensor[k] = 0.0;
@@ -873,6 +942,7 @@ extern "C" int32_t lumol_cuda_kinetic_tensor(lumol_cuda_context* ctx, double ten
 
 extern "C" int32_t lumol_cuda_ewald_kvectors(lumol_cuda_context* ctx, int64_t capacity, int64_t* count, int32_t* index,
                                              double* energy_factor, double* rho) {
+    MULTI_FAN(ctx, rank != 0 ? 0 : lumol_cuda_ewald_kvectors(child, capacity, count, index, energy_factor, rho));
     CTX_OR_FAIL(ctx);
     if (c->coulomb.kind != 1) return c->fail(LUMOL_CUDA_ERROR_STATE, "Ewald is not the active coulomb potential");
     int status = ewald_prepare(c);
@@ -894,6 +964,12 @@ extern "C" int32_t lumol_cuda_ewald_kvectors(lumol_cuda_context* ctx, int64_t ca
 
 extern "C" int32_t lumol_cuda_move_molecules_cost(lumol_cuda_context* ctx, int64_t ntrials, const int64_t* molecules,
                                                   const double* new_positions, lumol_cuda_energy* costs) {
+    if (ctx != nullptr && ctx->multi != nullptr) {
+        return multi_run(ctx, [=](lumol_cuda_context* child, int rank) -> int32_t {
+            std::vector<lumol_cuda_energy> unused((size_t)(rank == 0 || ntrials < 0 || ntrials > 65535 ? 0 : ntrials));
+            return lumol_cuda_move_molecules_cost(child, ntrials, molecules, new_positions, rank == 0 || costs == nullptr ? costs : unused.data());
+        });
+    }
     CTX_OR_FAIL(ctx);
     if (ntrials < 0 || ntrials > 65535 || (ntrials > 0 && (molecules == nullptr || new_positions == nullptr || costs == nullptr))) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_move_molecules_cost: bad trial count or null array");
@@ -969,6 +1045,7 @@ extern "C" int32_t lumol_cuda_move_molecule_cost(lumol_cuda_context* ctx, int64_
 }
 
 extern "C" int32_t lumol_cuda_move_molecule_accept(lumol_cuda_context* ctx, int64_t trial) {
+    MULTI_FAN(ctx, lumol_cuda_move_molecule_accept(child, trial));
     CTX_OR_FAIL(ctx);
     if (c->mc_positions_epoch != c->positions_epoch) {
         // cache.rs:123-126
@@ -996,6 +1073,7 @@ extern "C" int32_t lumol_cuda_move_molecule_accept(lumol_cuda_context* ctx, int6
 // ------------------------------------------------------------------------------------------------
 
 extern "C" int32_t lumol_cuda_md_setup(lumol_cuda_context* ctx, int32_t integrator, double timestep) {
+    MULTI_FAN(ctx, lumol_cuda_md_setup(child, integrator, timestep));
     CTX_OR_FAIL(ctx);
     if (integrator < LUMOL_CUDA_INTEGRATOR_VELOCITY_VERLET || integrator > LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown integrator %d", integrator);
@@ -1010,6 +1088,7 @@ extern "C" int32_t lumol_cuda_md_setup(lumol_cuda_context* ctx, int32_t integrat
 }
 
 extern "C" int32_t lumol_cuda_md_set_degrees_of_freedom(lumol_cuda_context* ctx, int32_t mode, int64_t frozen) {
+    MULTI_FAN(ctx, lumol_cuda_md_set_degrees_of_freedom(child, mode, frozen));
     CTX_OR_FAIL(ctx);
     if (mode != LUMOL_CUDA_DOF_PARTICLES && mode != LUMOL_CUDA_DOF_MOLECULES) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown degrees-of-freedom mode %d", mode);
@@ -1020,6 +1099,7 @@ extern "C" int32_t lumol_cuda_md_set_degrees_of_freedom(lumol_cuda_context* ctx,
 }
 
 extern "C" int32_t lumol_cuda_md_set_thermostat(lumol_cuda_context* ctx, int32_t thermostat, double temperature, double parameter) {
+    MULTI_FAN(ctx, lumol_cuda_md_set_thermostat(child, thermostat, temperature, parameter));
     CTX_OR_FAIL(ctx);
     if (thermostat < LUMOL_CUDA_THERMOSTAT_NONE || thermostat > LUMOL_CUDA_THERMOSTAT_CSVR) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown thermostat %d", thermostat);
@@ -1040,6 +1120,7 @@ extern "C" int32_t lumol_cuda_md_set_thermostat(lumol_cuda_context* ctx, int32_t
 }
 
 extern "C" int32_t lumol_cuda_md_set_csvr_noise(lumol_cuda_context* ctx, int64_t nsteps, const double* noise) {
+    MULTI_FAN(ctx, lumol_cuda_md_set_csvr_noise(child, nsteps, noise));
     CTX_OR_FAIL(ctx);
     if (nsteps < 0 || (nsteps > 0 && noise == nullptr)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "bad noise array");
     LUMOL_CUDA_CHECK(c, c->csvr_noise_dev.reserve((size_t)2 * nsteps + 2));
@@ -1054,6 +1135,7 @@ extern "C" int32_t lumol_cuda_md_set_csvr_noise(lumol_cuda_context* ctx, int64_t
 }
 
 extern "C" int32_t lumol_cuda_md_set_controls(lumol_cuda_context* ctx, uint32_t controls) {
+    MULTI_FAN(ctx, lumol_cuda_md_set_controls(child, controls));
     CTX_OR_FAIL(ctx);
     if (controls & ~7u) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "unknown control bits");
     c->controls = controls;
@@ -1061,6 +1143,7 @@ extern "C" int32_t lumol_cuda_md_set_controls(lumol_cuda_context* ctx, uint32_t 
 }
 
 extern "C" int32_t lumol_cuda_md_set_barostat(lumol_cuda_context* ctx, const double target[9], double tau) {
+    MULTI_FAN(ctx, lumol_cuda_md_set_barostat(child, target, tau));
     CTX_OR_FAIL(ctx);
     if (target == nullptr || !(tau > 0.0)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_md_set_barostat: bad arguments");
     for (int k = 0; k < 9; k++) c->barostat_target[k] = target[k];
@@ -1069,6 +1152,7 @@ extern "C" int32_t lumol_cuda_md_set_barostat(lumol_cuda_context* ctx, const dou
 }
 
 extern "C" int32_t lumol_cuda_get_cell(lumol_cuda_context* ctx, double cell[9]) {
+    MULTI_FAN(ctx, rank != 0 ? 0 : lumol_cuda_get_cell(child, cell));
     CTX_OR_FAIL(ctx);
     if (cell == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
     for (int k = 0; k < 9; k++) cell[k] = c->cell.h[k];
@@ -1076,6 +1160,7 @@ extern "C" int32_t lumol_cuda_get_cell(lumol_cuda_context* ctx, double cell[9]) 
 }
 
 extern "C" int32_t lumol_cuda_remove_rotation(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_remove_rotation(child));
     CTX_OR_FAIL(ctx);
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
     int status = launch_remove_rotation(c);
@@ -1085,6 +1170,7 @@ extern "C" int32_t lumol_cuda_remove_rotation(lumol_cuda_context* ctx) {
 }
 
 extern "C" int32_t lumol_cuda_rewrap(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_rewrap(child));
     CTX_OR_FAIL(ctx);
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
     PositionsChange change(c);
@@ -1200,6 +1286,7 @@ int barostat_step(Context* c) {
 }  // namespace lumol
 
 extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
+    MULTI_FAN(ctx, lumol_cuda_md_run(child, nsteps));
     CTX_OR_FAIL(ctx);
     if (c->integrator < 0) return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_md_setup was not called");
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
@@ -1306,6 +1393,7 @@ extern "C" int32_t lumol_cuda_md_run(lumol_cuda_context* ctx, int64_t nsteps) {
 }
 
 extern "C" int32_t lumol_cuda_scale_velocities(lumol_cuda_context* ctx, double factor) {
+    MULTI_FAN(ctx, lumol_cuda_scale_velocities(child, factor));
     CTX_OR_FAIL(ctx);
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
     int status = launch_scale_velocities(c, factor, false);
@@ -1315,6 +1403,7 @@ extern "C" int32_t lumol_cuda_scale_velocities(lumol_cuda_context* ctx, double f
 }
 
 extern "C" int32_t lumol_cuda_remove_translation(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_remove_translation(child));
     CTX_OR_FAIL(ctx);
     if (c->n == 0) return LUMOL_CUDA_SUCCESS;
     int status = launch_remove_translation(c);
@@ -1328,12 +1417,14 @@ extern "C" int32_t lumol_cuda_remove_translation(lumol_cuda_context* ctx) {
 // ------------------------------------------------------------------------------------------------
 
 extern "C" int32_t lumol_cuda_set_profiling(lumol_cuda_context* ctx, int32_t enabled) {
+    MULTI_FAN(ctx, lumol_cuda_set_profiling(child, enabled));
     CTX_OR_FAIL(ctx);
     c->profiling = enabled != 0;
     return LUMOL_CUDA_SUCCESS;
 }
 
 extern "C" int32_t lumol_cuda_get_stats(lumol_cuda_context* ctx, lumol_cuda_stats* stats) {
+    MULTI_FAN(ctx, rank != 0 ? 0 : lumol_cuda_get_stats(child, stats));
     CTX_OR_FAIL(ctx);
     if (stats == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null stats");
     std::memset(stats, 0, sizeof(*stats));
@@ -1363,6 +1454,7 @@ extern "C" int32_t lumol_cuda_get_stats(lumol_cuda_context* ctx, lumol_cuda_stat
 }
 
 extern "C" int32_t lumol_cuda_reset_stats(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_reset_stats(child));
     CTX_OR_FAIL(ctx);
     c->launches = 0;
     c->clk_pair = c->clk_kspace = c->clk_integrate = c->clk_neighbor = c->clk_comm = KernelClock{};
@@ -1370,6 +1462,7 @@ extern "C" int32_t lumol_cuda_reset_stats(lumol_cuda_context* ctx) {
 }
 
 extern "C" int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t path) {
+    MULTI_FAN(ctx, lumol_cuda_set_neighbor_path(child, path));
     CTX_OR_FAIL(ctx);
     if (path < -1 || path > 2) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "neighbour path must be -1, 0, 1 or 2");
     c->forced_path = path;
@@ -1378,6 +1471,7 @@ extern "C" int32_t lumol_cuda_set_neighbor_path(lumol_cuda_context* ctx, int32_t
 }
 
 extern "C" int32_t lumol_cuda_set_kspace_algorithm(lumol_cuda_context* ctx, int32_t algorithm) {
+    MULTI_FAN(ctx, lumol_cuda_set_kspace_algorithm(child, algorithm));
     CTX_OR_FAIL(ctx);
     if (algorithm < -1 || algorithm > 1) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "the k-space algorithm must be -1, 0 or 1");
@@ -1387,6 +1481,7 @@ extern "C" int32_t lumol_cuda_set_kspace_algorithm(lumol_cuda_context* ctx, int3
 }
 
 extern "C" int32_t lumol_cuda_set_neighbor_skin(lumol_cuda_context* ctx, double skin) {
+    MULTI_FAN(ctx, lumol_cuda_set_neighbor_skin(child, skin));
     CTX_OR_FAIL(ctx);
     if (!(skin >= 0.0)) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "the neighbour-list skin must be >= 0");
     c->skin = skin;
@@ -1394,21 +1489,27 @@ extern "C" int32_t lumol_cuda_set_neighbor_skin(lumol_cuda_context* ctx, double 
     return LUMOL_CUDA_SUCCESS;
 }
 
-extern "C" void* lumol_cuda_stream(lumol_cuda_context* ctx) { return ctx ? (void*)ctx->impl.stream : nullptr; }
+extern "C" void* lumol_cuda_stream(lumol_cuda_context* ctx) {
+    if (ctx != nullptr && ctx->multi != nullptr) return (void*)multi_child(ctx, 0)->impl.stream;  // the first device's
+    return ctx ? (void*)ctx->impl.stream : nullptr;
+}
 
 extern "C" int32_t lumol_cuda_synchronize(lumol_cuda_context* ctx) {
+    MULTI_FAN(ctx, lumol_cuda_synchronize(child));
     CTX_OR_FAIL(ctx);
     LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return LUMOL_CUDA_SUCCESS;
 }
 
 extern "C" int32_t lumol_cuda_measure_fp64_peak(lumol_cuda_context* ctx, double* tflops) {
+    MULTI_FAN(ctx, rank != 0 ? 0 : lumol_cuda_measure_fp64_peak(child, tflops));
     CTX_OR_FAIL(ctx);
     if (tflops == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
     return measure_fp64_peak(c, tflops);
 }
 
 extern "C" int32_t lumol_cuda_measure_copy_bandwidth(lumol_cuda_context* ctx, double* gbs) {
+    MULTI_FAN(ctx, rank != 0 ? 0 : lumol_cuda_measure_copy_bandwidth(child, gbs));
     CTX_OR_FAIL(ctx);
     if (gbs == nullptr) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null output");
     return measure_copy_bandwidth(c, gbs);

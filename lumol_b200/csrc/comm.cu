@@ -11,6 +11,7 @@
 #include "context.hpp"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -90,8 +91,7 @@ struct Comm {
     DeviceBuffer<unsigned char> handle_staging;
     double* peer_inbox[PEER_MAX_RANKS] = {};
     int* peer_flags[PEER_MAX_RANKS] = {};
-    void* opened[2 * PEER_MAX_RANKS] = {};
-    int nopened = 0;
+    std::vector<void*> opened;
     // buffers of the sorted-resident engine mapped from the other ranks (comm_map_peer_buffers)
     std::vector<void*> mapped;
     std::vector<void*> mapped_local;  // the local pointers the current mapping was made for
@@ -126,9 +126,48 @@ int comm_allgather_blocks(Context* ctx, double* data, int64_t total) { return al
 // peer-memory position exchange
 // ------------------------------------------------------------------------------------------------
 
+// What one rank tells the others about a device buffer.  Ranks of other processes map it through CUDA IPC; ranks of the
+// same process (lumol_cuda_create_multi: one host process driving several devices) cannot open their own process's
+// IPC handles and use the pointer itself after enabling peer access between the two devices.
+struct PeerHandle {
+    int32_t pid;
+    int32_t device;
+    void* raw;
+    int64_t exported;  // the IPC handle below is valid
+    cudaIpcMemHandle_t ipc;
+};
+
+static bool export_handle(Context* ctx, void* local, PeerHandle* out) {
+    std::memset(out, 0, sizeof(PeerHandle));
+    out->pid = (int32_t)getpid();
+    out->device = ctx->device;
+    out->raw = local;
+    out->exported = cudaIpcGetMemHandle(&out->ipc, local) == cudaSuccess ? 1 : 0;
+    cudaGetLastError();
+    return true;  // a rank of another process finds out when it opens the handle
+}
+
+// `opened` collects what must be closed with cudaIpcCloseMemHandle later
+static bool open_handle(Context* ctx, const PeerHandle& theirs, void** pointer, std::vector<void*>& opened) {
+    if (theirs.pid == (int32_t)getpid()) {
+        if (theirs.device != ctx->device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctx->device, theirs.device) != cudaSuccess || can == 0) return false;
+            const cudaError_t status = cudaDeviceEnablePeerAccess(theirs.device, 0);
+            if (status != cudaSuccess && status != cudaErrorPeerAccessAlreadyEnabled) return false;
+            cudaGetLastError();
+        }
+        *pointer = theirs.raw;
+        return true;
+    }
+    if (theirs.exported == 0 || cudaIpcOpenMemHandle(pointer, theirs.ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+    opened.push_back(*pointer);
+    return true;
+}
+
 static void peer_close(Comm* comm) {
-    for (int k = 0; k < comm->nopened; k++) cudaIpcCloseMemHandle(comm->opened[k]);
-    comm->nopened = 0;
+    for (void* pointer : comm->opened) cudaIpcCloseMemHandle(pointer);
+    comm->opened.clear();
     comm->peer_state = 0;
 }
 
@@ -147,14 +186,13 @@ static int peer_setup(Context* ctx) {
     bool ok = nranks <= PEER_MAX_RANKS && (forced != nullptr ? forced[0] == '1' : nranks == 2);
     // the second inbox copy starts at an even number of doubles: the drift kernel stores double2 (16 bytes) into it
     const size_t n3 = ((size_t)3 * ctx->n + 1) & ~(size_t)1;
-    cudaIpcMemHandle_t mine[2];
+    PeerHandle mine[2];
     std::memset(mine, 0, sizeof(mine));
     if (ok) {
         ok = comm->inbox.reserve(2 * n3) == cudaSuccess && comm->inbox_flags.reserve(2 * PEER_MAX_RANKS + 8) == cudaSuccess;
         if (ok) {
             ok = cudaMemsetAsync(comm->inbox_flags.ptr, 0, (2 * PEER_MAX_RANKS + 8) * sizeof(int), ctx->stream) == cudaSuccess &&
-                 cudaIpcGetMemHandle(&mine[0], comm->inbox.ptr) == cudaSuccess &&
-                 cudaIpcGetMemHandle(&mine[1], comm->inbox_flags.ptr) == cudaSuccess;
+                 export_handle(ctx, comm->inbox.ptr, &mine[0]) && export_handle(ctx, comm->inbox_flags.ptr, &mine[1]);
         }
         cudaGetLastError();
     }
@@ -179,14 +217,11 @@ static int peer_setup(Context* ctx) {
                 comm->peer_flags[p] = comm->inbox_flags.ptr;
                 continue;
             }
-            cudaIpcMemHandle_t theirs[2];
+            PeerHandle theirs[2];
             std::memcpy(theirs, host.data() + record * (size_t)p + 16, sizeof(theirs));
             void* inbox = nullptr;
             void* flags = nullptr;
-            ok = cudaIpcOpenMemHandle(&inbox, theirs[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            if (ok) comm->opened[comm->nopened++] = inbox;
-            ok = ok && cudaIpcOpenMemHandle(&flags, theirs[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            if (ok) comm->opened[comm->nopened++] = flags;
+            ok = open_handle(ctx, theirs[0], &inbox, comm->opened) && open_handle(ctx, theirs[1], &flags, comm->opened);
             comm->peer_inbox[p] = (double*)inbox;
             comm->peer_flags[p] = (int*)flags;
         }
@@ -321,15 +356,15 @@ int comm_map_peer_buffers(Context* ctx, int count, void* const* local, void** pe
     }
     unmap_peer_buffers(comm);
     bool fine = true;
-    std::vector<cudaIpcMemHandle_t> mine((size_t)count);
-    for (int b = 0; b < count; b++) fine = fine && cudaIpcGetMemHandle(&mine[(size_t)b], local[b]) == cudaSuccess;
+    std::vector<PeerHandle> mine((size_t)count);
+    for (int b = 0; b < count; b++) fine = fine && export_handle(ctx, local[b], &mine[(size_t)b]);
     cudaGetLastError();
-    const size_t record = 16 + (size_t)count * sizeof(cudaIpcMemHandle_t);
+    const size_t record = 16 + (size_t)count * sizeof(PeerHandle);
     std::vector<unsigned char> host(record * (size_t)nranks, 0);
     LUMOL_CUDA_CHECK(ctx, comm->handle_staging.reserve(record * (size_t)nranks));
     unsigned char* own = host.data() + record * (size_t)ctx->rank;
     own[0] = fine ? 1 : 0;
-    std::memcpy(own + 16, mine.data(), (size_t)count * sizeof(cudaIpcMemHandle_t));
+    std::memcpy(own + 16, mine.data(), (size_t)count * sizeof(PeerHandle));
     LUMOL_CUDA_CHECK(ctx, cudaMemcpyAsync(comm->handle_staging.ptr + record * (size_t)ctx->rank, own, record, cudaMemcpyHostToDevice,
                                           ctx->stream));
     NCCL_CHECK(ctx, g_nccl.all_gather(comm->handle_staging.ptr + record * (size_t)ctx->rank, comm->handle_staging.ptr, record, NCCL_CHAR,
@@ -344,14 +379,11 @@ int comm_map_peer_buffers(Context* ctx, int count, void* const* local, void** pe
                 table[(size_t)b * PEER_MAX_RANKS + p] = local[b];
                 continue;
             }
-            cudaIpcMemHandle_t theirs;
-            std::memcpy(&theirs, host.data() + record * (size_t)p + 16 + (size_t)b * sizeof(cudaIpcMemHandle_t), sizeof(theirs));
+            PeerHandle theirs;
+            std::memcpy(&theirs, host.data() + record * (size_t)p + 16 + (size_t)b * sizeof(PeerHandle), sizeof(theirs));
             void* pointer = nullptr;
-            fine = cudaIpcOpenMemHandle(&pointer, theirs, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            if (fine) {
-                comm->mapped.push_back(pointer);
-                table[(size_t)b * PEER_MAX_RANKS + p] = pointer;
-            }
+            fine = open_handle(ctx, theirs, &pointer, comm->mapped);
+            if (fine) table[(size_t)b * PEER_MAX_RANKS + p] = pointer;
         }
     }
     cudaGetLastError();
@@ -424,6 +456,9 @@ extern "C" int32_t lumol_cuda_comm_unique_id(uint8_t id[128]) {
 extern "C" int32_t lumol_cuda_comm_init(lumol_cuda_context* ctx, int32_t nranks, int32_t rank, const uint8_t id[128]) {
     if (ctx == nullptr) return LUMOL_CUDA_ERROR_INVALID_ARGUMENT;
     Context* c = &ctx->impl;
+    if (ctx->multi != nullptr) {
+        return c->fail(LUMOL_CUDA_ERROR_STATE, "lumol_cuda_comm_init: a multi-device context already shards over its own devices");
+    }
     if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || (nranks > 1 && id == nullptr)) {
         return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "lumol_cuda_comm_init: bad rank %d of %d", rank, nranks);
     }

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,19 @@ struct DeviceBuffer {
         cudaError_t err = cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T));
         if (err == cudaSuccess) {
             capacity = want;
+        }
+        return err;
+    }
+
+    // like reserve, and a buffer that had to be (re)allocated starts as zeros: for tables whose tails are read ahead
+    // and discarded (list words behind the walked prefix, run slots behind the run count)
+    cudaError_t reserve_zeroed(size_t count, cudaStream_t stream) {
+        if (count <= capacity) {
+            return cudaSuccess;
+        }
+        cudaError_t err = reserve(count);
+        if (err == cudaSuccess) {
+            err = cudaMemsetAsync(ptr, 0, capacity * sizeof(T), stream);
         }
         return err;
     }
@@ -244,6 +258,7 @@ struct Context {
 
     // ---- measurement -----------------------------------------------------------------------------------
     bool profiling = false;
+    bool discard_downloads = false;  // child rank > 0 of a multi-device context: get_* calls run their collectives, copy nothing
     Timer timer;
     int64_t launches = 0;
     KernelClock clk_pair, clk_kspace, clk_integrate, clk_neighbor, clk_comm;
@@ -353,6 +368,21 @@ int measure_copy_bandwidth(Context* ctx, double* gbs);                          
 }  // namespace lumol
 
 // The opaque handle of include/lumol_cuda.h.
+namespace lumol {
+struct Multi;
+}
+
 struct lumol_cuda_context {
     lumol::Context impl;
+    lumol::Multi* multi = nullptr;  // lumol_cuda_create_multi: this context only fans calls out to one child per device
 };
+
+namespace lumol {
+// multi.cu
+typedef std::function<int32_t(lumol_cuda_context*, int)> MultiTask;
+int32_t multi_run(lumol_cuda_context* parent, const MultiTask& task);  // on every child at once; first failure, else child 0's status
+int multi_size(const lumol_cuda_context* parent);
+lumol_cuda_context* multi_child(const lumol_cuda_context* parent, int rank);
+void multi_destroy(lumol_cuda_context* parent);
+void set_create_error(const char* message);  // api.cu: the text lumol_cuda_last_error(NULL) returns
+}  // namespace lumol

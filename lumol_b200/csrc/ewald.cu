@@ -15,6 +15,7 @@
 #include "context.hpp"
 
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
 
 namespace lumol {
@@ -126,6 +127,14 @@ int ewald_prepare(Context* ctx) {
                 rows.push_back(row);
             }
         }
+        // The k list is a sphere: row (h, k) only has |l| <= sqrt(kmax^2 - h^2 - k^2).  Rows in order of decreasing reach make
+        // the row tiles of the tiled kernels homogeneous, so that a tile's bound on |l| (largest reach among its rows) is
+        // tight and never grows from one tile to the next.  Nothing else depends on the order of this table.
+        auto reach_of = [](const KRow& row) {
+            const int l_lo = (int)(short)(row.l_lo_hi & 0xffff), l_hi = row.l_lo_hi >> 16;
+            return std::max(std::abs(l_lo), std::abs(l_hi));
+        };
+        std::stable_sort(rows.begin(), rows.end(), [&](const KRow& x, const KRow& y) { return reach_of(x) > reach_of(y); });
         ctx->krows_regular = regular && !rows.empty();
         ctx->nkrows = (int64_t)rows.size();
         LUMOL_CUDA_CHECK(ctx, ctx->krows.reserve(rows.size() + 1));
@@ -488,6 +497,40 @@ struct TiledRhoArgs {
 // (TK_ATOMS x rows per block): in the main loop every thread of a warp reads the same atom, so rows and |l|
 // values must be the fastest index for the reads to be conflict-free.
 // grid: (row tiles, atom chunks)
+// barrier + maximum of `value` over the block (through one shared word the caller provides)
+__device__ __forceinline__ int block_max_barrier(int value, int* shared_word) {
+    if (threadIdx.x == 0) *shared_word = 0;
+    __syncthreads();
+    value = __reduce_max_sync(0xffffffffu, value);
+    if ((threadIdx.x & 31) == 0 && value > 0) atomicMax(shared_word, value);
+    __syncthreads();
+    return *shared_word;
+}
+
+// The contraction of one atom tile for a thread whose block needs only the first NL of its TK_TL groups of |l| values
+// (rows are sorted by reach: a block's rows all stop below NL * lq).
+template <int NL>
+__device__ __forceinline__ void rho_contract(double (&acc)[TK_TR][TK_TL][4], const double2* __restrict__ arow,
+                                             const double2* __restrict__ bcol, int rows_per_block, int row_groups, int lpad, int lq_count) {
+#pragma unroll 2
+    for (int atom = 0; atom < TK_ATOMS; atom++) {
+        double2 av[TK_TR], bv[NL];
+#pragma unroll
+        for (int r = 0; r < TK_TR; r++) av[r] = arow[(size_t)atom * rows_per_block + r * row_groups];
+#pragma unroll
+        for (int l = 0; l < NL; l++) bv[l] = bcol[(size_t)atom * 3 * lpad + l * lq_count];
+#pragma unroll
+        for (int r = 0; r < TK_TR; r++)
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                acc[r][l][0] = fma(av[r].x, bv[l].x, acc[r][l][0]);
+                acc[r][l][1] = fma(av[r].y, bv[l].y, acc[r][l][1]);
+                acc[r][l][2] = fma(av[r].x, bv[l].y, acc[r][l][2]);
+                acc[r][l][3] = fma(av[r].y, bv[l].x, acc[r][l][3]);
+            }
+    }
+}
+
 __global__ void __launch_bounds__(TK_THREADS, 1) ewald_rho_tiled_kernel(TiledRhoArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lpad = a.lq * TK_TL;
@@ -498,6 +541,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) ewald_rho_tiled_kernel(TiledRho
 
     const int t = threadIdx.x;
     const int row0 = blockIdx.x * rows_per_block;
+    __shared__ int s_reach;
+    int reach = 0;
     for (int r = t; r < rows_per_block; r += TK_THREADS) {
         KRow row;
         row.h = row.k = 0;
@@ -505,8 +550,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) ewald_rho_tiled_kernel(TiledRho
         row.l_lo_hi = (0 << 16) | 1;  // empty interval: l_lo = 1 > l_hi = 0
         if (row0 + r < a.nrows) row = a.rows[row0 + r];
         s_rows[r] = row;
+        const int l_lo = (int)(short)(row.l_lo_hi & 0xffff), l_hi = row.l_lo_hi >> 16;
+        if (l_lo <= l_hi) reach = max(reach, max(abs(l_lo), abs(l_hi)));
     }
-    __syncthreads();  // also for blocks whose atom chunk is empty: they still write zeros for their rows
+    // groups of |l| values the rows of this block reach: group j holds |l| in [j * lq, (j + 1) * lq)
+    const int block_reach = block_max_barrier(reach, &s_reach);  // (barrier: also for blocks whose atom chunk is empty)
+    const int ngroups = min(TK_TL, block_reach / a.lq + 1);
     const int lq = t % a.lq, rg = t / a.lq;
     const bool worker = rg < a.row_groups;
 
@@ -570,22 +619,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) ewald_rho_tiled_kernel(TiledRho
             // a warp read consecutive 16-byte words
             const double2* arow = amat + rg;
             const double2* bcol = table + 2 * lpad + lq;
-#pragma unroll 2
-            for (int atom = 0; atom < TK_ATOMS; atom++) {
-                double2 av[TK_TR], bv[TK_TL];
-#pragma unroll
-                for (int r = 0; r < TK_TR; r++) av[r] = arow[(size_t)atom * rows_per_block + r * a.row_groups];
-#pragma unroll
-                for (int l = 0; l < TK_TL; l++) bv[l] = bcol[(size_t)atom * 3 * lpad + l * a.lq];
-#pragma unroll
-                for (int r = 0; r < TK_TR; r++)
-#pragma unroll
-                    for (int l = 0; l < TK_TL; l++) {
-                        acc[r][l][0] = fma(av[r].x, bv[l].x, acc[r][l][0]);
-                        acc[r][l][1] = fma(av[r].y, bv[l].y, acc[r][l][1]);
-                        acc[r][l][2] = fma(av[r].x, bv[l].y, acc[r][l][2]);
-                        acc[r][l][3] = fma(av[r].y, bv[l].x, acc[r][l][3]);
-                    }
+            switch (ngroups) {
+                case 1: rho_contract<1>(acc, arow, bcol, rows_per_block, a.row_groups, lpad, a.lq); break;
+                case 2: rho_contract<2>(acc, arow, bcol, rows_per_block, a.row_groups, lpad, a.lq); break;
+                case 3: rho_contract<3>(acc, arow, bcol, rows_per_block, a.row_groups, lpad, a.lq); break;
+                default: rho_contract<TK_TL>(acc, arow, bcol, rows_per_block, a.row_groups, lpad, a.lq); break;
             }
         }
     }
@@ -722,14 +760,17 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
         for (int x = 0; x < TF_TA; x++) sh[x] = sk[x] = sl[x] = 0.0;
 
         const double2* ez = ez_table + ag;
+        int stage_m = lp;  // |l| values of the G tile to stage
         for (int tile = row_lo; tile < row_hi; tile += TF_ROWS) {
             __syncthreads();
             const int nrows = min(TF_ROWS, row_hi - tile);
             {
+                // rows come in order of decreasing reach: no row of this tile reaches beyond the bound of the previous tile
                 const double* src = a.gmat + (size_t)tile * lp * 4;
-                for (int w = t; w < TF_ROWS * lp * 4; w += TF_THREADS) {
-                    const int r = w / (lp * 4), c = w - r * (lp * 4);
-                    gtile[r * gstride + c] = r < nrows ? src[w] : 0.0;
+                const int columns = stage_m * 4;
+                for (int w = t; w < TF_ROWS * columns; w += TF_THREADS) {
+                    const int r = w / columns, c = w - r * columns;
+                    gtile[r * gstride + c] = r < nrows ? src[(size_t)r * lp * 4 + c] : 0.0;
                 }
             }
             if (t < TF_ROWS) {  // exactly the first warp
@@ -749,6 +790,7 @@ __global__ void __launch_bounds__(TF_ATOMS / TF_TA * TF_ROW_GROUPS) ewald_force_
             }
             __syncthreads();
             const int mend = s_mend;
+            stage_m = mend;
             double w0[TF_TR][TF_TA][2], w1[TF_TR][TF_TA][2];
 #pragma unroll
             for (int r = 0; r < TF_TR; r++)

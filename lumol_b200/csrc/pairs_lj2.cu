@@ -787,12 +787,19 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
             continue;
         }
         for (int b = 0; b < BUCKETS; b++) last[b][t] = 0;
-        for (int w = 0; w < nwords; w++) {
-            const uint4 word = words[w * 32];
-            const unsigned e[4] = {word.x, word.y, word.z, word.w};
+        // (four words in flight: the loop is bound by the latency of these loads otherwise)
+        for (int w0 = 0; w0 < nwords; w0 += 4) {
+            uint4 ahead[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (4 * w + q < count) last[bucket_of(e[q])][t]++;
+            for (int u = 0; u < 4; u++) ahead[u] = words[min(w0 + u, nwords - 1) * 32];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int w = w0 + u;
+                const unsigned e[4] = {ahead[u].x, ahead[u].y, ahead[u].z, ahead[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (4 * w + q < count) last[bucket_of(e[q])][t]++;
+                }
             }
         }
         int running = 0;
@@ -802,14 +809,20 @@ __global__ void __launch_bounds__(REORDER2_THREADS)
             last[b][t] = (COUNTER)running;
             if (b >= 15) cum_levels[(size_t)s_i * LJ2_LEVELS + (b - 15)] = (unsigned short)running;
         }
-        for (int w = 0; w < nwords; w++) {
-            const uint4 word = words[w * 32];
-            const unsigned e[4] = {word.x, word.y, word.z, word.w};
+        for (int w0 = 0; w0 < nwords; w0 += 4) {
+            uint4 ahead[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (4 * w + q < count) {
-                    const int position = cursor[bucket_of(e[q])][t]++;
-                    sorted[position * REORDER2_THREADS + t] = (unsigned short)(e[q] & 0xffffu);
+            for (int u = 0; u < 4; u++) ahead[u] = words[min(w0 + u, nwords - 1) * 32];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int w = w0 + u;
+                const unsigned e[4] = {ahead[u].x, ahead[u].y, ahead[u].z, ahead[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (4 * w + q < count) {
+                        const int position = cursor[bucket_of(e[q])][t]++;
+                        sorted[position * REORDER2_THREADS + t] = (unsigned short)(e[q] & 0xffffu);
+                    }
                 }
             }
         }
@@ -1498,7 +1511,7 @@ static int lj2_plan(Context* ctx, bool sharded, const UnitShape& shape, double c
         return ctx->fail(LUMOL_CUDA_ERROR_UNSUPPORTED, "too many atoms per GPU for the neighbour list (%d)", n);
     }
     LUMOL_CUDA_CHECK(ctx, ctx->nl_flags.reserve(16));
-    LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve(P.stride * (size_t)P.capacity));
+    LUMOL_CUDA_CHECK(ctx, ctx->nlist.reserve_zeroed(P.stride * (size_t)P.capacity, ctx->stream));
     LUMOL_CUDA_CHECK(ctx, ctx->ncount.reserve(P.stride));
     LUMOL_CUDA_CHECK(ctx, ctx->xref.reserve((size_t)3 * n));
     LUMOL_CUDA_CHECK(ctx, ctx->cell_of.reserve((size_t)2 * n));  // cell_of + slot_of
@@ -1515,7 +1528,7 @@ static int lj2_plan(Context* ctx, bool sharded, const UnitShape& shape, double c
     LUMOL_CUDA_CHECK(ctx, ctx->frame_atom.reserve(P.fstride));
     LUMOL_CUDA_CHECK(ctx, ctx->frame_pos.reserve(2 * (size_t)shape.width * P.fstride));  // two copies: a sharded run alternates with the step parity
     LUMOL_CUDA_CHECK(ctx, ctx->blk_header.reserve((size_t)P.nunits));
-    LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve((size_t)P.nunits * LJ2_MAX_RUNS));
+    LUMOL_CUDA_CHECK(ctx, ctx->blk_entries.reserve_zeroed((size_t)P.nunits * LJ2_MAX_RUNS, ctx->stream));
     LUMOL_CUDA_CHECK(ctx, ctx->cum_levels.reserve(P.stride * LJ2_LEVELS));
     P.deferred_capacity = n * DEFERRED_PER_ATOM + 1024;
     ctx->deferred_capacity = P.deferred_capacity;
@@ -2278,11 +2291,7 @@ static int sorted_md_run_checked(Context* ctx, int64_t nsteps) {
                 h.frame[r] = (double*)peers[2 * PEER_MAX_RANKS + r] + (size_t)parity * 3 * P.fstride;
                 h.sync[r] = (int*)peers[3 * PEER_MAX_RANKS + r];
             }
-            {
-                ScopedClock halo_clock(ctx, &ctx->clk_kspace);  // DIAGNOSTIC: halo copies timed apart from the waits
-                sre_halo_kernel<<<ctx->sm_count, SRE_THREADS, 0, ctx->stream>>>(h);
-                ctx->clk_kspace.launches++;
-            }
+            sre_halo_kernel<<<ctx->sm_count, SRE_THREADS, 0, ctx->stream>>>(h);
             ctx->launches++;
             ctx->clk_comm.launches++;
             sre_sync_kernel<<<1, 32, 0, ctx->stream>>>(ctx->nranks, epoch, parity, (float)(0.25 * P.skin * P.skin), ctx->sre_sync.ptr, flags,

@@ -41,12 +41,17 @@ def _pair_record(interaction, table_id):
 
 
 class DeviceSystem:
-    """Owns a ``lumol_cuda_context`` and mirrors one ``System`` into it."""
+    """Owns a ``lumol_cuda_context`` and mirrors one ``System`` into it.  ``device`` is a CUDA ordinal, or a sequence of
+    ordinals for one context sharded over several devices of this process (``lumol_cuda_create_multi``)."""
 
     def __init__(self, device=0):
         self.lib = _ffi.library()
         self.ctx = ctypes.c_void_p()
-        status = self.lib.lumol_cuda_create(device, ctypes.byref(self.ctx))
+        if isinstance(device, (list, tuple)):
+            devices = (ctypes.c_int32 * len(device))(*device)
+            status = self.lib.lumol_cuda_create_multi(devices, len(device), ctypes.byref(self.ctx))
+        else:
+            status = self.lib.lumol_cuda_create(device, ctypes.byref(self.ctx))
         if status < 0:
             raise _ffi.LumolCudaError(status, _ffi.last_error(None))
         self._synced_version = None

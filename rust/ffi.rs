@@ -107,6 +107,7 @@ pub const LUMOL_CUDA_INTEGRATOR_ANISO_BERENDSEN_BAROSTAT: i32 = 4;
 extern "C" {
     pub fn lumol_cuda_abi_version() -> i32;
     pub fn lumol_cuda_create(device: i32, ctx: *mut *mut lumol_cuda_context) -> i32;
+    pub fn lumol_cuda_create_multi(devices: *const i32, ndevices: i32, ctx: *mut *mut lumol_cuda_context) -> i32;
     pub fn lumol_cuda_destroy(ctx: *mut lumol_cuda_context) -> i32;
     pub fn lumol_cuda_last_error(ctx: *const lumol_cuda_context) -> *const c_char;
     pub fn lumol_cuda_set_cell(ctx: *mut lumol_cuda_context, cell: *const f64, shape: i32) -> i32;

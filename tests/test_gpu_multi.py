@@ -23,3 +23,17 @@ def test_ranks_match_one_rank(nranks):
     result = subprocess.run(command, capture_output=True, text=True, timeout=1500)
     assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-4000:]
     assert "multi-GPU check ok" in result.stdout
+
+
+@pytest.mark.parametrize("ndevices", [2, 8])
+def test_one_process_many_devices(ndevices):
+    """tools/multi_device_check.py: a context made by lumol_cuda_create_multi (one host process, one library thread per
+    device) against a single-device context: forces / energies / virials, MD across rebuilds, error propagation."""
+    import torch
+
+    if torch.cuda.device_count() < ndevices:
+        pytest.skip(f"needs {ndevices} GPUs")
+    command = [sys.executable, os.path.join(ROOT, "tools", "multi_device_check.py"), str(ndevices)]
+    result = subprocess.run(command, capture_output=True, text=True, timeout=1500)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-4000:]
+    assert "multi-device check ok" in result.stdout
