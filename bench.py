@@ -443,17 +443,22 @@ def measure(args, env, workload, lattice_text, steps, warmup, with_e2e, with_cpu
         p_out = ctypes.cast(host_forces.data_ptr(), ctypes.POINTER(ctypes.c_double))
         e2e_steps = max(3, min(steps, 20 if n > 2_000_000 else 50))
 
-        # sharded: every rank uploads the positions (its neighbours' atoms are among them) and reads back only the block
-        # of forces it evaluated; the union of the blocks is the force array of the host-side integrator
+        # sharded: every rank uploads the positions of the block of atoms its host-side integrator advances (the ranks
+        # exchange the blocks on the device over NVLink) and reads back the forces of that block; the union of the blocks
+        # is the state of the run
         first, owned = ctypes.c_int64(0), ctypes.c_int64(n)
         if world > 1:
             _ffi.check(ctx, lib.lumol_cuda_owned_range(ctx, ctypes.byref(first), ctypes.byref(owned)))
         what = _ffi.FORCES | (_ffi.OWNED_FORCES if world > 1 else 0)
+        p_owned = ctypes.cast(host_positions.data_ptr() + 24 * int(first.value), ctypes.POINTER(ctypes.c_double))
 
         def e2e_step():
             # what lumol's VelocityVerlet::integrate does around system.forces() (integrators.rs:44-69) when the
             # host arrays are the truth: positions in, forces out
-            _ffi.check(ctx, lib.lumol_cuda_set_positions(ctx, p_in))
+            if world > 1:
+                _ffi.check(ctx, lib.lumol_cuda_set_owned_positions(ctx, p_owned))
+            else:
+                _ffi.check(ctx, lib.lumol_cuda_set_positions(ctx, p_in))
             _ffi.check(ctx, lib.lumol_cuda_compute(ctx, what, _ffi.PART_ALL, p_out, None, None))
 
         for _ in range(3):
@@ -466,10 +471,13 @@ def measure(args, env, workload, lattice_text, steps, warmup, with_e2e, with_cpu
         barrier()
         e2e_ms = max_over_ranks(start.elapsed_time(stop))
         e2e = {
-            "value": n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * int(owned.value),
+            # bytes of the whole job (all ranks together); each rank moves its own block over its own PCIe link
+            "value": n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
+            "bytes_per_step_per_rank": 24 * int(owned.value),
             "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-            "call": "lumol_cuda_set_positions + lumol_cuda_compute(FORCES) with pinned host buffers, per rank"
-                    + (" (every rank uploads all positions and downloads the forces of its own block of atoms)" if world > 1 else ""),
+            "call": ("lumol_cuda_set_positions + lumol_cuda_compute(FORCES) with pinned host buffers" if world == 1 else
+                     "per rank: lumol_cuda_set_owned_positions (own block up, blocks exchanged over NVLink) + "
+                     "lumol_cuda_compute(FORCES | OWNED_FORCES) (own block down), pinned host buffers"),
         }
         # restore the device-resident state of the MD run
         _ffi.check(ctx, lib.lumol_cuda_set_positions(ctx, _ffi.as_double_pointer(positions)))

@@ -213,6 +213,11 @@ int32_t lumol_cuda_set_cell(lumol_cuda_context* ctx, const double cell[9], int32
 int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, const double* position, const double* velocity,
                                  const double* mass, const double* charge, const uint32_t* kind);
 int32_t lumol_cuda_set_positions(lumol_cuda_context* ctx, const double* position);
+/* Sharded contexts (lumol_cuda_comm_init): upload only the positions of this rank's block of atoms (count x 3 doubles,
+ * lumol_cuda_owned_range); the ranks exchange their blocks on the device over NVLink.  Collective: every rank calls it.
+ * Host-driven steps then move 24 B per owned atom over each PCIe link instead of 24 B per atom.  On an unsharded context
+ * it is lumol_cuda_set_positions. */
+int32_t lumol_cuda_set_owned_positions(lumol_cuda_context* ctx, const double* owned_position);
 int32_t lumol_cuda_set_velocities(lumol_cuda_context* ctx, const double* velocity);
 int32_t lumol_cuda_get_positions(lumol_cuda_context* ctx, double* position);
 int32_t lumol_cuda_get_velocities(lumol_cuda_context* ctx, double* velocity);

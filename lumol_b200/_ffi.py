@@ -119,6 +119,7 @@ SIGNATURES = {
     "lumol_cuda_set_cell": (_c.c_int32, [_ctx, _dp, _c.c_int32]),
     "lumol_cuda_set_particles": (_c.c_int32, [_ctx, _c.c_int64, _dp, _dp, _dp, _dp, _c.POINTER(_c.c_uint32)]),
     "lumol_cuda_set_positions": (_c.c_int32, [_ctx, _dp]),
+    "lumol_cuda_set_owned_positions": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_set_velocities": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_get_positions": (_c.c_int32, [_ctx, _dp]),
     "lumol_cuda_owned_range": (_c.c_int32, [_ctx, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),

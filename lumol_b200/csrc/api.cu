@@ -260,8 +260,37 @@ extern "C" int32_t lumol_cuda_set_particles(lumol_cuda_context* ctx, int64_t n, 
     return LUMOL_CUDA_SUCCESS;
 }
 
+extern "C" int32_t lumol_cuda_set_owned_positions(lumol_cuda_context* ctx, const double* owned_position) {
+    if (ctx != nullptr && ctx->multi != nullptr) return ctx->impl.fail(LUMOL_CUDA_ERROR_STATE, "a multi-device context takes whole arrays: lumol_cuda_set_positions");
+    CTX_OR_FAIL(ctx);
+    int64_t lo, hi;
+    c->owned_range(c->n, lo, hi);
+    if (owned_position == nullptr && hi > lo) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null positions");
+    PositionsChange change(c);
+    if (hi > lo) {
+        int status = upload(c, c->position.ptr + 3 * lo, owned_position, (size_t)(hi - lo) * 3 * sizeof(double));
+        if (status) return status;
+    }
+    // the blocks of the other ranks arrive over NVLink instead of over every rank's PCIe link
+    if (c->nranks > 1) {
+        int status = comm_allgather_positions(c);
+        if (status) return status;
+    }
+    LUMOL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LUMOL_CUDA_SUCCESS;
+}
+
 extern "C" int32_t lumol_cuda_set_positions(lumol_cuda_context* ctx, const double* position) {
-    MULTI_FAN(ctx, lumol_cuda_set_positions(child, position));
+    if (ctx != nullptr && ctx->multi != nullptr) {
+        // every device uploads the block of atoms it owns; the devices exchange the blocks among themselves
+        if (position == nullptr) return ctx->impl.fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null positions");
+        return multi_run(ctx, [=](lumol_cuda_context* child, int rank) -> int32_t {
+            (void)rank;
+            int64_t lo, hi;
+            child->impl.owned_range(child->impl.n, lo, hi);
+            return lumol_cuda_set_owned_positions(child, position + 3 * lo);
+        });
+    }
     CTX_OR_FAIL(ctx);
     if (position == nullptr && c->n > 0) return c->fail(LUMOL_CUDA_ERROR_INVALID_ARGUMENT, "null positions");
     PositionsChange change(c);

@@ -116,6 +116,7 @@ extern "C" {
         charge: *const f64, kind: *const u32,
     ) -> i32;
     pub fn lumol_cuda_set_positions(ctx: *mut lumol_cuda_context, position: *const f64) -> i32;
+    pub fn lumol_cuda_set_owned_positions(ctx: *mut lumol_cuda_context, owned_position: *const f64) -> i32;
     pub fn lumol_cuda_set_velocities(ctx: *mut lumol_cuda_context, velocity: *const f64) -> i32;
     pub fn lumol_cuda_get_positions(ctx: *mut lumol_cuda_context, position: *mut f64) -> i32;
     pub fn lumol_cuda_get_velocities(ctx: *mut lumol_cuda_context, velocity: *mut f64) -> i32;

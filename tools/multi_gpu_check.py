@@ -41,6 +41,28 @@ def check(name, system, rank, world, local_rank, kspace=None):
     virial_error = np.abs(sharded.virial - single.virial).max() / np.abs(single.virial).max()
     assert force_error < 1e-12 and energy_error < 1e-12 and virial_error < 1e-12, (name, force_error, energy_error, virial_error)
 
+    # host-driven step of a sharded run: every rank uploads only its block of positions (the blocks travel between the
+    # devices) and downloads only its block of forces
+    import ctypes
+
+    moved = np.ascontiguousarray(system.positions + 0.01 * np.sin(np.arange(system.size() * 3).reshape(-1, 3)))
+    lib = sharded_device.lib
+    first, count = ctypes.c_int64(0), ctypes.c_int64(0)
+    _ffi.check(sharded_device.ctx, lib.lumol_cuda_owned_range(sharded_device.ctx, ctypes.byref(first), ctypes.byref(count)))
+    lo, hi = first.value, first.value + count.value
+    block = np.ascontiguousarray(moved[lo:hi])
+    _ffi.check(sharded_device.ctx, lib.lumol_cuda_set_owned_positions(sharded_device.ctx, _ffi.as_double_pointer(block)))
+    owned_forces = np.zeros((max(hi - lo, 1), 3))
+    _ffi.check(sharded_device.ctx, lib.lumol_cuda_compute(sharded_device.ctx, _ffi.FORCES | _ffi.OWNED_FORCES, _ffi.PART_ALL,
+                                                          _ffi.as_double_pointer(owned_forces), None, None))
+    _ffi.check(single_device.ctx, lib.lumol_cuda_set_positions(single_device.ctx, _ffi.as_double_pointer(moved)))
+    reference = single_device.compute(forces=True).forces
+    owned_error = np.abs(owned_forces[:hi - lo] - reference[lo:hi]).max() / max(np.abs(reference).max(), 1e-300) if hi > lo else 0.0
+    assert owned_error < 1e-12, (name, "owned block", owned_error)
+    original = np.ascontiguousarray(system.positions, dtype=np.float64)
+    for device in (single_device, sharded_device):
+        _ffi.check(device.ctx, lib.lumol_cuda_set_positions(device.ctx, _ffi.as_double_pointer(original)))
+
     # ten device-resident MD steps: sharded trajectory equals the single-GPU one to summation-order noise
     def run(device):
         lib, ctx = device.lib, device.ctx
