@@ -18,6 +18,7 @@ template <typename T>
 struct DeviceBuffer {
     T* ptr = nullptr;
     size_t capacity = 0;
+    bool zero_filled = false;  // the current allocation was cleared by reserve_zeroed
 
     cudaError_t reserve(size_t count) {
         if (count <= capacity) {
@@ -29,6 +30,7 @@ struct DeviceBuffer {
             capacity = 0;
         }
         size_t want = count + count / 8 + 32;
+        zero_filled = false;
         cudaError_t err = cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T));
         if (err == cudaSuccess) {
             capacity = want;
@@ -39,12 +41,14 @@ struct DeviceBuffer {
     // like reserve, and a buffer that had to be (re)allocated starts as zeros: for tables whose tails are read ahead
     // and discarded (list words behind the walked prefix, run slots behind the run count)
     cudaError_t reserve_zeroed(size_t count, cudaStream_t stream) {
-        if (count <= capacity) {
+        if (count <= capacity && zero_filled) {
             return cudaSuccess;
         }
         cudaError_t err = reserve(count);
         if (err == cudaSuccess) {
+            // (also a buffer that another path allocated earlier with plain reserve())
             err = cudaMemsetAsync(ptr, 0, capacity * sizeof(T), stream);
+            zero_filled = err == cudaSuccess;
         }
         return err;
     }

@@ -69,6 +69,14 @@ def test_no_cpu_fallback_without_device():
     status = lib.lumol_cuda_create(0, ctypes.byref(ctx))
     assert status == _ffi.ERROR_NO_DEVICE
     assert "no CPU fallback" in _ffi.last_error(None)
+    # the multi-device constructor refuses the same way, and checks its arguments before touching a device
+    devices = (ctypes.c_int32 * 2)(0, 1)
+    assert lib.lumol_cuda_create_multi(devices, 2, ctypes.byref(ctx)) == _ffi.ERROR_NO_DEVICE
+    assert "no CPU fallback" in _ffi.last_error(None)
+    twice = (ctypes.c_int32 * 2)(0, 0)
+    assert lib.lumol_cuda_create_multi(twice, 2, ctypes.byref(ctx)) == _ffi.ERROR_INVALID_ARGUMENT
+    assert "listed twice" in _ffi.last_error(None)
+    assert lib.lumol_cuda_create_multi(devices, 0, ctypes.byref(ctx)) == _ffi.ERROR_INVALID_ARGUMENT
     import lumol_b200 as lumol
     import systems
 
