@@ -392,6 +392,13 @@ struct Build2Args {
 
 constexpr int BUILD2_CHUNKS = 8;
 
+// MUFU.RSQ without the denormal pre-scaling of rsqrtf (squared distances of distinct atoms are far from denormal)
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // One warp per 32-atom chunk of a home cell, one lane per atom; the 27 neighbour cells are streamed, eight candidates
 // (uniform addresses) loaded before the first is tested.  Survivors are collected in a per-lane shared-memory buffer and
 // written as whole 16-byte words (four entries).
@@ -402,6 +409,7 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
     const int item_lo = global_warp * a.cells_per_warp;
     const int item_hi = min(a.ncells * BUILD2_CHUNKS, item_lo + a.cells_per_warp);
     unsigned* mine = pending[threadIdx.x];
+    const float level_origin = -a.cutoff * a.inv_delta;
 
     for (int item = item_lo; item < item_hi; item++) {
         const int first_chunk = item / a.ncells, c = item - first_chunk * a.ncells;
@@ -492,7 +500,9 @@ __device__ __forceinline__ void list_build2_phase(int vb, const Build2Args& a, c
                             const float r2 = ddx * ddx + ddy * ddy + ddz * ddz;
                             if (r2 < a.radius2 && s_j != s_i && s_j < s1) {
                                 if (count < a.capacity) {
-                                    int level = (int)floorf((sqrtf(r2) - a.cutoff) * a.inv_delta);
+                                    // r2 * rsqrt(r2) is within a few ulp of the root: the levels are walked with a margin of
+                                    // 2e-3 A (Lj2Args::margin), five orders above that
+                                    int level = (int)floorf(fmaf(r2 * rsqrt_approx(r2), a.inv_delta, level_origin));
                                     level = max(0, min(LJ2_LEVELS - 1, level));
                                     unsigned value = (unsigned)(factor * (tag + s_j));
                                     if (FLAGS & 1) {
