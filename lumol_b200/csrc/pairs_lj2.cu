@@ -1531,7 +1531,7 @@ static int lj2_plan(Context* ctx, bool sharded, const UnitShape& shape, double c
     LUMOL_CUDA_CHECK(ctx, ctx->order.reserve((size_t)2 * n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_f32.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->sorted_cell.reserve((size_t)n));
-    LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve(P.stride));
+    LUMOL_CUDA_CHECK(ctx, ctx->self_local.reserve_zeroed(P.stride, ctx->stream));
     LUMOL_CUDA_CHECK(ctx, ctx->ext_start.reserve(2 * ((size_t)P.next + 2)));  // offsets, then the padded counts
     LUMOL_CUDA_CHECK(ctx, ctx->fidx.reserve((size_t)n));
     LUMOL_CUDA_CHECK(ctx, ctx->kshift.reserve((size_t)n));

@@ -116,3 +116,14 @@ pub fn restriction_code(restriction: lumol_core::energy::PairRestriction) -> (i3
 //         check(ctx, unsafe { lumol_cuda_set_coulomb_wolf(ctx, self.cutoff, restriction, scale14) });
 //         true                                                            // alpha = pi / cutoff inside, wolf.rs:68-84
 //     }
+
+// ---- lumol-core/src/sys/system.rs ------------------------------------------------------------------------------------
+//
+//     /// Bumped by everything that changes what the device mirrors apart from positions, velocities and the cell:
+//     /// `add_molecule` (system.rs:80), `Configuration::add_bond` / `remove_molecule`, `particles_mut()` when kinds,
+//     /// masses or charges are written, and every `set_*_potential` / `add_global_potential` (system.rs:122-175).
+//     pub fn structure_version(&self) -> u64 { self.structure_version }
+//
+// `device.rs::sync` compares it with the version of its last upload; positions are uploaded at every evaluation (the
+// host arrays are the truth in host-driven mode), everything else only when the counter moved.  The Python mirror does
+// the same with `System._version` (lumol_b200/sys.py, lumol_b200/device.py).
