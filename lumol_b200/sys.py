@@ -167,6 +167,7 @@ class Molecule:
 
 _SINGLE_FAR = np.full((1, 1), BOND_FAR, dtype=np.uint8)
 _SINGLE_FAR.setflags(write=False)
+_NO_CONNECTIONS = frozenset()
 
 
 class Bonding:
@@ -182,6 +183,22 @@ class Bonding:
         self.dihedrals = set()
         # single atoms share one read-only matrix (systems with millions of free atoms)
         self.distances = _SINGLE_FAR if end - start == 1 else np.full((end - start, end - start), BOND_FAR, dtype=np.uint8)
+
+    @classmethod
+    def single(cls, start):
+        """A one-atom molecule without the three per-instance sets: millions of free atoms (liquid argon) share one
+        immutable empty set; `bonds_for_update` swaps in a real set before the first bond is added."""
+        self = object.__new__(cls)
+        self.start = start
+        self.end = start + 1
+        self.bonds = self.angles = self.dihedrals = _NO_CONNECTIONS
+        self.distances = _SINGLE_FAR
+        return self
+
+    def bonds_for_update(self):
+        if not isinstance(self.bonds, set):
+            self.bonds = set(self.bonds)
+        return self.bonds
 
     def size(self):
         return self.end - self.start
@@ -350,7 +367,7 @@ class System:
         )
         first_id = len(self.bondings)
         self.molecule_ids = np.concatenate([self.molecule_ids, np.arange(first_id, first_id + count, dtype=np.int64)])
-        self.bondings += [Bonding(start + i, start + i + 1) for i in range(count)]
+        self.bondings += [Bonding.single(start + i) for i in range(count)]
         self._version += 1
 
     def molecules(self):
@@ -414,7 +431,7 @@ class System:
             for index, bonding in enumerate(self.bondings):
                 self.molecule_ids[bonding.start : bonding.end] = index
         bonding = self.bondings[int(self.molecule_ids[particle_i])]
-        bonding.bonds.add(_normalize_pair(particle_i, particle_j))
+        bonding.bonds_for_update().add(_normalize_pair(particle_i, particle_j))
         bonding.rebuild()
         self._version += 1
         return permutations
@@ -452,7 +469,7 @@ class System:
         self.bondings = [Bonding(int(s), int(e)) for s, e in zip(starts, ends)]
         self.molecule_ids = np.repeat(np.arange(len(starts), dtype=np.int64), ends - starts)
         for (i, j) in all_bonds:
-            self.bondings[int(self.molecule_ids[i])].bonds.add((i, j))
+            self.bondings[int(self.molecule_ids[i])].bonds_for_update().add((i, j))
         # molecules of the same shape share one rebuild
         cache = {}
         for bonding in self.bondings:
