@@ -100,3 +100,29 @@ def test_distances_with_and_without_a_cell():
     d = np.array([9.0, 0.0, 0.0])
     lib.orc_vector_image(oracle.dptr(cell), 0, oracle.dptr(d))
     assert np.linalg.norm(d) == 9.0
+
+
+def test_bulk_added_atoms_bond_like_molecules_added_one_by_one():
+    """`System.add_particles` makes one-atom molecules that share an immutable empty connection set (millions of free
+    atoms in the bench boxes); bonding them afterwards, one bond at a time or in bulk, gives the molecules of
+    `Configuration::add_bond` (configuration.rs:243-303)."""
+    import lumol_b200 as lumol
+
+    def fresh():
+        system = lumol.System(lumol.UnitCell.cubic(20.0))
+        system.add_particles(["O", "H", "H", "Ar"], np.arange(12.0).reshape(4, 3))
+        return system
+
+    system = fresh()
+    assert all(bonding.size() == 1 and not bonding.bonds for bonding in system.bondings)
+    system.add_bond(0, 1)
+    system.add_bond(0, 2)
+    bulk = fresh()
+    bulk.add_bonds([(0, 1), (0, 2)])
+    for built in (system, bulk):
+        water, argon = built.bondings
+        assert (water.start, water.end, argon.start, argon.end) == (0, 3, 3, 4)
+        assert sorted(water.bonds) == [(0, 1), (0, 2)] and sorted(water.angles) == [(1, 0, 2)] and not water.dihedrals
+        assert not argon.bonds and not argon.angles
+    # the shared empty set was not touched
+    assert not fresh().bondings[0].bonds
