@@ -127,6 +127,11 @@ class ClockSampler:
             )
         except OSError:
             self.process = None
+            return
+        # nvidia-smi needs a moment to attach to the driver: the timed pass starts once the first sample is on disk
+        deadline = time.perf_counter() + 5.0
+        while time.perf_counter() < deadline and os.path.getsize(self.file.name) == 0 and self.process.poll() is None:
+            time.sleep(0.02)
 
     def stop(self):
         if self.process is not None:
@@ -422,6 +427,9 @@ def measure(args, env, workload, lattice_text, steps, warmup, with_e2e, with_cpu
     _ffi.check(ctx, lib.lumol_cuda_reset_stats(ctx))
     window_ms, rebuilds_window, launches = timed_run(steps)
     long_steps = amortise_steps if amortise_steps else (args.amortise_steps or max(400, 10 * steps))
+    if not args.amortise_steps:
+        # at least ~2.5 s, so that the 20 ms clock samples of this pass are a population and not a handful
+        long_steps = min(max(long_steps, int(2500.0 / max(window_ms / max(steps, 1), 1e-3))), 20000)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
