@@ -34,6 +34,19 @@ impl DeviceSystem {
         DeviceSystem { ctx: Mutex::new(ctx), synced_version: u64::MAX, synced_cell: None }
     }
 
+    /// One context over several devices of this process (`lumol_cuda_create_multi`): same calls afterwards, the library
+    /// shards the system over the devices behind them.  `LUMOL_CUDA_DEVICES=0,1,2,3` in lumol's environment is the
+    /// intended switch (`System::device()` builds the context lazily on first use).
+    pub fn new_multi(devices: &[i32]) -> DeviceSystem {
+        let mut ctx = std::ptr::null_mut();
+        let status = unsafe { lumol_cuda_create_multi(devices.as_ptr(), devices.len() as i32, &mut ctx) };
+        if status < 0 {
+            let message = unsafe { CStr::from_ptr(lumol_cuda_last_error(std::ptr::null())) }.to_string_lossy().into_owned();
+            panic!("{}", message);
+        }
+        DeviceSystem { ctx: Mutex::new(ctx), synced_version: u64::MAX, synced_cell: None }
+    }
+
     /// Upload what changed since the last call (the flattening of lumol_b200/device.py, which the parity tests run):
     /// cell when it differs, positions always (the host arrays are the truth in host-driven mode), everything else
     /// when `System::structure_version()` moved -- a counter lumol-core bumps in `add_molecule`, `add_bond`,
