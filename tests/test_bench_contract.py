@@ -96,3 +96,26 @@ def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
     assert len(lines) == 1
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+
+
+def test_clock_sampler_waits_for_its_first_sample(tmp_path, monkeypatch):
+    """`clocks.samples` must not be zero for a short timed pass: the sampler returns from start() once nvidia-smi has
+    written its first line (a stand-in nvidia-smi that needs 0.3 s to attach is used here)."""
+    import stat
+    import time
+
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.3\nwhile true; do echo '0, 1965, 1965, 700.0, 0x0, Not Active, Not Active, Not Active, Active'; sleep 0.02; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    sys.path.insert(0, ROOT)
+    import bench
+
+    sampler = bench.ClockSampler(0)
+    begin = time.perf_counter()
+    sampler.start()
+    assert 0.25 < time.perf_counter() - begin < 3.0
+    time.sleep(0.2)
+    clocks = sampler.stop()
+    assert clocks["samples"] >= 5 and clocks["sm_mhz"] == 1965.0 and clocks["sm_max_mhz"] == 1965.0
+    assert clocks["reasons"] == ["sw_power_cap"]
